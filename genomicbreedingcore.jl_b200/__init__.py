@@ -1,0 +1,14 @@
+"""grm-b200: a B200-native (sm_100a) backend for the genomic relationship matrix path of GenomicBreedingCore.jl
+(src/grm/calc.jl: grmsimple, grmploidyaware, inflatediagonals!).
+
+The directory name contains a dot, so import it through the repo-root shim:  `import grm_b200`.
+"""
+from . import _lib, synth
+from ._lib import Context, GrmCudaError, default_context
+from .grm import grmploidyaware, grmsimple, inflatediagonals
+from .structs import GRM, ArgumentError, ErrorException, Genomes, MissingDataError, checkdims, clone
+
+__all__ = [
+    "Context", "GrmCudaError", "default_context", "grmsimple", "grmploidyaware", "inflatediagonals", "GRM", "Genomes",
+    "ArgumentError", "ErrorException", "MissingDataError", "checkdims", "clone", "synth",
+]

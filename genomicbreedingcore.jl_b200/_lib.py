@@ -1,0 +1,185 @@
+"""ctypes binding of libgrm_cuda.so — a 1:1 image of include/grm_cuda.h.
+
+This is the same binding a Julia `ccall` shim makes (julia/GRMCuda.jl); Python is used here because
+Julia is not available in the build image.  There is no CPU fallback: if the shared library is missing, or the
+machine has no sm_100 GPU, the compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgrm_cuda.so")
+
+OK = 0
+ERR_BAD_ARGUMENT = 1
+ERR_MISSING = 2
+ERR_NONFINITE = 3
+ERR_NOT_SYMMETRIC = 4
+ERR_NAN_MATRIX = 5
+ERR_INF_MATRIX = 6
+ERR_CUDA = 7
+ERR_OOM = 8
+ERR_NOT_DOSAGE = 9
+ERR_OVERFLOW = 10
+
+PATH_AUTO, PATH_I8, PATH_F64 = 0, 1, 2
+LOC_HOST, LOC_DEVICE = 0, 1
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("path", C.c_int32),
+        ("denominator", C.c_int32),
+        ("max_iter", C.c_int32),
+        ("skip_repair", C.c_int32),
+        ("input_location", C.c_int32),
+        ("output_location", C.c_int32),
+        ("rank", C.c_int32),
+        ("world", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("chunk_loci", C.c_int64),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("path", C.c_int32),
+        ("denominator", C.c_int32),
+        ("repair_iters", C.c_int32),
+        ("eps_total", C.c_double),
+        ("scale", C.c_double),
+        ("tiles", C.c_int64),
+        ("ms_h2d", C.c_float),
+        ("ms_pack", C.c_float),
+        ("ms_rowdot", C.c_float),
+        ("ms_syrk", C.c_float),
+        ("ms_finalize", C.c_float),
+        ("ms_repair", C.c_float),
+        ("ms_d2h", C.c_float),
+        ("ms_total", C.c_float),
+        ("kernel_launches", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if not name.startswith("reserved")}
+
+
+_vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+
+# name -> (restype, argtypes); every symbol include/grm_cuda.h declares
+SIGNATURES = {
+    "grm_cuda_version": (_i32, []),
+    "grm_cuda_last_error": (C.c_char_p, []),
+    "grm_cuda_status_string": (C.c_char_p, [_i32]),
+    "grm_cuda_options_default": (None, [C.POINTER(Options)]),
+    "grm_cuda_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "grm_cuda_ctx_destroy": (_i32, [_vp]),
+    "grm_cuda_ctx_stream": (_vp, [_vp]),
+    "grm_cuda_ctx_synchronize": (_i32, [_vp]),
+    "grm_cuda_simple": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
+    "grm_cuda_ploidyaware": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
+    "grm_cuda_inflate_diagonals": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
+    "grm_cuda_detect_denominator": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, C.POINTER(_i32)]),
+    "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
+    "grm_cuda_syrk_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32]),
+    "grm_cuda_syrk_i8_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
+    "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "grm_cuda_locus_stats_i8": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "grm_cuda_locus_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32]),
+    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _vp, _i64, _i32, _i32]),
+    "grm_cuda_scale_mirror": (_i32, [_vp, _vp, _i64, _i64, _f64]),
+    "grm_cuda_mirror": (_i32, [_vp, _vp, _i64, _i64]),
+    "grm_cuda_tile_edge": (_i32, []),
+    "grm_cuda_tile_count": (_i64, [_i64, _i32, _i32]),
+    "grm_cuda_tile_owner": (_i32, [_i64, _i64, _i64, _i32]),
+    "grm_cuda_tile_at": (_i32, [_i64, _i32, _i32, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+}
+
+
+class GrmCudaError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libgrm_cuda status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(nvcc, sm_100a).  There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        msg = load().grm_cuda_last_error().decode("utf-8", "replace")
+        raise GrmCudaError(status, msg)
+
+
+def default_options() -> Options:
+    o = Options()
+    load().grm_cuda_options_default(C.byref(o))
+    return o
+
+
+def new_info() -> Info:
+    i = Info()
+    i.struct_size = C.sizeof(Info)
+    return i
+
+
+class Context:
+    """Owns a grm_cuda_ctx (device, streams, grow-only workspaces)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        check(self.lib.grm_cuda_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.grm_cuda_ctx_stream(self.handle) or 0)
+
+    def synchronize(self) -> None:
+        check(self.lib.grm_cuda_ctx_synchronize(self.handle))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.grm_cuda_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

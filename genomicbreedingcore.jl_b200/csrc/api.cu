@@ -1,0 +1,553 @@
+// api.cu — context, error plumbing, tile partition and the three reference-facing entry points of libgrm_cuda
+// (grmsimple / grmploidyaware / inflatediagonals!, src/grm/calc.jl:115-142, :189-217, :41-70).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+
+#include "common.cuh"
+
+int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
+                          double *eps_total);
+extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom);
+extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                            double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate);
+extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                     int32_t centred, double ploidy, const double *d_q, int32_t accumulate, double *d_G,
+                                     int64_t ldg, int32_t rank, int32_t world);
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void grm_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *grm_cuda_last_error(void) { return g_err; }
+extern "C" int32_t grm_cuda_version(void) { return GRM_CUDA_VERSION; }
+
+extern "C" const char *grm_cuda_status_string(int32_t s) {
+    switch (s) {
+        case GRM_CUDA_OK: return "ok";
+        case GRM_CUDA_ERR_BAD_ARGUMENT: return "bad argument";
+        case GRM_CUDA_ERR_MISSING: return "allele_frequencies contains missing (NaN) values";
+        case GRM_CUDA_ERR_NONFINITE: return "allele_frequencies contains non-finite values";
+        case GRM_CUDA_ERR_NOT_SYMMETRIC: return "The input matrix is not symmetric.";
+        case GRM_CUDA_ERR_NAN_MATRIX: return "The input matrix contains NaN values.";
+        case GRM_CUDA_ERR_INF_MATRIX: return "The input matrix contains Inf values.";
+        case GRM_CUDA_ERR_CUDA: return "CUDA error";
+        case GRM_CUDA_ERR_OOM: return "out of memory";
+        case GRM_CUDA_ERR_NOT_DOSAGE: return "input is not dosage-quantised";
+        case GRM_CUDA_ERR_OVERFLOW: return "int32 accumulator overflow";
+        default: return "unknown status";
+    }
+}
+
+extern "C" void grm_cuda_options_default(grm_cuda_options *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->struct_size = static_cast<int32_t>(sizeof(*o));
+    o->path = GRM_CUDA_PATH_AUTO;
+    o->max_iter = 1000;  // calc.jl:41,115,189
+    o->world = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// buffers / context
+// ---------------------------------------------------------------------------------------------------------------
+int32_t DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap && ptr) return GRM_CUDA_OK;
+    if (ptr) {
+        cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    GRM_CUDA_TRY(cudaMalloc(&ptr, bytes));
+    cap = bytes;
+    return GRM_CUDA_OK;
+}
+void DevBuf::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) {
+    if (!out) {
+        grm_set_error("ctx_create: null output pointer");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        grm_set_error("no CUDA device available (%s); libgrm_cuda has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return GRM_CUDA_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        grm_set_error("ctx_create: device %d out of range [0,%d)", device, count);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GRM_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        grm_set_error("device %d is sm_%d%d; libgrm_cuda is built for sm_100a (B200) only", device, prop.major,
+                      prop.minor);
+        return GRM_CUDA_ERR_CUDA;
+    }
+    grm_cuda_ctx *ctx = new (std::nothrow) grm_cuda_ctx();
+    if (!ctx) return GRM_CUDA_ERR_OOM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    GRM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GRM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) GRM_CUDA_TRY(cudaEventCreate(&ev));
+    for (int i = 0; i < 2; ++i) {
+        GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+        GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming));
+    }
+    *out = ctx;
+    return GRM_CUDA_OK;
+}
+
+int32_t grm_cusolver_destroy(void *h);
+
+extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
+    if (!ctx) return GRM_CUDA_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->cusolver) grm_cusolver_destroy(ctx->cusolver);
+    DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
+                      &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->lu, &ctx->lu_work, &ctx->ipiv, &ctx->misc,
+                      &ctx->tiles_i8.buf, &ctx->tiles_f64.buf};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(ctx->copy_done[i]);
+        cudaEventDestroy(ctx->stage_free[i]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return GRM_CUDA_OK;
+}
+
+extern "C" void *grm_cuda_ctx_stream(grm_cuda_ctx *ctx) { return ctx ? ctx->stream : nullptr; }
+
+extern "C" int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx) {
+    if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GRM_CUDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile partition: 256 x 256 tiles of the upper triangle, enumerated in bands of 8 tile rows so that tiles that are
+// in flight together (and the contiguous range a rank owns) share few operand panels -> L2 reuse of the codes.
+// ---------------------------------------------------------------------------------------------------------------
+void grm_tile_order(int64_t n, std::vector<int2> &tiles) {
+    const int T = static_cast<int>((n + GRM_TILE - 1) / GRM_TILE);
+    constexpr int BAND = 8;
+    tiles.clear();
+    tiles.reserve(static_cast<size_t>(T) * (T + 1) / 2);
+    for (int r0 = 0; r0 < T; r0 += BAND) {
+        const int r1 = std::min(T, r0 + BAND);
+        for (int tj = r0; tj < T; ++tj)
+            for (int ti = r0; ti < std::min(r1, tj + 1); ++ti) tiles.push_back(make_int2(ti, tj));
+    }
+}
+
+void grm_tile_range(int64_t total, int32_t rank, int32_t world, int64_t *begin, int64_t *end) {
+    *begin = total * rank / world;
+    *end = total * (rank + 1) / world;
+}
+
+extern "C" int32_t grm_cuda_tile_edge(void) { return GRM_TILE; }
+
+extern "C" int64_t grm_cuda_tile_count(int64_t n, int32_t rank, int32_t world) {
+    if (n < 1 || world < 1 || rank < 0 || rank >= world) return -1;
+    const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
+    int64_t b, e;
+    grm_tile_range(T * (T + 1) / 2, rank, world, &b, &e);
+    return e - b;
+}
+
+extern "C" int32_t grm_cuda_tile_owner(int64_t n, int64_t ti, int64_t tj, int32_t world) {
+    if (n < 1 || world < 1 || ti < 0 || tj < ti) return -1;
+    std::vector<int2> order;
+    grm_tile_order(n, order);
+    const int64_t total = static_cast<int64_t>(order.size());
+    for (int64_t t = 0; t < total; ++t)
+        if (order[t].x == ti && order[t].y == tj) {
+            for (int32_t r = 0; r < world; ++r) {
+                int64_t b, e;
+                grm_tile_range(total, r, world, &b, &e);
+                if (t >= b && t < e) return r;
+            }
+        }
+    return -1;
+}
+
+// position t of the rank's tile list -> (ti, tj); lets a host build gather plans without a device
+extern "C" int32_t grm_cuda_tile_at(int64_t n, int32_t rank, int32_t world, int64_t t, int64_t *ti, int64_t *tj) {
+    if (n < 1 || world < 1 || rank < 0 || rank >= world || !ti || !tj) return GRM_CUDA_ERR_BAD_ARGUMENT;
+    std::vector<int2> order;
+    grm_tile_order(n, order);
+    int64_t b, e;
+    grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
+    if (t < 0 || b + t >= e) return GRM_CUDA_ERR_BAD_ARGUMENT;
+    *ti = order[b + t].x;
+    *tj = order[b + t].y;
+    return GRM_CUDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host <-> device streaming of loci chunks (a chunk = a contiguous column range = contiguous memory in Julia's
+// column-major layout).  Two staging buffers; copies run on copy_stream and overlap the pack / SYRK of the
+// previous chunk on the compute stream.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ChunkFeeder {
+    grm_cuda_ctx *ctx;
+    const double *A;
+    int64_t n, p, lda;
+    bool host;
+    int64_t chunk;
+    int64_t nchunks;
+    int issued = 0;  // host chunks whose copy has been enqueued
+
+    int32_t init(grm_cuda_ctx *c, const double *A_, int64_t n_, int64_t p_, int64_t lda_, bool host_, int64_t want) {
+        ctx = c;
+        A = A_;
+        n = n_;
+        p = p_;
+        lda = lda_;
+        host = host_;
+        if (!host) {
+            chunk = p;
+            nchunks = 1;
+            return GRM_CUDA_OK;
+        }
+        int64_t ch = want;
+        if (ch <= 0) ch = std::max<int64_t>(128, ((256ll << 20) / (n * 8)) / 128 * 128);
+        ch = std::max<int64_t>(128, ch / 128 * 128);
+        chunk = std::min(ch, (p + 127) / 128 * 128);
+        nchunks = (p + chunk - 1) / chunk;
+        const size_t bytes = static_cast<size_t>(n) * static_cast<size_t>(std::min(chunk, p)) * sizeof(double);
+        GRM_TRY(ctx->stage[0].reserve(bytes));
+        if (nchunks > 1) GRM_TRY(ctx->stage[1].reserve(bytes));
+        return GRM_CUDA_OK;
+    }
+    int64_t k0(int64_t c) const { return c * chunk; }
+    int64_t len(int64_t c) const { return std::min(chunk, p - c * chunk); }
+    int64_t ld_dev() const { return host ? n : lda; }
+
+    int32_t enqueue_copy(int64_t c) {
+        const int b = static_cast<int>(c & 1);
+        if (c >= 2) GRM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+        const double *src = A + k0(c) * lda;
+        double *dst = ctx->stage[b].as<double>();
+        if (lda == n)
+            GRM_CUDA_TRY(cudaMemcpyAsync(dst, src, static_cast<size_t>(n) * len(c) * sizeof(double),
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+        else
+            GRM_CUDA_TRY(cudaMemcpy2DAsync(dst, n * sizeof(double), src, lda * sizeof(double), n * sizeof(double),
+                                           static_cast<size_t>(len(c)), cudaMemcpyHostToDevice, ctx->copy_stream));
+        GRM_CUDA_TRY(cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
+        return GRM_CUDA_OK;
+    }
+    // device pointer of chunk c, valid on the compute stream; prefetches chunk c+1
+    int32_t acquire(int64_t c, const double **d) {
+        if (!host) {
+            *d = A;
+            return GRM_CUDA_OK;
+        }
+        while (issued <= c + 1 && issued < nchunks) {
+            GRM_TRY(enqueue_copy(issued));
+            ++issued;
+        }
+        const int b = static_cast<int>(c & 1);
+        GRM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[b], 0));
+        *d = ctx->stage[b].as<double>();
+        return GRM_CUDA_OK;
+    }
+    int32_t release(int64_t c) {
+        if (!host) return GRM_CUDA_OK;
+        GRM_CUDA_TRY(cudaEventRecord(ctx->stage_free[c & 1], ctx->stream));
+        return GRM_CUDA_OK;
+    }
+};
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    float ms() const {
+        return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+
+int32_t flags_to_status(uint32_t f) {
+    if (f & 1u) {
+        grm_set_error("allele_frequencies contains missing (NaN) values; the reference GRM functions throw on missing data "
+                      "(src/grm/calc.jl:127,205) — filter or impute first");
+        return GRM_CUDA_ERR_MISSING;
+    }
+    if (f & 2u) {
+        grm_set_error("allele_frequencies contains +-Inf");
+        return GRM_CUDA_ERR_NONFINITE;
+    }
+    return GRM_CUDA_OK;
+}
+
+int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda, bool centred, int32_t ploidy,
+                double *G, int64_t ldg, const grm_cuda_options *uopts, grm_cuda_info *info) {
+    Timer wall;
+    grm_cuda_options o;
+    grm_cuda_options_default(&o);
+    if (uopts) memcpy(&o, uopts, std::min<size_t>(sizeof(o), static_cast<size_t>(std::max(uopts->struct_size, 0))));
+    if (!ctx || !A || !G || n < 1 || p < 1 || lda < n || ldg < n || o.world < 1 || o.rank < 0 || o.rank >= o.world ||
+        o.max_iter < 0) {
+        grm_set_error("bad argument (n=%lld p=%lld lda=%lld ldg=%lld rank=%d world=%d)", (long long)n, (long long)p,
+                      (long long)lda, (long long)ldg, o.rank, o.world);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    if (n > INT32_MAX - 512 || p > INT32_MAX - 512) {
+        grm_set_error("n and p must fit TMA's 32-bit coordinates");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    const bool in_host = o.input_location == GRM_CUDA_LOC_HOST;
+    const bool out_host = o.output_location == GRM_CUDA_LOC_HOST;
+    const bool sharded = o.world > 1;
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t *ev = ctx->ev;
+
+    grm_cuda_info inf;
+    memset(&inf, 0, sizeof(inf));
+    inf.struct_size = static_cast<int32_t>(sizeof(inf));
+
+    // output buffer on the device
+    double *dG = G;
+    int64_t ldG = ldg;
+    if (out_host) {
+        GRM_TRY(ctx->G.reserve(static_cast<size_t>(n) * n * sizeof(double)));
+        dG = ctx->G.as<double>();
+        ldG = n;
+        if (sharded) GRM_CUDA_TRY(cudaMemsetAsync(dG, 0, static_cast<size_t>(n) * n * sizeof(double), st));
+    }
+
+    ChunkFeeder feed;
+    GRM_TRY(feed.init(ctx, A, n, p, lda, in_host, o.chunk_loci));
+
+    GRM_TRY(ctx->flags.reserve(64));
+    uint32_t *d_flags = ctx->flags.as<uint32_t>();
+    GRM_CUDA_TRY(cudaMemsetAsync(d_flags, 0, 16 * sizeof(uint32_t), st));
+    GRM_TRY(ctx->stats.reserve(8 * sizeof(double)));
+    double *d_stats = ctx->stats.as<double>();
+
+    GRM_CUDA_TRY(cudaEventRecord(ev[0], st));
+
+    // ---- path decision: dosage denominator "detected on load" (first chunk), unless given ---------------------
+    int32_t m = 0;
+    int path = o.path;
+    if (path != GRM_CUDA_PATH_F64) {
+        m = o.denominator;
+        if (m == 0) {
+            const double *d0;
+            GRM_TRY(feed.acquire(0, &d0));
+            GRM_TRY(grm_cuda_detect_denominator(ctx, d0, n, feed.len(0), feed.ld_dev(), 0, &m));
+        } else if (m < 1 || m > 64 || (m & (m - 1)) != 0) {
+            grm_set_error("denominator must be a power of two in [1,64], got %d", m);
+            return GRM_CUDA_ERR_BAD_ARGUMENT;
+        }
+        if (m == 0) {
+            if (path == GRM_CUDA_PATH_I8) {
+                grm_set_error("int8 path requested but the allele frequencies are not multiples of 1/m, m = 2^k <= 64");
+                return GRM_CUDA_ERR_NOT_DOSAGE;
+            }
+            path = GRM_CUDA_PATH_F64;
+        } else {
+            path = GRM_CUDA_PATH_I8;
+        }
+    }
+
+    double denom = 0.0;
+    bool done = false;
+    while (!done) {
+        if (path == GRM_CUDA_PATH_I8) {
+            if (static_cast<double>(m) * m * static_cast<double>(p) >= 2147483648.0) {
+                grm_set_error("m^2 * p = %d^2 * %lld overflows the int32 accumulators", m, (long long)p);
+                return GRM_CUDA_ERR_OVERFLOW;
+            }
+            const int64_t ldc = (p + 127) / 128 * 128;
+            GRM_TRY(ctx->codes.reserve(static_cast<size_t>(n) * ldc));
+            GRM_TRY(ctx->colsum.reserve(static_cast<size_t>(ldc) * sizeof(int32_t)));
+            int8_t *d_codes = ctx->codes.as<int8_t>();
+            int32_t *d_colsum = ctx->colsum.as<int32_t>();
+            GRM_CUDA_TRY(cudaMemsetAsync(d_colsum, 0, static_cast<size_t>(ldc) * sizeof(int32_t), st));
+            for (int64_t c = 0; c < feed.nchunks; ++c) {
+                const double *dc;
+                GRM_TRY(feed.acquire(c, &dc));
+                GRM_TRY(grm_cuda_pack_dosage(ctx, dc, n, feed.len(c), feed.ld_dev(), m, d_codes + feed.k0(c), ldc,
+                                             d_colsum + feed.k0(c), d_flags));
+                GRM_TRY(feed.release(c));
+            }
+            GRM_CUDA_TRY(cudaEventRecord(ev[1], st));
+            uint32_t h_flags = 0;
+            GRM_CUDA_TRY(cudaMemcpyAsync(&h_flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            GRM_CUDA_TRY(cudaStreamSynchronize(st));
+            GRM_TRY(flags_to_status(h_flags));
+            if (h_flags & 4u) {
+                // a later chunk broke the denominator guessed from the first one
+                if (o.path == GRM_CUDA_PATH_I8 || o.denominator != 0) {
+                    grm_set_error("allele frequencies are not all multiples of 1/%d", m);
+                    return GRM_CUDA_ERR_NOT_DOSAGE;
+                }
+                if (m < 64) {
+                    m = 64;  // retry once with the finest supported grid, then give up on int8
+                } else {
+                    path = GRM_CUDA_PATH_F64;
+                }
+                GRM_CUDA_TRY(cudaMemsetAsync(d_flags, 0, 16 * sizeof(uint32_t), st));
+                feed.issued = 0;
+                continue;
+            }
+            if (!centred) {
+                denom = static_cast<double>(p);  // calc.jl:127
+                GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
+                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1.0 / (static_cast<double>(m) * m), 0.0, 0.0,
+                                             denom, nullptr, dG, ldG, o.rank, o.world));
+            } else {
+                GRM_TRY(ctx->q.reserve(static_cast<size_t>(ldc) * sizeof(double)));
+                GRM_TRY(ctx->w.reserve(static_cast<size_t>(ldc) * sizeof(double)));
+                GRM_TRY(ctx->u.reserve(static_cast<size_t>(n) * sizeof(double)));
+                GRM_TRY(grm_cuda_locus_stats_i8(ctx, d_colsum, p, n, m, ploidy, ctx->q.as<double>(),
+                                                ctx->w.as<double>(), d_stats));
+                GRM_TRY(grm_cuda_rowdot_i8(ctx, d_codes, n, p, ldc, ctx->w.as<double>(), ctx->u.as<double>()));
+                double h_stats[3];
+                GRM_CUDA_TRY(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+                GRM_CUDA_TRY(cudaStreamSynchronize(st));
+                denom = static_cast<double>(ploidy) * h_stats[0];  // calc.jl:201
+                const double s = static_cast<double>(ploidy) / static_cast<double>(m);
+                GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
+                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, s * s, s, h_stats[1], denom, ctx->u.as<double>(),
+                                             dG, ldG, o.rank, o.world));
+            }
+            GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
+            if (!sharded) GRM_TRY(grm_cuda_scale_mirror(ctx, dG, n, ldG, 1.0));
+            done = true;
+        } else {
+            // ---- FP64 path: per chunk, column means (+ validity) then accumulate Z_c * Z_c' into G ------------
+            GRM_TRY(ctx->q.reserve(static_cast<size_t>(p) * sizeof(double)));
+            float syrk_ms = 0.f;
+            (void)syrk_ms;
+            for (int64_t c = 0; c < feed.nchunks; ++c) {
+                const double *dc;
+                GRM_TRY(feed.acquire(c, &dc));
+                GRM_TRY(grm_cuda_locus_stats_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), ctx->q.as<double>() + feed.k0(c),
+                                                 d_stats, d_flags, c > 0));
+                GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), centred ? 1 : 0,
+                                          static_cast<double>(ploidy), ctx->q.as<double>() + feed.k0(c), c > 0, dG, ldG,
+                                          o.rank, o.world));
+                GRM_TRY(feed.release(c));
+            }
+            GRM_CUDA_TRY(cudaEventRecord(ev[1], st));
+            GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
+            uint32_t h_flags = 0;
+            double h_stats[3];
+            GRM_CUDA_TRY(cudaMemcpyAsync(&h_flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            GRM_CUDA_TRY(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+            GRM_CUDA_TRY(cudaStreamSynchronize(st));
+            GRM_TRY(flags_to_status(h_flags));
+            denom = centred ? static_cast<double>(ploidy) * h_stats[0] : static_cast<double>(p);
+            GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
+            if (!sharded) GRM_TRY(grm_cuda_scale_mirror(ctx, dG, n, ldG, denom));
+            // sharded FP64 calls return raw sums scaled by the caller (it owns the exchange of d)
+            done = true;
+        }
+    }
+    GRM_CUDA_TRY(cudaEventRecord(ev[4], st));
+
+    // ---- inflatediagonals! (calc.jl:133 / :211) -----------------------------------------------------------------
+    if (!o.skip_repair && !sharded) {
+        GRM_TRY(grm_repair_device(ctx, dG, n, ldG, o.max_iter, &inf.repair_iters, &inf.eps_total));
+    }
+    GRM_CUDA_TRY(cudaEventRecord(ev[5], st));
+    if (out_host) {
+        if (ldg == n)
+            GRM_CUDA_TRY(cudaMemcpyAsync(G, dG, static_cast<size_t>(n) * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else
+            GRM_CUDA_TRY(cudaMemcpy2DAsync(G, ldg * sizeof(double), dG, n * sizeof(double), n * sizeof(double),
+                                           static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+    }
+    GRM_CUDA_TRY(cudaEventRecord(ev[6], st));
+    GRM_CUDA_TRY(cudaStreamSynchronize(st));
+
+    inf.path = path;
+    inf.denominator = path == GRM_CUDA_PATH_I8 ? m : 0;
+    inf.scale = denom;
+    inf.tiles = grm_cuda_tile_count(n, o.rank, o.world);
+    cudaEventElapsedTime(&inf.ms_pack, ev[0], ev[1]);
+    cudaEventElapsedTime(&inf.ms_rowdot, ev[1], ev[2]);
+    cudaEventElapsedTime(&inf.ms_syrk, ev[2], ev[3]);
+    cudaEventElapsedTime(&inf.ms_finalize, ev[3], ev[4]);
+    cudaEventElapsedTime(&inf.ms_repair, ev[4], ev[5]);
+    cudaEventElapsedTime(&inf.ms_d2h, ev[5], ev[6]);
+    inf.ms_h2d = in_host ? inf.ms_pack : 0.f;  // host input: the ingest stage is the H2D stream with the pack hidden under it
+    inf.ms_total = wall.ms();
+    inf.kernel_launches = ctx->launches;
+    if (info) memcpy(info, &inf, std::min<size_t>(sizeof(inf), static_cast<size_t>(std::max(info->struct_size, 0))));
+    return GRM_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t grm_cuda_simple(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda, double *G,
+                                   int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info) {
+    return run_grm(ctx, A, n, p, lda, false, 0, G, ldg, opts, info);
+}
+
+extern "C" int32_t grm_cuda_ploidyaware(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
+                                        int32_t ploidy, double *G, int64_t ldg, const grm_cuda_options *opts,
+                                        grm_cuda_info *info) {
+    return run_grm(ctx, A, n, p, lda, true, ploidy, G, ldg, opts, info);
+}
+
+extern "C" int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
+                                              int32_t location, int32_t *iters, double *eps_total) {
+    if (!ctx || !X || n < 1 || ldx < n || max_iter < 0) {
+        grm_set_error("inflate_diagonals: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    int32_t it = 0;
+    double tot = 0.0;
+    int32_t status;
+    if (location == GRM_CUDA_LOC_DEVICE) {
+        status = grm_repair_device(ctx, X, n, ldx, max_iter, &it, &tot);
+    } else {
+        GRM_TRY(ctx->G.reserve(static_cast<size_t>(n) * n * sizeof(double)));
+        double *d = ctx->G.as<double>();
+        GRM_CUDA_TRY(cudaMemcpy2DAsync(d, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double),
+                                       static_cast<size_t>(n), cudaMemcpyHostToDevice, ctx->stream));
+        status = grm_repair_device(ctx, d, n, n, max_iter, &it, &tot);
+        if (status == GRM_CUDA_OK && it > 0) {
+            GRM_CUDA_TRY(cudaMemcpy2DAsync(X, ldx * sizeof(double), d, n * sizeof(double), n * sizeof(double),
+                                           static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (iters) *iters = it;
+    if (eps_total) *eps_total = tot;
+    return status;
+}

@@ -1,0 +1,192 @@
+// common.cuh — shared declarations of libgrm_cuda (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/grm_cuda.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing: no exception crosses the C ABI; every internal failure becomes a status + thread-local text
+// ---------------------------------------------------------------------------------------------------------
+void grm_set_error(const char *fmt, ...);
+
+#define GRM_CUDA_TRY(expr)                                                                           \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            grm_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? GRM_CUDA_ERR_OOM : GRM_CUDA_ERR_CUDA;         \
+        }                                                                                            \
+    } while (0)
+
+#define GRM_TRY(expr)                        \
+    do {                                     \
+        int32_t _s = (expr);                 \
+        if (_s != GRM_CUDA_OK) return _s;    \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int32_t reserve(size_t bytes);
+    void release();
+    template <class T> T *as() { return reinterpret_cast<T *>(ptr); }
+};
+
+struct TileListCache {
+    int64_t n = -1;
+    int32_t rank = -1, world = -1, kind = -1;
+    int32_t count = 0;
+    DevBuf buf;
+};
+
+struct grm_cuda_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;   // compute
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    cudaEvent_t copy_done[2] = {}, stage_free[2] = {};
+    void *cusolver = nullptr;  // cusolverDnHandle_t
+    // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc;
+    TileListCache tiles_i8, tiles_f64;
+    int32_t launches = 0;  // kernels launched since last reset
+};
+
+// tile partition (tiles.cpp part of api.cu)
+constexpr int GRM_TILE = 256;  // edge, in entries, of the unit of multi-GPU sharding
+void grm_tile_order(int64_t n, std::vector<int2> &tiles);  // all upper-triangular (ti<=tj) tiles, L2-friendly order
+void grm_tile_range(int64_t total, int32_t rank, int32_t world, int64_t *begin, int64_t *end);
+
+// kernels' host launchers (implemented across the .cu files)
+int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,
+                          uint32_t *d_out /* [0]=OR of code64, [1]=flags */);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers (mbarrier, TMA, tcgen05).  sm_100a only.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    // bounded spin: a protocol bug traps (error 719) instead of hanging the GPU.  2^26 polls is seconds, orders of
+    // magnitude beyond any legitimate wait in these kernels.
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// 2D tiled load global -> shared, completion on an mbarrier (bytes)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, uint64_t *bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// ---- tcgen05 ----
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <uint32_t NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive 32-bit columns: thread t gets lane (base_lane + t), columns [c, c+32)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand tile, 128-byte swizzle, rows of 128 bytes, 8-row groups
+// 1024 bytes apart (the layout a SWIZZLE_128B TMA box {128 B, rows} lands in).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address        [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                      // leading byte offset   [16,30) (unused for SW128 K-major)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset    [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                      // descriptor version 1 (sm_100)
+    d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::i8: S8 x S8 -> S32, both operands K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4)                                  // D format S32
+           | (1u << 7)                                // A format: signed 8-bit
+           | (1u << 10)                               // B format: signed 8-bit
+           | (static_cast<uint32_t>(N >> 3) << 17)    // N
+           | (static_cast<uint32_t>(M >> 4) << 24);   // M
+}
+#endif  // __CUDACC__

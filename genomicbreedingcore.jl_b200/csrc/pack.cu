@@ -1,0 +1,390 @@
+// pack.cu — the HBM-bound pass over genomes.allele_frequencies (n x p FP64, column-major) and the small
+// per-locus / per-entry vector kernels around it.
+//
+//   detect_kernel        dosage denominator detection ("detected on load")
+//   pack_dosage_kernel   per-locus integer column sums + validity flags + FP64 -> int8 quantise + transpose to the
+//                        K-major layout the tcgen05 SYRK consumes, one coalesced pass (replaces mean(A, dims=1),
+//                        calc.jl:197, and the implicit "any missing => throw", calc.jl:127)
+//   locus_stats_*        q_k, w_k = ploidy/2 + q_k, sum q(1-q) (calc.jl:197,201), fixed-order reductions
+//   rowdot_i8_kernel     u_i = sum_k c_ik w_k for the rank-1 centring correction
+#include "common.cuh"
+
+namespace {
+
+constexpr uint32_t FLAG_NAN = 1u, FLAG_INF = 2u, FLAG_NOT_DOSAGE = 4u;
+
+// -------------------------------------------------------------------------------------------------------------
+// detection: OR of round(64*x) over the sampled cells; any cell that is not k/64 in [0,1] raises a flag.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void detect_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, int64_t cells,
+                              uint32_t *__restrict__ out) {
+    uint32_t bits = 0, flags = 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < cells; idx += stride) {
+        const int64_t k = idx / n, i = idx - k * n;
+        if (k >= p) break;
+        const double x = A[i + k * lda];
+        const double t = x * 64.0;
+        const int c = __double2int_rn(t);
+        if (static_cast<double>(c) == t && c >= 0 && c <= 64) {
+            bits |= static_cast<uint32_t>(c);
+        } else {
+            flags |= (x != x) ? FLAG_NAN : (isinf(x) ? FLAG_INF : FLAG_NOT_DOSAGE);
+        }
+    }
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if ((threadIdx.x & 31) == 0) {
+        if (bits) atomicOr(&out[0], bits);
+        if (flags) atomicOr(&out[1], flags);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// pack: block = 8 warps, tile = 128 loci x (64*EITERS) entries.
+//   read : warp w owns loci [16w, 16w+16) of the tile; lane l reads entries l and l+32 of each 64-entry slab
+//          (two fully coalesced 256-byte warp loads per locus), 4 loci at a time -> one packed 32-bit word
+//   smem : word tile [64 entries][32 words + 1 pad]  (conflict-free both ways)
+//   write: 8 threads x 16 bytes = one 128-byte line per entry row of the K-major code matrix
+// -------------------------------------------------------------------------------------------------------------
+constexpr int PK_LOCI = 128;
+constexpr int PK_SLAB = 64;
+
+template <int EITERS>
+__global__ void __launch_bounds__(256) pack_dosage_kernel(const double *__restrict__ A, int64_t n, int64_t pc,
+                                                          int64_t lda, int m, int8_t *__restrict__ codes, int64_t ldc,
+                                                          int32_t *__restrict__ colsum, uint32_t *__restrict__ flags) {
+    __shared__ uint32_t tile[PK_SLAB][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t k0 = static_cast<int64_t>(blockIdx.x) * PK_LOCI;
+    const int64_t e_base = static_cast<int64_t>(blockIdx.y) * (PK_SLAB * EITERS);
+    const double mf = static_cast<double>(m);
+
+    int32_t acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0;
+    uint32_t bad = 0;
+
+#pragma unroll 1
+    for (int it = 0; it < EITERS; ++it) {
+        const int64_t e0 = e_base + static_cast<int64_t>(it) * PK_SLAB;
+        if (e0 >= n) break;
+        const int64_t ea = e0 + lane, eb = e0 + lane + 32;
+        const bool va = ea < n, vb = eb < n;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            double xa[4], xb[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int64_t k = k0 + warp * 16 + g * 4 + kk;
+                const bool vk = k < pc;
+                xa[kk] = (vk && va) ? __ldg(A + ea + k * lda) : 0.0;
+                xb[kk] = (vk && vb) ? __ldg(A + eb + k * lda) : 0.0;
+            }
+            uint32_t wa = 0, wb = 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const double ta = xa[kk] * mf, tb = xb[kk] * mf;
+                int ca = __double2int_rn(ta), cb = __double2int_rn(tb);
+                if (!(static_cast<double>(ca) == ta && ca >= 0 && ca <= m)) {
+                    bad |= (xa[kk] != xa[kk]) ? FLAG_NAN : (isinf(xa[kk]) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    ca = 0;
+                }
+                if (!(static_cast<double>(cb) == tb && cb >= 0 && cb <= m)) {
+                    bad |= (xb[kk] != xb[kk]) ? FLAG_NAN : (isinf(xb[kk]) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    cb = 0;
+                }
+                wa |= static_cast<uint32_t>(ca) << (8 * kk);
+                wb |= static_cast<uint32_t>(cb) << (8 * kk);
+                acc[g * 4 + kk] += ca + cb;
+            }
+            tile[lane][warp * 4 + g] = wa;
+            tile[lane + 32][warp * 4 + g] = wb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int r = pass * 32 + (threadIdx.x >> 3);
+            const int c = (threadIdx.x & 7) * 4;
+            const int64_t e = e0 + r;
+            if (e < n) {
+                uint4 v = make_uint4(tile[r][c], tile[r][c + 1], tile[r][c + 2], tile[r][c + 3]);
+                *reinterpret_cast<uint4 *>(codes + e * ldc + k0 + c * 4) = v;
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int32_t s = __reduce_add_sync(0xffffffffu, acc[i]);
+        const int64_t k = k0 + warp * 16 + i;
+        if (lane == 0 && k < pc && s != 0) atomicAdd(&colsum[k], s);
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) atomicOr(flags, bad);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// fixed-order block reduction of up to 3 doubles per thread (bit-reproducible for a fixed launch shape)
+// -------------------------------------------------------------------------------------------------------------
+constexpr int RED_BLOCKS = 256;
+constexpr int RED_THREADS = 256;
+
+template <int NV> __device__ __forceinline__ void block_reduce(double (&v)[NV], double *out /* NV doubles */) {
+    __shared__ double sh[NV][RED_THREADS / 32];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[i][warp] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+            for (int w = 0; w < RED_THREADS / 32; ++w) s += sh[i][w];
+            out[i] = s;
+        }
+    }
+}
+
+// q, w and per-block partials {sum q(1-q), sum w^2, sum q}; block b owns a contiguous range of loci.
+__global__ void __launch_bounds__(RED_THREADS)
+locus_stats_i8_kernel(const int32_t *__restrict__ colsum, int64_t p, double n, double m, double half_ploidy,
+                      double *__restrict__ q, double *__restrict__ w, double *__restrict__ partials) {
+    const int64_t per = (p + gridDim.x - 1) / gridDim.x;
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * per, e = min(p, b + per);
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) {
+        const double qk = (static_cast<double>(colsum[k]) / m) / n;  // fl(S_k / n), S_k = colsum/m exact (calc.jl:197)
+        const double wk = half_ploidy + qk;
+        q[k] = qk;
+        w[k] = wk;
+        v[0] += qk * (1.0 - qk);                                     // calc.jl:201
+        v[1] += wk * wk;
+        v[2] += qk;
+    }
+    block_reduce<3>(v, partials + 3 * blockIdx.x);
+}
+
+// one warp per locus column, lanes stride over entries with a fixed shuffle tree: bit-reproducible column means
+__global__ void __launch_bounds__(256)
+colmean_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, double *__restrict__ q,
+                   uint32_t *__restrict__ flags) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+    if (k >= p) return;
+    const double *col = A + k * lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    uint32_t bad = 0;
+    int64_t i = lane;
+    for (; i + 96 < n; i += 128) {
+        const double a = __ldg(col + i), b = __ldg(col + i + 32), c = __ldg(col + i + 64), d = __ldg(col + i + 96);
+        s0 += a;
+        s1 += b;
+        s2 += c;
+        s3 += d;
+    }
+    for (; i < n; i += 32) s0 += __ldg(col + i);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (s != s) bad |= FLAG_NAN;  // NaN anywhere (or Inf-Inf) poisons the column sum
+        else if (isinf(s)) bad |= FLAG_INF;
+        q[k] = s / static_cast<double>(n);
+        if (bad) atomicOr(flags, bad);
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+locus_stats_f64_kernel(const double *__restrict__ q, int64_t p, double *__restrict__ partials) {
+    const int64_t per = (p + gridDim.x - 1) / gridDim.x;
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * per, e = min(p, b + per);
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) {
+        const double qk = q[k];
+        v[0] += qk * (1.0 - qk);
+        v[2] += qk;
+    }
+    block_reduce<3>(v, partials + 3 * blockIdx.x);
+}
+
+// stats[j] (+)= sum_b partials[b][j] in block order
+__global__ void final_stats_kernel(const double *__restrict__ partials, int blocks, double *__restrict__ stats,
+                                   int accumulate) {
+    if (threadIdx.x < 3) {
+        double s = accumulate ? stats[threadIdx.x] : 0.0;
+        for (int b = 0; b < blocks; ++b) s += partials[3 * b + threadIdx.x];
+        stats[threadIdx.x] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// u_i = sum_k c_ik w_k : block = 256 threads x 8 entry rows; thread t owns 16-locus groups t, t+256, ...
+// (w is read once per 8 rows; codes once).  Per-thread sequential FMA chain + fixed tree => reproducible.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int RD_ROWS = 8;
+
+__global__ void __launch_bounds__(256)
+rowdot_i8_kernel(const int8_t *__restrict__ codes, int64_t n, int64_t p, int64_t ldc, const double *__restrict__ w,
+                 double *__restrict__ u) {
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * RD_ROWS;
+    double acc[RD_ROWS];
+#pragma unroll
+    for (int r = 0; r < RD_ROWS; ++r) acc[r] = 0.0;
+    const int64_t groups = (p + 15) / 16;
+    for (int64_t g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int64_t k = g * 16;
+        double wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) wv[j] = (k + j < p) ? __ldg(w + k + j) : 0.0;
+#pragma unroll
+        for (int r = 0; r < RD_ROWS; ++r) {
+            const int64_t row = r0 + r;
+            if (row < n) {
+                // ldc is a multiple of 128 and the padding columns are zero, so the 16-byte read is in bounds
+                const uint4 cv = __ldg(reinterpret_cast<const uint4 *>(codes + row * ldc + k));
+                const uint32_t words[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = static_cast<int8_t>((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
+                    acc[r] = fma(static_cast<double>(c), wv[j], acc[r]);
+                }
+            }
+        }
+    }
+    __shared__ double sh[RD_ROWS][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int r = 0; r < RD_ROWS; ++r) {
+        double v = acc[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[r][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < RD_ROWS && r0 + threadIdx.x < n) {
+        double s = 0.0;
+        for (int wi = 0; wi < 8; ++wi) s += sh[threadIdx.x][wi];
+        u[r0 + threadIdx.x] = s;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// host launchers / C ABI
+// ---------------------------------------------------------------------------------------------------------------
+int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,
+                          uint32_t *d_out) {
+    int64_t cells = n * p;
+    if (max_cells > 0 && max_cells < cells) cells = max_cells;
+    GRM_CUDA_TRY(cudaMemsetAsync(d_out, 0, 2 * sizeof(uint32_t), ctx->stream));
+    const int blocks = static_cast<int>(std::min<int64_t>((cells + 255) / 256, static_cast<int64_t>(ctx->num_sms) * 16));
+    detect_kernel<<<blocks, 256, 0, ctx->stream>>>(dA, n, p, lda, cells, d_out);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                               int64_t max_cells, int32_t *m_out) {
+    if (!ctx || !dA || !m_out || n < 1 || p < 1 || lda < n) {
+        grm_set_error("detect_denominator: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_TRY(ctx->misc.reserve(64));
+    uint32_t *d_out = ctx->misc.as<uint32_t>();
+    GRM_TRY(grm_launch_detect(ctx, dA, n, p, lda, max_cells, d_out));
+    uint32_t h[2];
+    GRM_CUDA_TRY(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h[1] != 0) {
+        *m_out = 0;  // continuous (or missing / non-finite: the caller's full pass reports which)
+        return GRM_CUDA_OK;
+    }
+    // every code64 is a multiple of 2^tz  =>  x = (code64 >> tz) / (64 >> tz)
+    int tz = 6;
+    if (h[0] != 0) {
+        tz = 0;
+        while (((h[0] >> tz) & 1u) == 0) ++tz;
+    }
+    *m_out = 64 >> tz;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
+                                        int32_t m, int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags) {
+    if (!ctx || !dA || !d_codes || !d_colsum || !d_flags || n < 1 || pc < 1 || lda < n || m < 1 || m > 64 ||
+        (m & (m - 1)) != 0 || (ldc % 128) != 0 || ldc < ((pc + 127) / 128) * 128) {
+        grm_set_error("pack_dosage: bad argument (n=%lld pc=%lld lda=%lld m=%d ldc=%lld)", (long long)n, (long long)pc,
+                      (long long)lda, m, (long long)ldc);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    constexpr int EITERS = 4;
+    dim3 grid(static_cast<unsigned>((pc + PK_LOCI - 1) / PK_LOCI),
+              static_cast<unsigned>((n + PK_SLAB * EITERS - 1) / (PK_SLAB * EITERS)));
+    pack_dosage_kernel<EITERS><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum, d_flags);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_locus_stats_i8(grm_cuda_ctx *ctx, const int32_t *d_colsum, int64_t p, int64_t n, int32_t m,
+                                           int32_t ploidy, double *d_q, double *d_w, double *d_stats) {
+    if (!ctx || !d_colsum || !d_q || !d_w || !d_stats || p < 1 || n < 1 || m < 1) {
+        grm_set_error("locus_stats_i8: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_TRY(ctx->partials.reserve(3 * RED_BLOCKS * sizeof(double)));
+    locus_stats_i8_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_colsum, p, static_cast<double>(n),
+                                                                       static_cast<double>(m), 0.5 * ploidy, d_q, d_w,
+                                                                       ctx->partials.as<double>());
+    GRM_CUDA_TRY(cudaGetLastError());
+    final_stats_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partials.as<double>(), RED_BLOCKS, d_stats, 0);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 2;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                            double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate) {
+    if (!ctx || !dA || !d_q || !d_stats || !d_flags || p < 1 || n < 1 || lda < n) {
+        grm_set_error("locus_stats_f64: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_TRY(ctx->partials.reserve(3 * RED_BLOCKS * sizeof(double)));
+    colmean_f64_kernel<<<static_cast<unsigned>((p + 7) / 8), 256, 0, ctx->stream>>>(dA, n, p, lda, d_q, d_flags);
+    GRM_CUDA_TRY(cudaGetLastError());
+    locus_stats_f64_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_q, p, ctx->partials.as<double>());
+    GRM_CUDA_TRY(cudaGetLastError());
+    final_stats_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partials.as<double>(), RED_BLOCKS, d_stats, accumulate);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                      const double *d_w, double *d_u) {
+    if (!ctx || !d_codes || !d_w || !d_u || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p) {
+        grm_set_error("rowdot_i8: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    rowdot_i8_kernel<<<static_cast<unsigned>((n + RD_ROWS - 1) / RD_ROWS), 256, 0, ctx->stream>>>(d_codes, n, p, ldc,
+                                                                                                 d_w, d_u);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}

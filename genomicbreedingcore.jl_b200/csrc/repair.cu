@@ -1,0 +1,260 @@
+// repair.cu — inflatediagonals! (src/grm/calc.jl:41-70) on the device.
+//
+// The reference decides with det(X) (LU with partial pivoting, then the SEQUENTIAL product of U's diagonal, which
+// under/overflows for n >~ 500) and isposdef(X) (Cholesky).  The decision therefore depends on IEEE under/overflow
+// of a running product, so it is reproduced literally: cuSOLVER Dgetrf/Dpotrf factorise on the device, the n pivots
+// come back to the host and are multiplied in pivot order in plain binary64 (gradual underflow, no log-domain
+// shortcut) — SURVEY.md A.4.  This step is O(n^3) FP64 library work and is reported separately from the GRM itself.
+#include <cusolverDn.h>
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+#define GRM_SOLVER_TRY(expr)                                                                  \
+    do {                                                                                      \
+        cusolverStatus_t _s = (expr);                                                         \
+        if (_s != CUSOLVER_STATUS_SUCCESS) {                                                  \
+            grm_set_error("%s failed at %s:%d: cusolver status %d", #expr, __FILE__, __LINE__, (int)_s); \
+            return (_s == CUSOLVER_STATUS_ALLOC_FAILED) ? GRM_CUDA_ERR_OOM : GRM_CUDA_ERR_CUDA; \
+        }                                                                                     \
+    } while (0)
+
+namespace {
+
+// out[0] |= 1 not symmetric (X[i,j] != X[j,i], NaN counts: calc.jl:43 uses issymmetric), 2 NaN, 4 Inf;
+// out64[1] = bit pattern of max |X| (non-negative doubles order like unsigned integers)
+__global__ void __launch_bounds__(256) scan_kernel(const double *__restrict__ X, int64_t n, int64_t ldx,
+                                                   unsigned long long *__restrict__ out) {
+    unsigned flags = 0;
+    unsigned long long mx = 0;
+    const int64_t j = blockIdx.y;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const double a = X[i + j * ldx];
+        if (i <= j) {
+            const double b = X[j + i * ldx];
+            if (!(a == b)) flags |= 1u;
+        }
+        if (a != a) flags |= 2u;
+        else if (isinf(a)) flags |= 4u;
+        else {
+            const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fabs(a)));
+            mx = bits > mx ? bits : mx;
+        }
+    }
+    flags = __reduce_or_sync(0xffffffffu, flags);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = other > mx ? other : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (flags) atomicOr(&out[0], static_cast<unsigned long long>(flags));
+        if (mx) atomicMax(&out[1], mx);
+    }
+}
+
+__global__ void copy_matrix_kernel(const double *__restrict__ X, int64_t n, int64_t ldx, double *__restrict__ Y) {
+    const int64_t j = blockIdx.y;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        Y[i + j * n] = X[i + j * ldx];
+}
+
+__global__ void diag_extract_kernel(const double *__restrict__ LU, int64_t n, double *__restrict__ d) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = LU[i + i * n];
+}
+
+// X[i,i] = fl(X[i,i] + eps)   (calc.jl:63)
+__global__ void diag_add_kernel(double *__restrict__ X, int64_t n, int64_t ldx, double eps) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) X[i + i * ldx] = X[i + i * ldx] + eps;
+}
+
+struct Repair {
+    grm_cuda_ctx *ctx;
+    cusolverDnHandle_t h;
+    double *X;
+    int64_t n, ldx;
+    double *work_mat;  // n x n copy that the factorisations destroy
+    double *lwork;
+    int lwork_len;
+    int *ipiv, *info;
+    double *d_diag;
+    std::vector<double> h_diag;
+    std::vector<int> h_ipiv;
+
+    int32_t copy_in() {
+        const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
+        copy_matrix_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(X, n, ldx, work_mat);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
+
+    // Julia: det(X) = det(lu(X; check=false)): 0 if the factorisation hit an exact zero pivot, otherwise the
+    // sequential product of diag(U) times (-1)^(number of row interchanges).
+    int32_t det(double *out) {
+        GRM_TRY(copy_in());
+        GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), work_mat, static_cast<int>(n),
+                                        lwork, ipiv, info));
+        diag_extract_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(work_mat, n, d_diag);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        int h_info = 0;
+        GRM_CUDA_TRY(cudaMemcpyAsync(h_diag.data(), d_diag, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (h_info < 0) {
+            grm_set_error("cusolverDnDgetrf: illegal argument %d", -h_info);
+            return GRM_CUDA_ERR_CUDA;
+        }
+        if (h_info > 0) {
+            *out = 0.0;
+            return GRM_CUDA_OK;
+        }
+        volatile double P = 1.0;  // volatile: one IEEE binary64 rounding per multiply, no reassociation
+        int swaps = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            P = P * h_diag[i];
+            if (h_ipiv[i] != static_cast<int>(i + 1)) ++swaps;
+        }
+        *out = (swaps & 1) ? -P : P;
+        return GRM_CUDA_OK;
+    }
+
+    // Julia: isposdef(X) = ishermitian(X) && LAPACK.potrf!('U', copy(X)) succeeded (symmetry already checked)
+    int32_t posdef(bool *out) {
+        GRM_TRY(copy_in());
+        GRM_SOLVER_TRY(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), work_mat, static_cast<int>(n),
+                                        lwork, lwork_len, info));
+        int h_info = 0;
+        GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (h_info < 0) {
+            grm_set_error("cusolverDnDpotrf: illegal argument %d", -h_info);
+            return GRM_CUDA_ERR_CUDA;
+        }
+        *out = (h_info == 0);
+        return GRM_CUDA_OK;
+    }
+};
+
+}  // namespace
+
+int32_t grm_cusolver_destroy(void *h) {
+    cusolverDnDestroy(static_cast<cusolverDnHandle_t>(h));
+    return GRM_CUDA_OK;
+}
+
+// device-resident implementation; X is a device pointer
+int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
+                          double *eps_total) {
+    *iters = 0;
+    *eps_total = 0.0;
+    if (n > 46000) {  // legacy 32-bit cuSOLVER indexing: n*n must stay below 2^31
+        grm_set_error("inflate_diagonals: n=%lld exceeds the single-GPU cuSOLVER range (n <= 46000)", (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    if (!ctx->cusolver) {
+        cusolverDnHandle_t h;
+        GRM_SOLVER_TRY(cusolverDnCreate(&h));
+        ctx->cusolver = h;
+    }
+    cusolverDnHandle_t h = static_cast<cusolverDnHandle_t>(ctx->cusolver);
+    GRM_SOLVER_TRY(cusolverDnSetStream(h, ctx->stream));
+
+    // calc.jl:43-48 — symmetry (squareness is implied by the C signature), plus the NaN/Inf/max|X| scan
+    GRM_TRY(ctx->misc.reserve(64));
+    unsigned long long *d_scan = ctx->misc.as<unsigned long long>();
+    GRM_CUDA_TRY(cudaMemsetAsync(d_scan, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+        const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
+        scan_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(X, n, ldx, d_scan);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+    }
+    unsigned long long h_scan[2];
+    GRM_CUDA_TRY(cudaMemcpyAsync(h_scan, d_scan, sizeof(h_scan), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_scan[0] & 1ull) {
+        grm_set_error("The input matrix is not symmetric.");
+        return GRM_CUDA_ERR_NOT_SYMMETRIC;
+    }
+
+    Repair r;
+    r.ctx = ctx;
+    r.h = h;
+    r.X = X;
+    r.n = n;
+    r.ldx = ldx;
+    GRM_TRY(ctx->lu.reserve(static_cast<size_t>(n) * n * sizeof(double)));
+    r.work_mat = ctx->lu.as<double>();
+    int lw1 = 0, lw2 = 0;
+    GRM_SOLVER_TRY(cusolverDnDgetrf_bufferSize(h, static_cast<int>(n), static_cast<int>(n), r.work_mat,
+                                               static_cast<int>(n), &lw1));
+    GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), r.work_mat,
+                                               static_cast<int>(n), &lw2));
+    r.lwork_len = std::max(lw1, lw2);
+    GRM_TRY(ctx->lu_work.reserve(std::max<size_t>(static_cast<size_t>(r.lwork_len), 1) * sizeof(double)));
+    r.lwork = ctx->lu_work.as<double>();
+    // ipiv (n ints) | info (1 int) | padding to 8 bytes | diag(U) (n doubles)
+    const int64_t int_slots = (n + 16 + 1) & ~int64_t(1);
+    GRM_TRY(ctx->ipiv.reserve(static_cast<size_t>(int_slots) * sizeof(int) + static_cast<size_t>(n) * sizeof(double)));
+    r.ipiv = ctx->ipiv.as<int>();
+    r.info = r.ipiv + n;
+    r.d_diag = reinterpret_cast<double *>(r.ipiv + int_slots);
+    r.h_diag.resize(n);
+    r.h_ipiv.resize(n);
+
+    const double eps = DBL_EPSILON;
+    // calc.jl:49-51 — early return; isposdef is evaluated only if det > eps (&& short-circuit)
+    double det0 = 0.0;
+    GRM_TRY(r.det(&det0));
+    if (det0 > eps) {
+        bool pd = false;
+        GRM_TRY(r.posdef(&pd));
+        if (pd) return GRM_CUDA_OK;
+    }
+    // calc.jl:52-57
+    if (h_scan[0] & 2ull) {
+        grm_set_error("The input matrix contains NaN values.");
+        return GRM_CUDA_ERR_NAN_MATRIX;
+    }
+    if (h_scan[0] & 4ull) {
+        grm_set_error("The input matrix contains Inf values.");
+        return GRM_CUDA_ERR_INF_MATRIX;
+    }
+    // calc.jl:58-66.  The first evaluation of the loop condition looks at the SAME matrix as the early test, so its
+    // det is reused (same input, same factorisation, same value).
+    double e = 0.0;
+    {
+        const long long bits = static_cast<long long>(h_scan[1]);
+        memcpy(&e, &bits, sizeof(double));
+    }
+    double total = 0.0;
+    int iter = 0;
+    double det_cur = det0;
+    for (;;) {
+        bool need = det_cur < eps;  // NaN compares false, negative compares true (calc.jl:61)
+        if (!need) {
+            bool pd = false;
+            GRM_TRY(r.posdef(&pd));
+            need = !pd;
+        }
+        if (!need || iter >= max_iter) break;
+        ++iter;
+        diag_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(X, n, ldx, e);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        total += e;
+        e *= (1.0 + eps);
+        GRM_TRY(r.det(&det_cur));
+    }
+    *iters = iter;
+    *eps_total = total;
+    return GRM_CUDA_OK;
+}

@@ -1,0 +1,234 @@
+// syrk_f64.cu — FP64 upper-triangular SYRK for continuous (pool-seq) allele frequencies, plus the
+// scale-and-mirror pass that makes the result exactly symmetric.
+//
+// Replaces the pair loop of src/grm/calc.jl:124-131 (grmsimple, z = x) and :202-209 (grmploidyaware,
+// z_ik = fl(fl(ploidy*fl(x_ik - 0.5)) - q_k), calc.jl:198,205 — the centring is applied while the operand is
+// staged into shared memory, with the reference's rounding sequence: no FMA contraction).
+//
+// tcgen05 has no FP64 kind, so the contraction runs on the FP64 tensor path that exists on sm_100:
+// mma.sync.m8n8k4.f64 (DMMA).  Block tile 128 x 128 entries, 8 warps (2 x 4), warp tile 64 x 32, K slab of 16
+// loci, double-buffered shared memory with register prefetch.  Only tiles that touch the upper triangle run.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FB = 128;          // block tile edge (entries)
+constexpr int FK = 16;           // loci per slab
+constexpr int FLD = FB + 4;      // padded row length: 4a + b (a,b in 0..3) hits 16 distinct 8-byte banks
+constexpr size_t F64_SMEM = 2ull * 2 * FK * FLD * sizeof(double);
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool CENTRED>
+__global__ void __launch_bounds__(256, 1)
+syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, double ploidy,
+                const double *__restrict__ q, const int2 *__restrict__ tiles, double *__restrict__ G, int64_t ldg,
+                int accumulate) {
+    extern __shared__ double sm[];
+    double(*sA)[FK][FLD] = reinterpret_cast<double(*)[FK][FLD]>(sm);
+    double(*sB)[FK][FLD] = reinterpret_cast<double(*)[FK][FLD]>(sm + 2 * FK * FLD);
+
+    const int2 tc = tiles[blockIdx.x];
+    const int64_t row0 = tc.x, col0 = tc.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    // staging map: thread -> entry e (0..127) and 8 consecutive loci of the slab
+    const int e = tid & 127, kh = (tid >> 7) * 8;
+    const int64_t ra = row0 + e, rb = col0 + e;
+    const bool va = ra < n, vb = rb < n;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    double pa[8], pb[8];
+    auto fetch = [&](int64_t k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t k = k0 + kh + j;
+            const bool vk = k < p;
+            double xa = (vk && va) ? __ldg(A + ra + k * lda) : 0.0;
+            double xb = (vk && vb) ? __ldg(A + rb + k * lda) : 0.0;
+            if (CENTRED) {
+                const double qk = vk ? __ldg(q + k) : 0.0;
+                // z = fl(fl(ploidy * fl(x - 0.5)) - q): explicit round-to-nearest ops, never contracted
+                xa = (vk && va) ? __dsub_rn(__dmul_rn(ploidy, __dsub_rn(xa, 0.5)), qk) : 0.0;
+                xb = (vk && vb) ? __dsub_rn(__dmul_rn(ploidy, __dsub_rn(xb, 0.5)), qk) : 0.0;
+            }
+            pa[j] = xa;
+            pb[j] = xb;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sA[buf][kh + j][e] = pa[j];
+            sB[buf][kh + j][e] = pb[j];
+        }
+    };
+
+    const int64_t nslab = (p + FK - 1) / FK;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int64_t s = 0; s < nslab; ++s) {
+        const int buf = static_cast<int>(s & 1);
+        if (s + 1 < nslab) fetch((s + 1) * FK);
+#pragma unroll
+        for (int kk = 0; kk < FK / 4; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = sA[buf][kk * 4 + fk][wm * 64 + mi * 8 + fr];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = sB[buf][kk * 4 + fk][wn * 32 + ni * 8 + fr];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        if (s + 1 < nslab) stash(buf ^ 1);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        const int64_t row = row0 + wm * 64 + mi * 8 + fr;
+        if (row >= n) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t col = col0 + wn * 32 + ni * 8 + 2 * fk + h;
+                if (col < n) {
+                    double *dst = G + row + col * ldg;
+                    *dst = accumulate ? (*dst + acc[mi][ni][h]) : acc[mi][ni][h];
+                }
+            }
+        }
+    }
+}
+
+// G[i,j] = G[i,j] / denom for i <= j, then G[j,i] = G[i,j]: 32 x 32 tiles through shared memory so both the read
+// of the upper tile and the write of its mirror are coalesced.
+__global__ void __launch_bounds__(256) scale_mirror_kernel(double *__restrict__ G, int64_t n, int64_t ldg, double denom,
+                                                           int divide) {
+    __shared__ double t[32][33];
+    const int64_t bi = blockIdx.x, bj = blockIdx.y;
+    if (bi > bj) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t i0 = bi * 32, j0 = bj * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int jj = ty + 8 * r;
+        const int64_t i = i0 + tx, j = j0 + jj;
+        double v = 0.0;
+        if (i < n && j < n) {
+            v = G[i + j * ldg];
+            if (divide) {
+                v = v / denom;
+                if (i <= j) G[i + j * ldg] = v;
+            }
+        }
+        t[jj][tx] = v;  // t[j_local][i_local]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ii = ty + 8 * r;
+        // mirror element: row (j0 + tx), column (i0 + ii)  <-  upper element (i0 + ii, j0 + tx)
+        const int64_t i = i0 + ii, j = j0 + tx;
+        if (i < n && j < n && i < j) G[j + i * ldg] = t[tx][ii];
+    }
+}
+
+int32_t get_tile_list_f64(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_tiles, int *count) {
+    TileListCache &tc = ctx->tiles_f64;
+    if (tc.n != n || tc.rank != rank || tc.world != world) {
+        std::vector<int2> order;
+        grm_tile_order(n, order);
+        int64_t b, e;
+        grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
+        std::vector<int2> blk;
+        for (int64_t t = b; t < e; ++t) {
+            const int r0 = order[t].x * GRM_TILE, c0 = order[t].y * GRM_TILE;
+            for (int dr = 0; dr < GRM_TILE; dr += FB)
+                for (int dc = 0; dc < GRM_TILE; dc += FB) {
+                    const int r = r0 + dr, c = c0 + dc;
+                    if (r >= n || c >= n || r > c) continue;  // outside, or strictly below the diagonal
+                    blk.push_back(make_int2(r, c));
+                }
+        }
+        GRM_TRY(tc.buf.reserve(std::max<size_t>(blk.size(), 1) * sizeof(int2)));
+        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        tc.n = n;
+        tc.rank = rank;
+        tc.world = world;
+        tc.count = static_cast<int32_t>(blk.size());
+    }
+    *d_tiles = tc.buf.as<int2>();
+    *count = tc.count;
+    return GRM_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                     int32_t centred, double ploidy, const double *d_q, int32_t accumulate, double *d_G,
+                                     int64_t ldg, int32_t rank, int32_t world) {
+    if (!ctx || !dA || !d_G || n < 1 || p < 1 || lda < n || ldg < n || (centred && !d_q) || world < 1 || rank < 0 ||
+        rank >= world) {
+        grm_set_error("syrk_f64: bad argument (n=%lld p=%lld lda=%lld ldg=%lld)", (long long)n, (long long)p,
+                      (long long)lda, (long long)ldg);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int2 *d_tiles;
+    int count;
+    GRM_TRY(get_tile_list_f64(ctx, n, rank, world, &d_tiles, &count));
+    if (count == 0) return GRM_CUDA_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_f64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(F64_SMEM)));
+        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_f64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(F64_SMEM)));
+        attr_set = true;
+    }
+    if (centred)
+        syrk_f64_kernel<true><<<count, 256, F64_SMEM, ctx->stream>>>(dA, n, p, lda, ploidy, d_q, d_tiles, d_G, ldg,
+                                                                     accumulate);
+    else
+        syrk_f64_kernel<false><<<count, 256, F64_SMEM, ctx->stream>>>(dA, n, p, lda, ploidy, d_q, d_tiles, d_G, ldg,
+                                                                      accumulate);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom) {
+    if (!ctx || !d_G || n < 1 || ldg < n) {
+        grm_set_error("scale_mirror: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const unsigned nb = static_cast<unsigned>((n + 31) / 32);
+    scale_mirror_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(d_G, n, ldg, denom, denom != 1.0 ? 1 : 0);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg) {
+    return grm_cuda_scale_mirror(ctx, d_G, n, ldg, 1.0);
+}

@@ -1,0 +1,309 @@
+// syrk_i8.cu — exact integer Gram matrix C = c * c' of the packed dosage codes on tcgen05 tensor cores.
+//
+// Replaces the pair loop `dot(A[i,:], A[j,:])` of the reference (src/grm/calc.jl:124-131 and :202-209) for
+// dosage-quantised input: with x = c/m the reference's FP64 sum is exactly C_ij/m^2, so the
+// contraction is done in int8 x int8 -> int32 and the FP64 scaling / rank-1 centring is applied
+// in the epilogue.
+//
+// Kernel shape (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: operand tiles (K-major int8, 128-byte swizzle) global -> shared, 4-stage ring
+//   warp 1      MMA issuer:   tcgen05.mma.kind::i8, M=128 x N=256 x K=32 per instruction, accumulators in TMEM
+//   warps 2..5  epilogue:     tcgen05.ld TMEM -> registers -> (int32 | FP64 formula) -> global, overlapped with the
+//                             next tile's main loop through two TMEM accumulator stages (2 x 256 columns)
+// Work items are 128 x 256 output tiles taken from a host-built list that covers only the upper triangle.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;       // rows of A per CTA tile  (UMMA M)
+constexpr int BN = 256;       // rows of B per CTA tile  (UMMA N)
+constexpr int BK = 128;       // bytes (= int8 elements) of K per pipeline stage = one 128-byte swizzle atom
+constexpr int UMMA_K = 32;    // K per tcgen05.mma for 8-bit operands
+constexpr int STAGES = 4;
+constexpr uint32_t A_BYTES = BM * BK;               // 16 KiB
+constexpr uint32_t B_BYTES = BN * BK;               // 32 KiB
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES; // 48 KiB
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 2 * BN;              // two accumulator stages of 256 int32 columns
+constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct EpiParams {
+    int64_t n;
+    int32_t *C;      // mode 0
+    int64_t ldC;
+    double *G;       // modes 1, 2
+    int64_t ldg;
+    double alpha, beta, gamma, denom;
+    const double *u;
+};
+
+// EPI: 0 = store int32 C;  1 = G = (alpha*C)/denom;  2 = G = ((alpha*C - beta*(u_i+u_j)) + gamma)/denom
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
+               EpiParams ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int2 tc = tiles[t];
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *sA = smem + stage * STAGE_BYTES;
+                    uint8_t *sB = sA + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(sA, &tmap, &full_bar[stage], kb * BK, tc.x);
+                    tma_load_2d(sB, &tmap, &full_bar[stage], kb * BK, tc.y);
+                    tma_load_2d(sB + 128 * BK, &tmap, &full_bar[stage], kb * BK, tc.y + 128);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_k_sw128(sA);
+                    const uint64_t bdesc = umma_desc_k_sw128(sA + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advancing K by 32 bytes inside the 128-byte swizzle atom = +2 in the 16-byte address field
+                        umma_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        int local = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int2 tc = tiles[t];
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int64_t row = static_cast<int64_t>(tc.x) + quarter * 32 + lane;
+            const bool row_ok = row < ep.n;
+            double ui = 0.0;
+            if (EPI == 2 && row_ok) ui = ep.u[row];
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + acc * BN + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+                tmem_wait_ld();
+                const int64_t col0 = static_cast<int64_t>(tc.y) + c0;
+                if (row_ok && col0 < ep.n) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t col = col0 + j;
+                        if (col < ep.n) {
+                            const int32_t c = static_cast<int32_t>(r[j]);
+                            if (EPI == 0) {
+                                ep.C[row + col * ep.ldC] = c;
+                            } else {
+                                double v = static_cast<double>(c) * ep.alpha;
+                                if (EPI == 2) {
+                                    const double uj = __ldg(ep.u + col);
+                                    v = (v - ep.beta * (ui + uj)) + ep.gamma;
+                                }
+                                ep.G[row + col * ep.ldg] = v / ep.denom;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, CUtensorMap *out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GRM_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            grm_set_error("cuTensorMapEncodeTiled not available from the driver");
+            return GRM_CUDA_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    // dim0 = loci (bytes, contiguous), dim1 = entries.  Out-of-range rows/loci are zero-filled by TMA, so ragged
+    // n (not a multiple of 128) and p (not a multiple of 128) contribute exact zeros to the integer sums.
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(n)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ldc)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), 128u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(d_codes), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        grm_set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld p=%lld ldc=%lld)", (int)r, (long long)n,
+                      (long long)p, (long long)ldc);
+        return GRM_CUDA_ERR_CUDA;
+    }
+    return GRM_CUDA_OK;
+}
+
+// 128 x 256 CTA tiles of the owned 256 x 256 sharding tiles, in the L2-friendly order of grm_tile_order().
+int32_t get_tile_list(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_tiles, int *count) {
+    TileListCache &tc = ctx->tiles_i8;
+    if (tc.n != n || tc.rank != rank || tc.world != world) {
+        std::vector<int2> order;
+        grm_tile_order(n, order);
+        int64_t b, e;
+        grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
+        std::vector<int2> cta;
+        cta.reserve(2 * (e - b));
+        for (int64_t t = b; t < e; ++t) {
+            const int row0 = order[t].x * GRM_TILE, col0 = order[t].y * GRM_TILE;
+            cta.push_back(make_int2(row0, col0));
+            if (row0 + BM < n) cta.push_back(make_int2(row0 + BM, col0));
+        }
+        GRM_TRY(tc.buf.reserve(std::max<size_t>(cta.size(), 1) * sizeof(int2)));
+        // pageable -> device copy is synchronous with respect to the host buffer, safe to free afterwards
+        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, cta.data(), cta.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        tc.n = n;
+        tc.rank = rank;
+        tc.world = world;
+        tc.count = static_cast<int32_t>(cta.size());
+    }
+    *d_tiles = tc.buf.as<int2>();
+    *count = tc.count;
+    return GRM_CUDA_OK;
+}
+
+template <int EPI>
+int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, const EpiParams &ep,
+               int32_t rank, int32_t world) {
+    if (!ctx || !d_codes || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1 || rank < 0 || rank >= world) {
+        grm_set_error("syrk_i8: bad argument (n=%lld p=%lld ldc=%lld rank=%d world=%d)", (long long)n, (long long)p,
+                      (long long)ldc, rank, world);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    CUtensorMap tmap;
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, &tmap));
+    const int2 *d_tiles;
+    int count;
+    GRM_TRY(get_tile_list(ctx, n, rank, world, &d_tiles, &count));
+    if (count == 0) return GRM_CUDA_OK;
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[EPI]) {
+        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(SMEM_BYTES)));
+        attr_set[EPI] = true;
+    }
+    const int num_kb = static_cast<int>((p + BK - 1) / BK);
+    const int grid = std::min(count, ctx->num_sms);
+    syrk_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmap, d_tiles, count, num_kb, ep);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                    int32_t *d_C, int64_t ldC, int32_t rank, int32_t world) {
+    if (!d_C || ldC < n) {
+        grm_set_error("syrk_i8: bad output (ldC=%lld n=%lld)", (long long)ldC, (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    EpiParams ep{};
+    ep.n = n;
+    ep.C = d_C;
+    ep.ldC = ldC;
+    return launch<0>(ctx, d_codes, n, p, ldc, ep, rank, world);
+}
+
+extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                        double alpha, double beta, double gamma, double denom, const double *d_u,
+                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+    if (!d_G || ldg < n || (beta != 0.0 && !d_u)) {
+        grm_set_error("syrk_i8_f64: bad output or missing u (ldg=%lld n=%lld)", (long long)ldg, (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    EpiParams ep{};
+    ep.n = n;
+    ep.G = d_G;
+    ep.ldg = ldg;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.gamma = gamma;
+    ep.denom = denom;
+    ep.u = d_u;
+    if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, ep, rank, world);
+    return launch<2>(ctx, d_codes, n, p, ldc, ep, rank, world);
+}

@@ -1,0 +1,178 @@
+"""Staged device-side API over torch CUDA tensors (PyTorch only provides device memory and streams here).
+
+Layout convention: an n x p column-major matrix is a contiguous torch tensor of shape (p, n); the n x n column-major
+GRM is a contiguous (n, n) tensor whose [j, i] element is G[i, j] (symmetric, so the distinction only matters for
+partially filled, sharded outputs).  All work is enqueued on the context's stream; call `ctx.synchronize()` (or use
+`on_ctx_stream`) before touching results from torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from contextlib import contextmanager
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+@contextmanager
+def on_ctx_stream(ctx: _lib.Context):
+    """Make the library stream torch's current stream (so torch.cuda.Event timings see the library's kernels)."""
+    torch = _torch()
+    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", ctx.device))
+    with torch.cuda.stream(ext):
+        yield ext
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def padded_loci(p: int) -> int:
+    return (p + 127) // 128 * 128
+
+
+def detect_denominator(ctx, A_pn, max_cells: int = 0) -> int:
+    p, n = A_pn.shape
+    m = C.c_int32(0)
+    _lib.check(ctx.lib.grm_cuda_detect_denominator(ctx.handle, _ptr(A_pn), n, p, n, max_cells, C.byref(m)))
+    return m.value
+
+
+def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int = 0):
+    """Quantise + transpose A (loci k0..k0+pc of the full problem) into codes[:, k0:k0+pc]; returns
+    (codes[n, ldc] int8, colsum[ldc] int32, flags[16] uint32-as-int32)."""
+    torch = _torch()
+    pc, n = A_pn.shape
+    dev = A_pn.device
+    if codes is None:
+        codes = torch.zeros((n, padded_loci(k0 + pc)), dtype=torch.int8, device=dev)
+    ldc = codes.shape[1]
+    if colsum is None:
+        colsum = torch.zeros((ldc,), dtype=torch.int32, device=dev)
+    if flags is None:
+        flags = torch.zeros((16,), dtype=torch.int32, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_pack_dosage(ctx.handle, _ptr(A_pn), n, pc, n, m,
+                                            C.c_void_p(codes.data_ptr() + k0), ldc,
+                                            C.c_void_p(colsum.data_ptr() + 4 * k0), _ptr(flags)))
+    return codes, colsum, flags
+
+
+def syrk_i8(ctx, codes, p: int, rank: int = 0, world: int = 1, out=None):
+    torch = _torch()
+    n, ldc = codes.shape
+    if out is None:
+        out = torch.zeros((n, n), dtype=torch.int32, device=codes.device)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_syrk_i8(ctx.handle, _ptr(codes), n, p, ldc, _ptr(out), n, rank, world))
+    return out
+
+
+def syrk_i8_f64(ctx, codes, p: int, alpha: float, beta: float, gamma: float, denom: float, u=None, rank: int = 0,
+                world: int = 1, out=None):
+    torch = _torch()
+    n, ldc = codes.shape
+    if out is None:
+        out = torch.zeros((n, n), dtype=torch.float64, device=codes.device)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_syrk_i8_f64(ctx.handle, _ptr(codes), n, p, ldc, alpha, beta, gamma, denom,
+                                            _ptr(u) if u is not None else None, _ptr(out), n, rank, world))
+    return out
+
+
+def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
+    torch = _torch()
+    dev = colsum.device
+    q = torch.empty((p,), dtype=torch.float64, device=dev)
+    w = torch.empty((p,), dtype=torch.float64, device=dev)
+    stats = torch.zeros((3,), dtype=torch.float64, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_locus_stats_i8(ctx.handle, _ptr(colsum), p, n, m, ploidy, _ptr(q), _ptr(w), _ptr(stats)))
+    return q, w, stats
+
+
+def rowdot_i8(ctx, codes, p: int, w):
+    torch = _torch()
+    n, ldc = codes.shape
+    u = torch.empty((n,), dtype=torch.float64, device=codes.device)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_rowdot_i8(ctx.handle, _ptr(codes), n, p, ldc, _ptr(w), _ptr(u)))
+    return u
+
+
+def locus_stats_f64(ctx, A_pn, accumulate: bool = False, q=None, stats=None, flags=None):
+    torch = _torch()
+    p, n = A_pn.shape
+    dev = A_pn.device
+    if q is None:
+        q = torch.empty((p,), dtype=torch.float64, device=dev)
+    if stats is None:
+        stats = torch.zeros((3,), dtype=torch.float64, device=dev)
+    if flags is None:
+        flags = torch.zeros((16,), dtype=torch.int32, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_locus_stats_f64(ctx.handle, _ptr(A_pn), n, p, n, _ptr(q), _ptr(stats), _ptr(flags),
+                                                1 if accumulate else 0))
+    return q, stats, flags
+
+
+def syrk_f64(ctx, A_pn, centred: bool, ploidy: float = 2.0, q=None, accumulate: bool = False, rank: int = 0,
+             world: int = 1, out=None):
+    torch = _torch()
+    p, n = A_pn.shape
+    if out is None:
+        out = torch.zeros((n, n), dtype=torch.float64, device=A_pn.device)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_syrk_f64(ctx.handle, _ptr(A_pn), n, p, n, 1 if centred else 0, float(ploidy),
+                                         _ptr(q) if q is not None else None, 1 if accumulate else 0, _ptr(out), n,
+                                         rank, world))
+    return out
+
+
+def scale_mirror(ctx, G, denom: float = 1.0):
+    n = G.shape[0]
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_scale_mirror(ctx.handle, _ptr(G), n, n, float(denom)))
+    return G
+
+
+def grm_device(ctx, A_pn, ploidy=None, *, path=_lib.PATH_AUTO, denominator=0, skip_repair=False, max_iter=1000,
+               rank=0, world=1, out=None):
+    """One-call device-resident GRM (inputs and output already in HBM): grmsimple if `ploidy` is None, else
+    grmploidyaware.  Returns (G, info dict)."""
+    torch = _torch()
+    p, n = A_pn.shape
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float64, device=A_pn.device)
+        if world > 1:
+            out.zero_()
+    o = _lib.default_options()
+    o.path, o.denominator, o.max_iter = path, denominator, max_iter
+    o.skip_repair = 1 if skip_repair else 0
+    o.input_location = o.output_location = _lib.LOC_DEVICE
+    o.rank, o.world = rank, world
+    info = _lib.new_info()
+    ctx.synchronize_with_torch()
+    if ploidy is None:
+        st = ctx.lib.grm_cuda_simple(ctx.handle, _ptr(A_pn), n, p, n, _ptr(out), n, C.byref(o), C.byref(info))
+    else:
+        st = ctx.lib.grm_cuda_ploidyaware(ctx.handle, _ptr(A_pn), n, p, n, int(ploidy), _ptr(out), n, C.byref(o),
+                                          C.byref(info))
+    _lib.check(st)
+    return out, info.as_dict()
+
+
+def _synchronize_with_torch(self):
+    """Order the library stream after everything torch has enqueued on its current stream for this device."""
+    torch = _torch()
+    cur = torch.cuda.current_stream(torch.device("cuda", self.device))
+    if cur.cuda_stream != self.stream:
+        cur.synchronize()
+
+
+_lib.Context.synchronize_with_torch = _synchronize_with_torch

@@ -1,0 +1,108 @@
+"""grmsimple / grmploidyaware / inflatediagonals — the reference's operator interface for the GRM path
+(src/grm/calc.jl:115-142, :189-217, :41-70), backed by libgrm_cuda on a B200.
+
+Same names, argument meaning and error behaviour as the Julia functions:
+    grmsimple(genomes; max_iter=1000, verbose=false)::GRM
+    grmploidyaware(genomes; ploidy=2, max_iter=1000, verbose=false)::GRM
+    inflatediagonals!(X; max_iter=1000, verbose=false)::Nothing      (here: inflatediagonals(X, ...), in place)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .structs import GRM, ArgumentError, ErrorException, Genomes, MissingDataError, checkdims
+
+
+def _raise_for(err: _lib.GrmCudaError):
+    s = err.status
+    if s == _lib.ERR_MISSING:
+        raise MissingDataError(err.message) from None
+    if s in (_lib.ERR_BAD_ARGUMENT, _lib.ERR_NOT_SYMMETRIC, _lib.ERR_NAN_MATRIX, _lib.ERR_INF_MATRIX,
+             _lib.ERR_NONFINITE, _lib.ERR_NOT_DOSAGE, _lib.ERR_OVERFLOW):
+        raise ArgumentError(err.message) from None
+    raise err
+
+
+def _colmajor(a: np.ndarray) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags.f_contiguous:
+        a = np.asfortranarray(a, dtype=np.float64)
+    return a
+
+
+def _run(genomes: Genomes, centred: bool, ploidy: int, max_iter: int, verbose: bool, ctx, path, denominator,
+         skip_repair) -> GRM:
+    if not checkdims(genomes):
+        raise ArgumentError("The Genomes struct is corrupted ☹.")  # calc.jl:118-120, :191-193
+    ctx = ctx or _lib.default_context()
+    A = _colmajor(genomes.allele_frequencies)
+    n, p = A.shape
+    G = np.empty((n, n), dtype=np.float64, order="F")  # calc.jl:123
+    o = _lib.default_options()
+    o.path = path
+    o.denominator = denominator
+    o.max_iter = int(max_iter)
+    o.skip_repair = 1 if skip_repair else 0
+    info = _lib.new_info()
+    lib = ctx.lib
+    try:
+        if centred:
+            _lib.check(lib.grm_cuda_ploidyaware(ctx.handle, A.ctypes.data, n, p, n, int(ploidy), G.ctypes.data, n,
+                                                C.byref(o), C.byref(info)))
+        else:
+            _lib.check(lib.grm_cuda_simple(ctx.handle, A.ctypes.data, n, p, n, G.ctypes.data, n, C.byref(o),
+                                           C.byref(info)))
+    except _lib.GrmCudaError as e:
+        _raise_for(e)
+    if verbose:  # calc.jl:67-69
+        print(f"Performed {info.repair_iters} iterations of diagonal inflation to ensure matrix invertibility "
+              f"(ϵ_total = {info.eps_total}).")
+    # entries / loci_alleles alias the input vectors, like calc.jl:123,196
+    grm = GRM(genomes.entries, genomes.loci_alleles, G, info=info.as_dict())
+    if not centred and not checkdims(grm):
+        raise ErrorException("Error computing a simple GRM.")  # calc.jl:135-137
+    return grm
+
+
+def grmsimple(genomes: Genomes, max_iter: int = 1_000, verbose: bool = False, *, ctx: Optional[_lib.Context] = None,
+              path: int = _lib.PATH_AUTO, denominator: int = 0, skip_repair: bool = False) -> GRM:
+    """G = A*A'/p then inflatediagonals! (calc.jl:115-142).  Keyword-only extras select the backend path."""
+    return _run(genomes, False, 0, max_iter, verbose, ctx, path, denominator, skip_repair)
+
+
+def grmploidyaware(genomes: Genomes, ploidy: int = 2, max_iter: int = 1_000, verbose: bool = False, *,
+                   ctx: Optional[_lib.Context] = None, path: int = _lib.PATH_AUTO, denominator: int = 0,
+                   skip_repair: bool = False) -> GRM:
+    """q = colmean(A); Z = ploidy*(A-0.5) - 1q'; G = Z*Z'/(ploidy*sum(q(1-q))) then inflatediagonals!
+    (calc.jl:189-217)."""
+    return _run(genomes, True, ploidy, max_iter, verbose, ctx, path, denominator, skip_repair)
+
+
+def inflatediagonals(X: np.ndarray, max_iter: int = 1_000, verbose: bool = False, *,
+                     ctx: Optional[_lib.Context] = None):
+    """inflatediagonals!(X) (calc.jl:41-70): modifies X in place, returns None.  X must be a float64 square matrix;
+    a C-ordered symmetric matrix is its own transpose, so either memory order is accepted."""
+    if not isinstance(X, np.ndarray) or X.dtype != np.float64 or X.ndim != 2:
+        raise TypeError("inflatediagonals expects a 2-D float64 numpy array (Matrix{Float64})")
+    if X.shape[0] != X.shape[1]:
+        # the reference checks symmetry first (calc.jl:43), so a non-square matrix reports "not symmetric"
+        raise ArgumentError("The input matrix is not symmetric.")
+    if not (X.flags.f_contiguous or X.flags.c_contiguous):
+        raise TypeError("inflatediagonals needs a contiguous matrix to update in place")
+    ctx = ctx or _lib.default_context()
+    n = X.shape[0]
+    iters = C.c_int32(0)
+    tot = C.c_double(0.0)
+    try:
+        _lib.check(ctx.lib.grm_cuda_inflate_diagonals(ctx.handle, X.ctypes.data, n, n, int(max_iter), _lib.LOC_HOST,
+                                                      C.byref(iters), C.byref(tot)))
+    except _lib.GrmCudaError as e:
+        _raise_for(e)
+    if verbose:
+        print(f"Performed {iters.value} iterations of diagonal inflation to ensure matrix invertibility "
+              f"(ϵ_total = {tot.value}).")
+    return None

@@ -1,0 +1,196 @@
+/*
+ * grm_cuda.h — C ABI of libgrm_cuda, the B200 (sm_100a) backend for the genomic
+ * relationship matrix (GRM) path of GenomicBreedingCore.jl.
+ *
+ * The reference has no FFI: its boundary is three exported Julia functions in
+ * src/grm/calc.jl.  Each entry point below names the reference interface it
+ * replaces (file:line, relative to the reference repository root):
+ *
+ *   grm_cuda_simple             <- grmsimple(genomes; max_iter, verbose)             src/grm/calc.jl:115-142
+ *   grm_cuda_ploidyaware        <- grmploidyaware(genomes; ploidy, max_iter, verbose) src/grm/calc.jl:189-217
+ *   grm_cuda_inflate_diagonals  <- inflatediagonals!(X; max_iter, verbose)           src/grm/calc.jl:41-70
+ *
+ * Conventions (mirroring the Julia side):
+ *   - All matrices are COLUMN-MAJOR, exactly as Julia stores them.  The input is
+ *     genomes.allele_frequencies, n entries x p loci, element (i,k) at A[i + k*lda];
+ *     a missing value is passed as NaN.  The output is the n x n Float64 GRM,
+ *     element (i,j) at G[i + j*ldg]; both triangles are written and are
+ *     bit-identical mirrors of each other (the reference asserts issymmetric,
+ *     calc.jl:43).  Row/column order is the input order of genomes.entries
+ *     (calc.jl:123,196); nothing is sorted.
+ *   - Pointers are borrowed for the duration of the call only.
+ *   - No C++ exception crosses this boundary.  Every function returns a
+ *     grm_cuda_status; grm_cuda_last_error() returns a thread-local message.
+ *   - There is no CPU fallback: without a usable CUDA device every compute entry
+ *     point returns GRM_CUDA_ERR_CUDA.
+ *   - Callable from any host thread; the library sets the device per call and
+ *     installs no signal handlers.
+ */
+#ifndef GRM_CUDA_H
+#define GRM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRM_CUDA_VERSION 100 /* 0.1.0 */
+
+typedef enum grm_cuda_status {
+    GRM_CUDA_OK = 0,
+    GRM_CUDA_ERR_BAD_ARGUMENT = 1,   /* null pointer, n<1, p<1, lda<n, ...  -> ArgumentError                       */
+    GRM_CUDA_ERR_MISSING = 2,        /* NaN ("missing") in allele_frequencies -> the reference throws (calc.jl:127)  */
+    GRM_CUDA_ERR_NONFINITE = 3,      /* +-Inf in the input                                                           */
+    GRM_CUDA_ERR_NOT_SYMMETRIC = 4,  /* inflatediagonals!: "The input matrix is not symmetric."      calc.jl:43-45   */
+    GRM_CUDA_ERR_NAN_MATRIX = 5,     /* inflatediagonals!: "The input matrix contains NaN values."   calc.jl:52-54   */
+    GRM_CUDA_ERR_INF_MATRIX = 6,     /* inflatediagonals!: "The input matrix contains Inf values."   calc.jl:55-57   */
+    GRM_CUDA_ERR_CUDA = 7,           /* CUDA runtime/driver/cuSOLVER failure, or no sm_100 device                    */
+    GRM_CUDA_ERR_OOM = 8,            /* device or pinned-host allocation failed                                      */
+    GRM_CUDA_ERR_NOT_DOSAGE = 9,     /* int8 path forced but the frequencies are not k/m with m a power of two <= 64 */
+    GRM_CUDA_ERR_OVERFLOW = 10       /* m*m*p would overflow the int32 accumulators                                  */
+} grm_cuda_status;
+
+/* Which contraction ran (grm_cuda_info.path) / may run (grm_cuda_options.path). */
+#define GRM_CUDA_PATH_AUTO 0 /* detect dosage-quantised input on load; fall back to FP64 for continuous input */
+#define GRM_CUDA_PATH_I8   1 /* exact int8 tcgen05 SYRK + FP64 epilogue                                        */
+#define GRM_CUDA_PATH_F64  2 /* FP64 upper-triangular SYRK (pool-seq / continuous frequencies)                 */
+
+#define GRM_CUDA_LOC_HOST   0
+#define GRM_CUDA_LOC_DEVICE 1
+
+typedef struct grm_cuda_ctx grm_cuda_ctx; /* opaque: device, streams, workspaces, cuSOLVER handle */
+
+typedef struct grm_cuda_options {
+    int32_t struct_size;     /* = sizeof(grm_cuda_options); lets the struct grow compatibly                    */
+    int32_t path;            /* GRM_CUDA_PATH_*                                                                */
+    int32_t denominator;     /* dosage denominator m if known (1,2,4,...,64); 0 = detect                       */
+    int32_t max_iter;        /* inflatediagonals! max_iter (reference default 1000, calc.jl:41)                */
+    int32_t skip_repair;     /* 1 = return the raw GRM, i.e. stop before calc.jl:133 / :211                    */
+    int32_t input_location;  /* GRM_CUDA_LOC_*: where A lives                                                  */
+    int32_t output_location; /* GRM_CUDA_LOC_*: where G lives                                                  */
+    int32_t rank;            /* tile sharding: this process computes tiles t with owner(t) == rank ...         */
+    int32_t world;           /* ... out of `world` ranks (1 = everything).  Sharded calls imply skip_repair.   */
+    int32_t reserved0;
+    int64_t chunk_loci;      /* loci per host->device streaming chunk; 0 = automatic                           */
+} grm_cuda_options;
+
+typedef struct grm_cuda_info {
+    int32_t struct_size;   /* = sizeof(grm_cuda_info)                                                          */
+    int32_t path;          /* GRM_CUDA_PATH_I8 or GRM_CUDA_PATH_F64                                            */
+    int32_t denominator;   /* detected dosage denominator m (int8 path), else 0                                */
+    int32_t repair_iters;  /* rounds of diagonal inflation performed (calc.jl:62)                              */
+    double eps_total;      /* total added to the diagonal (the value calc.jl:68 prints)                        */
+    double scale;          /* divisor applied: p for grmsimple (calc.jl:127), d for grmploidyaware (calc.jl:201)*/
+    int64_t tiles;         /* upper-triangular output tiles this call computed                                 */
+    /* device timings, CUDA events on the library stream, milliseconds */
+    float ms_h2d;
+    float ms_pack;         /* column statistics + quantise/pack kernel                                         */
+    float ms_rowdot;       /* u = c.w row dot products for the rank-1 correction                               */
+    float ms_syrk;         /* int8 tcgen05 or FP64 SYRK kernel                                                 */
+    float ms_finalize;     /* mirror kernel                                                                    */
+    float ms_repair;       /* inflatediagonals! (cuSOLVER LU/Cholesky + host pivot product)                    */
+    float ms_d2h;
+    float ms_total;        /* wall time of the whole call, host clock                                          */
+    int32_t kernel_launches; /* kernels of this library launched by the call                                   */
+    int32_t reserved0;
+} grm_cuda_info;
+
+/* ---- library / context ------------------------------------------------------------------------------------ */
+int32_t grm_cuda_version(void);
+const char *grm_cuda_last_error(void);
+const char *grm_cuda_status_string(int32_t status);
+void grm_cuda_options_default(grm_cuda_options *opts);
+
+int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out);
+int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx);
+/* cudaStream_t the context launches on (so a caller can order its own work / record events against it). */
+void *grm_cuda_ctx_stream(grm_cuda_ctx *ctx);
+int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx);
+
+/* ---- the three reference entry points ---------------------------------------------------------------------- */
+/* grmsimple, calc.jl:115-142:  G = A*A'/p, then inflatediagonals!. */
+int32_t grm_cuda_simple(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
+                        double *G, int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info);
+
+/* grmploidyaware, calc.jl:189-217:  q = colmean(A); Z = ploidy*(A-0.5) - 1q'; d = ploidy*sum(q(1-q));
+ * G = Z*Z'/d, then inflatediagonals!. */
+int32_t grm_cuda_ploidyaware(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
+                             int32_t ploidy, double *G, int64_t ldg, const grm_cuda_options *opts,
+                             grm_cuda_info *info);
+
+/* inflatediagonals!, calc.jl:41-70.  `location` says where X lives (GRM_CUDA_LOC_*). */
+int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
+                                   int32_t location, int32_t *iters, double *eps_total);
+
+/* ---- staged device-side API (all pointers are DEVICE pointers; work is enqueued on the context stream) ------
+ * These are the pieces the three entry points are assembled from.  They exist so that parity tests can look at
+ * intermediate results (integer Gram matrix, q, d) and so that a multi-GPU host (one process per GPU) can put its
+ * own exchange step between them. */
+
+/* Smallest power-of-two m <= 64 such that m*x is an integer in [0,m] for every sampled cell; 0 if none
+ * (continuous data).  Reads at most `max_cells` cells (<=0: all).  Synchronises the stream. */
+int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                    int64_t max_cells, int32_t *m_out);
+
+/* Column statistics + quantise + transpose in ONE pass over A (n x pc, column-major):
+ *   codes[i*ldc + k] = int8(m * A[i + k*lda])   (row-major, locus fastest; columns [pc, ldc) are zero-filled
+ *                                                 when ldc covers them up to the next multiple of 128)
+ *   colsum[k]        = sum_i codes[i,k]           (int32, exact)
+ *   flags[0]        |= 1 if a cell is NaN, 2 if +-Inf, 4 if m*x is not an integer in [0,m]
+ * ldc (bytes per packed row) must be a multiple of 128. */
+int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda, int32_t m,
+                             int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags);
+
+/* Exact integer Gram matrix of the packed codes over the tiles owned by (rank, world):
+ *   C[i + j*ldC] = sum_k codes[i,k]*codes[j,k]   for every (i,j) inside an owned upper-triangular tile.
+ * int8 x int8 -> int32 on tcgen05 tensor cores (kind::i8), operands by TMA, accumulators in TMEM. */
+int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                         int32_t *d_C, int64_t ldC, int32_t rank, int32_t world);
+
+/* Same contraction with the FP64 epilogue fused:
+ *   G[i + j*ldg] = ((alpha*C_ij - beta*(u_i + u_j)) + gamma) / denom
+ * d_u may be NULL when beta == 0 (grmsimple: alpha = 1/m^2, denom = p). */
+int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                             double alpha, double beta, double gamma, double denom, const double *d_u,
+                             double *d_G, int64_t ldg, int32_t rank, int32_t world);
+
+/* u[i] = sum_k codes[i,k] * w[k]  in FP64, fixed summation order (bit-reproducible). */
+int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                           const double *d_w, double *d_u);
+
+/* Per-locus centre and scale of grmploidyaware from the integer column sums (calc.jl:197,201):
+ *   q[k] = (colsum[k]/m)/n ;  w[k] = ploidy/2 + q[k] ;  stats = { sum q(1-q), sum w^2, sum q }  (3 doubles) */
+int32_t grm_cuda_locus_stats_i8(grm_cuda_ctx *ctx, const int32_t *d_colsum, int64_t p, int64_t n, int32_t m,
+                                int32_t ploidy, double *d_q, double *d_w, double *d_stats);
+
+/* FP64 path: q[k] = mean_i A[i,k] with a fixed summation order; flags as in grm_cuda_pack_dosage (bits 1,2);
+ * stats = { sum q(1-q), 0, sum q }; accumulate != 0 adds to the existing stats (loci streamed in chunks). */
+int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
+                                 double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate);
+
+/* FP64 upper-triangular SYRK over owned tiles, raw sums (no division):
+ *   centred == 0: G (+)= A*A'            (grmsimple, calc.jl:127)
+ *   centred == 1: G (+)= Z*Z', z_ik = fl(fl(ploidy*fl(A_ik - 0.5)) - q_k) formed on operand load (calc.jl:198,205)
+ * accumulate != 0 adds to G (loci streamed in chunks).  FP64 tensor path (mma.sync m8n8k4.f64). */
+int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int32_t centred,
+                          double ploidy, const double *d_q, int32_t accumulate, double *d_G, int64_t ldg,
+                          int32_t rank, int32_t world);
+
+/* G[i,j] = G[i,j]/denom for i <= j, then G[j,i] = G[i,j] for i < j (whole matrix; exact symmetry). */
+int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom);
+/* Copy the upper triangle onto the lower one (scale_mirror with denom = 1). */
+int32_t grm_cuda_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg);
+
+/* Tile partition used by the sharded calls: tile edge in entries, tile count per side, and owner of tile
+ * (ti <= tj).  Pure host arithmetic; no device needed. */
+int32_t grm_cuda_tile_edge(void);
+int64_t grm_cuda_tile_count(int64_t n, int32_t rank, int32_t world);
+int32_t grm_cuda_tile_owner(int64_t n, int64_t ti, int64_t tj, int32_t world);
+/* (ti, tj) of the t-th tile owned by `rank` (t in [0, grm_cuda_tile_count)). */
+int32_t grm_cuda_tile_at(int64_t n, int32_t rank, int32_t world, int64_t t, int64_t *ti, int64_t *tj);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRM_CUDA_H */
