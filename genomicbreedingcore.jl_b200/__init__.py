@@ -5,10 +5,10 @@ The directory name contains a dot, so import it through the repo-root shim:  `im
 """
 from . import _lib, synth
 from ._lib import Context, GrmCudaError, default_context
-from .grm import grmploidyaware, grmsimple, inflatediagonals
+from .grm import grm_call, grmploidyaware, grmsimple, inflatediagonals
 from .structs import GRM, ArgumentError, ErrorException, Genomes, MissingDataError, checkdims, clone
 
 __all__ = [
-    "Context", "GrmCudaError", "default_context", "grmsimple", "grmploidyaware", "inflatediagonals", "GRM", "Genomes",
+    "Context", "GrmCudaError", "default_context", "grm_call", "grmsimple", "grmploidyaware", "inflatediagonals", "GRM", "Genomes",
     "ArgumentError", "ErrorException", "MissingDataError", "checkdims", "clone", "synth",
 ]

@@ -365,7 +365,9 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
         if (m == 0) {
             const double *d0;
             GRM_TRY(feed.acquire(0, &d0));
-            GRM_TRY(grm_cuda_detect_denominator(ctx, d0, n, feed.len(0), feed.ld_dev(), 0, &m));
+            // a sample decides (the first 2^22 cells); the pack pass verifies every cell against it and the loop
+            // below retries with m = 64 / falls back to FP64 if a later locus disagrees
+            GRM_TRY(grm_cuda_detect_denominator(ctx, d0, n, feed.len(0), feed.ld_dev(), 1ll << 22, &m));
         } else if (m < 1 || m > 64 || (m & (m - 1)) != 0) {
             grm_set_error("denominator must be a power of two in [1,64], got %d", m);
             return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -425,7 +427,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             if (!centred) {
                 denom = static_cast<double>(p);  // calc.jl:127
                 GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
-                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1.0 / (static_cast<double>(m) * m), 0.0, 0.0,
+                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, 1.0 / (static_cast<double>(m) * m), 0.0, 0.0,
                                              denom, nullptr, dG, ldG, o.rank, o.world));
             } else {
                 GRM_TRY(ctx->q.reserve(static_cast<size_t>(ldc) * sizeof(double)));
@@ -440,7 +442,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 denom = static_cast<double>(ploidy) * h_stats[0];  // calc.jl:201
                 const double s = static_cast<double>(ploidy) / static_cast<double>(m);
                 GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
-                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, s * s, s, h_stats[1], denom, ctx->u.as<double>(),
+                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, s * s, s, h_stats[1], denom, ctx->u.as<double>(),
                                              dG, ldG, o.rank, o.world));
             }
             GRM_CUDA_TRY(cudaEventRecord(ev[3], st));

@@ -123,6 +123,16 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, ui
         : "memory");
 }
 
+// 3D tiled load (loci, entries, slab)
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, uint64_t *bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ---- tcgen05 ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -47,11 +47,18 @@ __global__ void detect_kernel(const double *__restrict__ A, int64_t n, int64_t p
 //   smem : word tile [64 entries][32 words + 1 pad]  (conflict-free both ways)
 //   write: 8 threads x 16 bytes = one 128-byte line per entry row of the K-major code matrix
 // -------------------------------------------------------------------------------------------------------------
+// streaming 8-byte load: read-only path, do not allocate in L1 (every byte of A is touched exactly once)
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 constexpr int PK_LOCI = 128;
 constexpr int PK_SLAB = 64;
 
 template <int EITERS>
-__global__ void __launch_bounds__(256) pack_dosage_kernel(const double *__restrict__ A, int64_t n, int64_t pc,
+__global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__restrict__ A, int64_t n, int64_t pc,
                                                           int64_t lda, int m, int8_t *__restrict__ codes, int64_t ldc,
                                                           int32_t *__restrict__ colsum, uint32_t *__restrict__ flags) {
     __shared__ uint32_t tile[PK_SLAB][33];
@@ -71,27 +78,29 @@ __global__ void __launch_bounds__(256) pack_dosage_kernel(const double *__restri
         if (e0 >= n) break;
         const int64_t ea = e0 + lane, eb = e0 + lane + 32;
         const bool va = ea < n, vb = eb < n;
+        // all 32 loads of this slab first (256 bytes in flight per thread), then the arithmetic
+        double xa[16], xb[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t k = k0 + warp * 16 + j;
+            const bool vk = k < pc;
+            xa[j] = (vk && va) ? ld_stream(A + ea + k * lda) : 0.0;
+            xb[j] = (vk && vb) ? ld_stream(A + eb + k * lda) : 0.0;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            double xa[4], xb[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int64_t k = k0 + warp * 16 + g * 4 + kk;
-                const bool vk = k < pc;
-                xa[kk] = (vk && va) ? __ldg(A + ea + k * lda) : 0.0;
-                xb[kk] = (vk && vb) ? __ldg(A + eb + k * lda) : 0.0;
-            }
             uint32_t wa = 0, wb = 0;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const double ta = xa[kk] * mf, tb = xb[kk] * mf;
+                const double va_ = xa[g * 4 + kk], vb_ = xb[g * 4 + kk];
+                const double ta = va_ * mf, tb = vb_ * mf;
                 int ca = __double2int_rn(ta), cb = __double2int_rn(tb);
                 if (!(static_cast<double>(ca) == ta && ca >= 0 && ca <= m)) {
-                    bad |= (xa[kk] != xa[kk]) ? FLAG_NAN : (isinf(xa[kk]) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    bad |= (va_ != va_) ? FLAG_NAN : (isinf(va_) ? FLAG_INF : FLAG_NOT_DOSAGE);
                     ca = 0;
                 }
                 if (!(static_cast<double>(cb) == tb && cb >= 0 && cb <= m)) {
-                    bad |= (xb[kk] != xb[kk]) ? FLAG_NAN : (isinf(xb[kk]) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    bad |= (vb_ != vb_) ? FLAG_NAN : (isinf(vb_) ? FLAG_INF : FLAG_NOT_DOSAGE);
                     cb = 0;
                 }
                 wa |= static_cast<uint32_t>(ca) << (8 * kk);

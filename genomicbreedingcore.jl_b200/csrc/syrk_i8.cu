@@ -41,7 +41,7 @@ struct EpiParams {
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
-               EpiParams ep) {
+               int kb_per_slab, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
@@ -78,14 +78,19 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict_
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 const int2 tc = tiles[t];
+                int slab = 0, kin = 0;  // loci are stored as [slab][entry][locus-in-slab]
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *sA = smem + stage * STAGE_BYTES;
                     uint8_t *sB = sA + A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    tma_load_2d(sA, &tmap, &full_bar[stage], kb * BK, tc.x);
-                    tma_load_2d(sB, &tmap, &full_bar[stage], kb * BK, tc.y);
-                    tma_load_2d(sB + 128 * BK, &tmap, &full_bar[stage], kb * BK, tc.y + 128);
+                    tma_load_3d(sA, &tmap, &full_bar[stage], kin * BK, tc.x, slab);
+                    tma_load_3d(sB, &tmap, &full_bar[stage], kin * BK, tc.y, slab);
+                    tma_load_3d(sB + 128 * BK, &tmap, &full_bar[stage], kin * BK, tc.y + 128, slab);
+                    if (++kin == kb_per_slab) {
+                        kin = 0;
+                        ++slab;
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -185,7 +190,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, CUtensorMap *out) {
+int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -197,13 +202,14 @@ int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    // dim0 = loci (bytes, contiguous), dim1 = entries.  Out-of-range rows/loci are zero-filled by TMA, so ragged
-    // n (not a multiple of 128) and p (not a multiple of 128) contribute exact zeros to the integer sums.
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(n)};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ldc)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), 128u};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(d_codes), gdim, gstride, box, estr,
+    // dim0 = loci of one slab (bytes, contiguous), dim1 = entries, dim2 = slab.  Out-of-range rows/loci are
+    // zero-filled by TMA, so ragged n (not a multiple of 128) and p (not a multiple of 128) contribute exact zeros
+    // to the integer sums.
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(nslabs)};
+    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ldc), static_cast<cuuint64_t>(ldc) * static_cast<cuuint64_t>(n)};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), 128u, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(d_codes), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -245,16 +251,17 @@ int32_t get_tile_list(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world,
 }
 
 template <int EPI>
-int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, const EpiParams &ep,
-               int32_t rank, int32_t world) {
-    if (!ctx || !d_codes || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1 || rank < 0 || rank >= world) {
+int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs,
+               const EpiParams &ep, int32_t rank, int32_t world) {
+    if (!ctx || !d_codes || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || nslabs < 1 || world < 1 || rank < 0 ||
+        rank >= world) {
         grm_set_error("syrk_i8: bad argument (n=%lld p=%lld ldc=%lld rank=%d world=%d)", (long long)n, (long long)p,
                       (long long)ldc, rank, world);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     CUtensorMap tmap;
-    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, &tmap));
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
     const int2 *d_tiles;
     int count;
     GRM_TRY(get_tile_list(ctx, n, rank, world, &d_tiles, &count));
@@ -265,9 +272,10 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
                                           static_cast<int>(SMEM_BYTES)));
         attr_set[EPI] = true;
     }
-    const int num_kb = static_cast<int>((p + BK - 1) / BK);
+    const int kb_per_slab = static_cast<int>((p + BK - 1) / BK);
+    const int num_kb = kb_per_slab * static_cast<int>(nslabs);
     const int grid = std::min(count, ctx->num_sms);
-    syrk_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmap, d_tiles, count, num_kb, ep);
+    syrk_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmap, d_tiles, count, num_kb, kb_per_slab, ep);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
@@ -276,7 +284,7 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
 }  // namespace
 
 extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                    int32_t *d_C, int64_t ldC, int32_t rank, int32_t world) {
+                                    int64_t nslabs, int32_t *d_C, int64_t ldC, int32_t rank, int32_t world) {
     if (!d_C || ldC < n) {
         grm_set_error("syrk_i8: bad output (ldC=%lld n=%lld)", (long long)ldC, (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -285,11 +293,11 @@ extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, in
     ep.n = n;
     ep.C = d_C;
     ep.ldC = ldC;
-    return launch<0>(ctx, d_codes, n, p, ldc, ep, rank, world);
+    return launch<0>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
 }
 
 extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                        double alpha, double beta, double gamma, double denom, const double *d_u,
+                                        int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
                                         double *d_G, int64_t ldg, int32_t rank, int32_t world) {
     if (!d_G || ldg < n || (beta != 0.0 && !d_u)) {
         grm_set_error("syrk_i8_f64: bad output or missing u (ldg=%lld n=%lld)", (long long)ldg, (long long)n);
@@ -304,6 +312,6 @@ extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes
     ep.gamma = gamma;
     ep.denom = denom;
     ep.u = d_u;
-    if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, ep, rank, world);
-    return launch<2>(ctx, d_codes, n, p, ldc, ep, rank, world);
+    if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
+    return launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
 }

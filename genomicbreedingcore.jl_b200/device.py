@@ -63,24 +63,31 @@ def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int 
     return codes, colsum, flags
 
 
+def _slabs(codes):
+    if codes.dim() == 3:
+        return codes.shape[0], codes.shape[1], codes.shape[2]
+    return 1, codes.shape[0], codes.shape[1]
+
+
 def syrk_i8(ctx, codes, p: int, rank: int = 0, world: int = 1, out=None):
+    """codes: [n, ldc] or [nslabs, n, ldc] int8; p = valid loci per slab."""
     torch = _torch()
-    n, ldc = codes.shape
+    nslabs, n, ldc = _slabs(codes)
     if out is None:
         out = torch.zeros((n, n), dtype=torch.int32, device=codes.device)
     ctx.synchronize_with_torch()
-    _lib.check(ctx.lib.grm_cuda_syrk_i8(ctx.handle, _ptr(codes), n, p, ldc, _ptr(out), n, rank, world))
+    _lib.check(ctx.lib.grm_cuda_syrk_i8(ctx.handle, _ptr(codes), n, p, ldc, nslabs, _ptr(out), n, rank, world))
     return out
 
 
 def syrk_i8_f64(ctx, codes, p: int, alpha: float, beta: float, gamma: float, denom: float, u=None, rank: int = 0,
                 world: int = 1, out=None):
     torch = _torch()
-    n, ldc = codes.shape
+    nslabs, n, ldc = _slabs(codes)
     if out is None:
         out = torch.zeros((n, n), dtype=torch.float64, device=codes.device)
     ctx.synchronize_with_torch()
-    _lib.check(ctx.lib.grm_cuda_syrk_i8_f64(ctx.handle, _ptr(codes), n, p, ldc, alpha, beta, gamma, denom,
+    _lib.check(ctx.lib.grm_cuda_syrk_i8_f64(ctx.handle, _ptr(codes), n, p, ldc, nslabs, alpha, beta, gamma, denom,
                                             _ptr(u) if u is not None else None, _ptr(out), n, rank, world))
     return out
 

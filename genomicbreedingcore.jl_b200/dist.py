@@ -1,0 +1,161 @@
+"""Multi-GPU GRM: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+
+Decomposition (north_star):
+  * loci are split into `world` contiguous ranges; rank r holds (and, end to end, uploads over its own PCIe link)
+    only the FP64 columns of its range and packs them to int8 on its GPU — every input byte crosses PCIe once;
+  * the packed int8 slabs (n*p bytes in total — 1/8 of the FP64 input) and the integer column sums are all-gathered:
+    this is the one real exchange step of the path;
+  * the upper-triangular 256 x 256 output tiles are dealt to the ranks in contiguous runs of an L2-friendly order
+    (grm_cuda_tile_*); each rank runs the tcgen05 SYRK over its own tiles with all loci.  The integer Gram matrix
+    is exact under any partition, so results do not depend on the number of ranks;
+  * the finished tiles stay sharded; `gather()` sums the zero-padded local matrices onto every rank (each element is
+    written by exactly one rank, so the sum is exact) when a single-device copy is requested, e.g. for the repair.
+
+The exchange helpers take plain tensors and a process group, so they run under `gloo` on CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def loci_range(p: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous loci range of `rank`: equal slabs of ceil(p/world) loci (the last ones may be short or empty)."""
+    L = (p + world - 1) // world
+    return min(p, rank * L), min(p, (rank + 1) * L)
+
+
+def slab_stride(p: int, world: int) -> int:
+    """Bytes per packed row of one slab: ceil(p/world) rounded up to the 128-byte TMA/K-block granule."""
+    L = (p + world - 1) // world
+    return (L + 127) // 128 * 128
+
+
+def exchange_codes(codes_slab, colsum_slab, group=None):
+    """all-gather of the packed slabs and their column sums -> ([world, n, lds] int8, [world, lds] int32)."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    codes_all = torch.empty((world,) + tuple(codes_slab.shape), dtype=codes_slab.dtype, device=codes_slab.device)
+    colsum_all = torch.empty((world,) + tuple(colsum_slab.shape), dtype=colsum_slab.dtype, device=colsum_slab.device)
+    dist.all_gather_into_tensor(codes_all, codes_slab.contiguous(), group=group)
+    dist.all_gather_into_tensor(colsum_all, colsum_slab.contiguous(), group=group)
+    return codes_all, colsum_all
+
+
+def gather_tiles_sum(G_local, group=None):
+    """Every rank's local matrix is zero outside its own tiles; the sum over ranks is the full (upper) matrix."""
+    import torch.distributed as dist
+
+    dist.all_reduce(G_local, op=dist.ReduceOp.SUM, group=group)
+    return G_local
+
+
+class ShardedGRM:
+    """Per-rank driver of the sharded int8 path on device-resident loci slabs."""
+
+    def __init__(self, n: int, p: int, ploidy: Optional[int], denominator: int, ctx: _lib.Context, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+
+        self.n, self.p, self.ploidy, self.m = n, p, ploidy, denominator
+        self.ctx = ctx
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.k0, self.k1 = loci_range(p, self.rank, self.world)
+        self.lds = slab_stride(p, self.world)
+        self.L = (p + self.world - 1) // self.world
+        dev = torch.device("cuda", ctx.device)
+        self.codes_slab = torch.zeros((n, self.lds), dtype=torch.int8, device=dev)
+        self.colsum_slab = torch.zeros((self.lds,), dtype=torch.int32, device=dev)
+        self.codes_all = torch.zeros((self.world, n, self.lds), dtype=torch.int8, device=dev)
+        self.colsum_all = torch.zeros((self.world, self.lds), dtype=torch.int32, device=dev)
+        self.flags = torch.zeros((16,), dtype=torch.int32, device=dev)
+        self.G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        self.launches = 0
+        self._gathered = False
+
+    def step(self, A_slab_pn, timings: Optional[dict] = None):
+        """A_slab_pn: (k1-k0, n) contiguous FP64 CUDA tensor = this rank's loci, column-major n x pc.
+        Leaves this rank's tiles of the raw GRM in self.G (zeros elsewhere).  Runs on the context stream."""
+        torch = _torch()
+        import torch.distributed as dist
+
+        from . import device as D
+
+        ctx, n, p, m = self.ctx, self.n, self.p, self.m
+        pc = self.k1 - self.k0
+        with D.on_ctx_stream(ctx):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
+            if ev:
+                ev[0].record()
+            self.colsum_slab.zero_()
+            self.flags.zero_()
+            if self._gathered:  # other ranks' tiles were summed in by gather(): start from zeros again
+                self.G.zero_()
+                self._gathered = False
+            if pc > 0:
+                D.pack_dosage(ctx, A_slab_pn, m, codes=self.codes_slab, colsum=self.colsum_slab, flags=self.flags)
+                self.launches += 1
+            if ev:
+                ev[1].record()
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.codes_all, self.codes_slab, group=self.group)
+                dist.all_gather_into_tensor(self.colsum_all, self.colsum_slab, group=self.group)
+            else:
+                self.codes_all[0].copy_(self.codes_slab)
+                self.colsum_all[0].copy_(self.colsum_slab)
+            if ev:
+                ev[2].record()
+            if self.ploidy is None:
+                alpha, beta, gamma, denom, u = 1.0 / (m * m), 0.0, 0.0, float(p), None
+            else:
+                stats = torch.zeros((3,), dtype=torch.float64, device=self.G.device)
+                u = torch.zeros((n,), dtype=torch.float64, device=self.G.device)
+                for r in range(self.world):  # fixed slab order => same bits on every rank
+                    a, b = loci_range(p, r, self.world)
+                    if b <= a:
+                        continue
+                    q, w, st = D.locus_stats_i8(ctx, self.colsum_all[r], b - a, n, m, self.ploidy)
+                    stats += st
+                    u += D.rowdot_i8(ctx, self.codes_all[r], b - a, w)
+                    self.launches += 3
+                h = stats.cpu()
+                s = self.ploidy / m
+                alpha, beta, gamma, denom = s * s, s, float(h[1]), self.ploidy * float(h[0])
+            self.scale = denom
+            if ev:
+                ev[3].record()
+            D.syrk_i8_f64(ctx, self.codes_all, min(self.L, p), alpha, beta, gamma, denom, u, rank=self.rank,
+                          world=self.world, out=self.G)
+            self.launches += 1
+            if ev:
+                ev[4].record()
+                ev[4].synchronize()
+                for name, i in (("ms_pack", 0), ("ms_exchange", 1), ("ms_rowdot", 2), ("ms_syrk", 3)):
+                    timings[name] = timings.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
+        flags = int(self.flags[0])
+        if flags:
+            raise _lib.GrmCudaError(_lib.ERR_MISSING if flags & 1 else _lib.ERR_NONFINITE if flags & 2
+                                    else _lib.ERR_NOT_DOSAGE, f"input flags {flags} on rank {self.rank}")
+        return self.G
+
+    def gather(self):
+        """Single-device copy on every rank: sum of the zero-padded tile sets, then mirror."""
+        from . import device as D
+
+        with D.on_ctx_stream(self.ctx):
+            if self.world > 1:
+                gather_tiles_sum(self.G, self.group)
+            D.scale_mirror(self.ctx, self.G, 1.0)
+        self._gathered = True
+        return self.G

@@ -27,42 +27,54 @@ def _raise_for(err: _lib.GrmCudaError):
     raise err
 
 
-def _colmajor(a: np.ndarray) -> np.ndarray:
-    a = np.asarray(a)
-    if a.dtype != np.float64 or not a.flags.f_contiguous:
-        a = np.asfortranarray(a, dtype=np.float64)
-    return a
+def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.Context] = None,
+             path: int = _lib.PATH_AUTO, denominator: int = 0, max_iter: int = 1_000, skip_repair: bool = False,
+             chunk_loci: int = 0, rank: int = 0, world: int = 1, out: Optional[np.ndarray] = None):
+    """The C-ABI call a Julia `ccall` shim makes, on host buffers: grm_cuda_simple (ploidy is None) or
+    grm_cuda_ploidyaware.  `A` is n x p (NaN = missing); a strided view of a larger Fortran array is passed with its
+    leading dimension, no copy.  Returns (G, info dict).  Raises GrmCudaError with the library status."""
+    ctx = ctx or _lib.default_context()
+    A = np.asarray(A)
+    if A.dtype != np.float64 or A.ndim != 2 or A.strides[0] != 8 or (A.shape[1] > 1 and A.strides[1] % 8) \
+            or (A.shape[1] > 1 and A.strides[1] < 8 * A.shape[0]):
+        A = np.asfortranarray(A, dtype=np.float64)
+    n, p = A.shape
+    lda = A.strides[1] // 8 if p > 1 else n
+    if out is None:
+        out = np.empty((n, n), dtype=np.float64, order="F")  # calc.jl:123
+        if world > 1:
+            out[...] = 0.0
+    ldg = out.strides[1] // 8 if n > 1 else n
+    o = _lib.default_options()
+    o.path, o.denominator, o.max_iter = path, denominator, int(max_iter)
+    o.skip_repair = 1 if skip_repair else 0
+    o.chunk_loci = int(chunk_loci)
+    o.rank, o.world = rank, world
+    info = _lib.new_info()
+    if ploidy is None:
+        st = ctx.lib.grm_cuda_simple(ctx.handle, A.ctypes.data, n, p, lda, out.ctypes.data, ldg, C.byref(o),
+                                     C.byref(info))
+    else:
+        st = ctx.lib.grm_cuda_ploidyaware(ctx.handle, A.ctypes.data, n, p, lda, int(ploidy), out.ctypes.data, ldg,
+                                          C.byref(o), C.byref(info))
+    _lib.check(st)
+    return out, info.as_dict()
 
 
 def _run(genomes: Genomes, centred: bool, ploidy: int, max_iter: int, verbose: bool, ctx, path, denominator,
          skip_repair) -> GRM:
     if not checkdims(genomes):
         raise ArgumentError("The Genomes struct is corrupted ☹.")  # calc.jl:118-120, :191-193
-    ctx = ctx or _lib.default_context()
-    A = _colmajor(genomes.allele_frequencies)
-    n, p = A.shape
-    G = np.empty((n, n), dtype=np.float64, order="F")  # calc.jl:123
-    o = _lib.default_options()
-    o.path = path
-    o.denominator = denominator
-    o.max_iter = int(max_iter)
-    o.skip_repair = 1 if skip_repair else 0
-    info = _lib.new_info()
-    lib = ctx.lib
     try:
-        if centred:
-            _lib.check(lib.grm_cuda_ploidyaware(ctx.handle, A.ctypes.data, n, p, n, int(ploidy), G.ctypes.data, n,
-                                                C.byref(o), C.byref(info)))
-        else:
-            _lib.check(lib.grm_cuda_simple(ctx.handle, A.ctypes.data, n, p, n, G.ctypes.data, n, C.byref(o),
-                                           C.byref(info)))
+        G, info = grm_call(genomes.allele_frequencies, ploidy if centred else None, ctx=ctx, path=path,
+                           denominator=denominator, max_iter=max_iter, skip_repair=skip_repair)
     except _lib.GrmCudaError as e:
         _raise_for(e)
     if verbose:  # calc.jl:67-69
-        print(f"Performed {info.repair_iters} iterations of diagonal inflation to ensure matrix invertibility "
-              f"(ϵ_total = {info.eps_total}).")
+        print(f"Performed {info['repair_iters']} iterations of diagonal inflation to ensure matrix invertibility "
+              f"(ϵ_total = {info['eps_total']}).")
     # entries / loci_alleles alias the input vectors, like calc.jl:123,196
-    grm = GRM(genomes.entries, genomes.loci_alleles, G, info=info.as_dict())
+    grm = GRM(genomes.entries, genomes.loci_alleles, G, info=info)
     if not centred and not checkdims(grm):
         raise ErrorException("Error computing a simple GRM.")  # calc.jl:135-137
     return grm

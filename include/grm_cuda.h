@@ -144,15 +144,17 @@ int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int
 
 /* Exact integer Gram matrix of the packed codes over the tiles owned by (rank, world):
  *   C[i + j*ldC] = sum_k codes[i,k]*codes[j,k]   for every (i,j) inside an owned upper-triangular tile.
- * int8 x int8 -> int32 on tcgen05 tensor cores (kind::i8), operands by TMA, accumulators in TMEM. */
+ * int8 x int8 -> int32 on tcgen05 tensor cores (kind::i8), operands by TMA, accumulators in TMEM.
+ * The loci may be stored as `nslabs` consecutive slabs [slab][entry][ldc] of p loci each (the layout an
+ * all-gather of per-GPU packed loci ranges produces); nslabs = 1 is the plain n x ldc matrix. */
 int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                         int32_t *d_C, int64_t ldC, int32_t rank, int32_t world);
+                         int64_t nslabs, int32_t *d_C, int64_t ldC, int32_t rank, int32_t world);
 
 /* Same contraction with the FP64 epilogue fused:
  *   G[i + j*ldg] = ((alpha*C_ij - beta*(u_i + u_j)) + gamma) / denom
  * d_u may be NULL when beta == 0 (grmsimple: alpha = 1/m^2, denom = p). */
 int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                             double alpha, double beta, double gamma, double denom, const double *d_u,
+                             int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
                              double *d_G, int64_t ldg, int32_t rank, int32_t world);
 
 /* u[i] = sum_k codes[i,k] * w[k]  in FP64, fixed summation order (bit-reproducible). */

@@ -1,0 +1,329 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs,
+against the committed golden vectors, and — at BASELINE.json's full sizes — through size-independent properties.
+
+Bars (north_star): integer X X' bit-exact; final Float64 GRM within 1e-12 relative on the int8 path and 1e-10 on the
+FP64 path (relative to max |G|); for power-of-two dosages grmsimple is bit-identical.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import grm_b200
+from grm_b200 import (ArgumentError, Genomes, MissingDataError, _lib, grm_call, grmploidyaware, grmsimple,
+                      inflatediagonals, synth)
+from oracle import oracle as O
+
+RTOL_I8 = 1e-12   # north_star: final GRM within 1e-12 relative (int8 path)
+RTOL_F64 = 1e-10  # north_star: 1e-10 relative (FP64 path)
+EPS = np.finfo(np.float64).eps
+
+
+def relerr(G, ref):
+    return np.abs(G - ref).max() / np.abs(ref).max()
+
+
+def dev():
+    import torch
+
+    return torch.device("cuda", 0)
+
+
+def to_dev(A):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(A).T)).to(dev())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors
+# ---------------------------------------------------------------------------------------------------------------
+DOSAGE_CASES = ["dip", "tet", "dip_as_tet", "wide"]
+CONT_CASES = ["cont", "unif"]
+
+
+@pytest.mark.parametrize("name", DOSAGE_CASES + CONT_CASES)
+def test_golden_raw_and_final(golden, name):
+    A = golden[f"{name}_A"]
+    ploidy = int(golden[f"{name}_ploidy"])
+    is_dosage = name in DOSAGE_CASES
+    tol = RTOL_I8 if is_dosage else RTOL_F64
+    G, info = grm_call(A, skip_repair=True)
+    assert info["path"] == (_lib.PATH_I8 if is_dosage else _lib.PATH_F64)
+    ref = golden[f"{name}_simple_raw"]
+    if is_dosage:
+        assert np.array_equal(G, ref), "grmsimple on power-of-two dosages must be bit-identical"
+    assert relerr(G, ref) <= tol
+    assert np.array_equal(G, G.T)
+    G, info = grm_call(A, ploidy, skip_repair=True)
+    assert relerr(G, golden[f"{name}_ploidy_raw"]) <= tol
+    assert abs(info["scale"] - float(golden[f"{name}_d"])) <= 1e-14 * info["scale"]
+    assert np.array_equal(G, G.T)
+    # with the repair: same number of rounds, same total, same matrix
+    for pl, kind in ((None, "simple"), (ploidy, "ploidy")):
+        G, info = grm_call(A, pl)
+        it, tot = golden[f"{name}_{kind}_repair"]
+        assert info["repair_iters"] == int(it)
+        assert abs(info["eps_total"] - tot) <= tol * max(1.0, abs(tot))
+        assert relerr(G, golden[f"{name}_{kind}_final"]) <= tol
+        assert np.array_equal(G, G.T)
+
+
+def test_golden_inflatediagonals_docstring_example(golden):
+    X = np.array(golden["rank1_X"], order="F")
+    inflatediagonals(X)
+    it, tot = golden["rank1_repair"]
+    assert relerr(X, golden["rank1_out"]) <= 1e-15
+    assert O.np_det_julia(X) > EPS  # calc.jl:37-38
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# P2/P3: integer Gram exactness, ragged shapes (non-multiples of the 128/256 tiles and of K = 32 / 128)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p,m", [(2, 2, 1), (2, 33, 2), (100, 10_000, 2), (257, 33, 4), (257, 10_000, 4),
+                                   (300, 4097, 2), (513, 129, 64), (1, 17, 2), (1000, 2, 4)])
+def test_integer_gram_bit_exact(ctx, n, p, m):
+    from grm_b200 import device as D
+
+    A = synth.dosage(n, p, m, seed=1000 + n + p)
+    codes_ref = O.dosage_codes(A, m)
+    At = to_dev(A)
+    assert D.detect_denominator(ctx, At) in {1, 2, 4, 8, 16, 32, 64} and m % D.detect_denominator(ctx, At) == 0
+    codes, colsum, flags = D.pack_dosage(ctx, At, m)
+    C = D.syrk_i8(ctx, codes, p)
+    ctx.synchronize()
+    assert int(flags[0]) == 0
+    assert np.array_equal(codes.cpu().numpy()[:, :p], codes_ref.astype(np.int8))
+    assert not codes.cpu().numpy()[:, p:].any()
+    assert np.array_equal(colsum.cpu().numpy()[:p], codes_ref.sum(0))
+    ref = O.np_gram_int(codes_ref)
+    got = C.cpu().numpy().T.astype(np.int64)  # [i, j] = C[i + j*n]
+    iu = np.triu_indices(n)
+    assert np.array_equal(got[iu], ref[iu])
+    # P3: final grmsimple through the C ABI is bit-identical to the sequential-dot reference
+    G, info = grm_call(A, skip_repair=True)
+    assert info["path"] == _lib.PATH_I8
+    assert np.array_equal(G, (ref.astype(np.float64) / (m * m)) / p)
+    if n * p <= 3_000_000:
+        st, Gc = O.c_grmsimple_raw(A, nthreads=4)
+        assert st == O.OK and np.array_equal(G, Gc)
+
+
+# P4: grmploidyaware on dosages, including ploidy != denominator
+@pytest.mark.parametrize("n,p,m,ploidy", [(100, 10_000, 2, 2), (257, 3000, 4, 4), (64, 5000, 2, 4), (130, 777, 4, 2),
+                                          (50, 400, 2, 6)])
+def test_ploidyaware_dosage(ctx, n, p, m, ploidy):
+    from grm_b200 import device as D
+
+    A = synth.dosage(n, p, m, seed=2000 + n)
+    st, Gc, qc, dc = O.c_grmploidyaware_raw(A, ploidy, nthreads=4)
+    G, info = grm_call(A, ploidy, skip_repair=True)
+    assert info["path"] == _lib.PATH_I8
+    assert relerr(G, Gc) <= RTOL_I8
+    T, _, _ = O.np_truth_ploidyaware(A, ploidy)
+    assert relerr(G, T) <= RTOL_I8
+    assert abs(info["scale"] - dc) <= 1e-14 * dc
+    # q bit-exact (column sums of power-of-two dosages are exact in any order)
+    At = to_dev(A)
+    codes, colsum, flags = D.pack_dosage(ctx, At, info["denominator"])
+    q, w, stats = D.locus_stats_i8(ctx, colsum, p, n, info["denominator"], ploidy)
+    ctx.synchronize()
+    assert np.array_equal(q.cpu().numpy(), qc)
+
+
+# P5: continuous FP64 path
+@pytest.mark.parametrize("n,p,gen", [(100, 10_000, "continuous"), (257, 1000, "continuous"), (123, 5000, "uniform"),
+                                     (130, 17, "continuous")])
+def test_fp64_path(n, p, gen):
+    A = getattr(synth, gen)(n, p, seed=3000 + n)
+    G, info = grm_call(A, skip_repair=True)
+    assert info["path"] == _lib.PATH_F64
+    st, Gc = O.c_grmsimple_raw(A, nthreads=4)
+    assert relerr(G, Gc) <= RTOL_F64
+    assert relerr(G, O.np_truth_simple(A)) <= 1e-13
+    for ploidy in (2, 4):
+        G, info = grm_call(A, ploidy, skip_repair=True)
+        st, Gc, qc, dc = O.c_grmploidyaware_raw(A, ploidy, nthreads=4)
+        assert relerr(G, Gc) <= RTOL_F64
+        assert relerr(G, O.np_truth_ploidyaware(A, ploidy)[0]) <= 1e-12
+        assert abs(info["scale"] - dc) <= 1e-13 * dc
+        assert np.array_equal(G, G.T)
+
+
+# P1: the reference's doctest properties through the reference-shaped API
+@pytest.mark.parametrize("gen", ["continuous", "dosage"])
+def test_reference_doctest_properties(gen):
+    A = synth.continuous(100, 1000, seed=42) if gen == "continuous" else synth.dosage(100, 1000, 2, seed=42)
+    g = Genomes.from_matrix(A)
+    for grm in (grmsimple(g), grmploidyaware(g)):
+        G = grm.genomic_relationship_matrix
+        assert G.shape == (100, 100) and np.array_equal(G, G.T)  # calc.jl:108-109
+        assert O.np_det_julia(G) > EPS  # calc.jl:111-112
+        assert grm.entries is g.entries and grm.loci_alleles is g.loci_alleles  # aliased, calc.jl:123
+
+
+# P6: repair decisions incl. det under/overflow
+def test_repair_matches_oracle_on_config_like_inputs():
+    for gen, n, p in (("continuous", 300, 2000), ("dosage", 300, 2000), ("continuous", 600, 3000)):
+        A = synth.continuous(n, p, seed=7) if gen == "continuous" else synth.dosage(n, p, 2, seed=7)
+        for ploidy in (None, 2):
+            Graw, _ = grm_call(A, ploidy, skip_repair=True)
+            st, X, it, tot = O.np_inflatediagonals(Graw)
+            G, info = grm_call(A, ploidy)
+            assert info["repair_iters"] == it
+            assert abs(info["eps_total"] - tot) <= 1e-15 * max(tot, 1.0)
+            assert np.array_equal(G, X), "same rounds on the same raw matrix => identical diagonal, untouched rest"
+
+
+def test_repair_edge_cases():
+    n = 400
+    half = np.asfortranarray(np.eye(n) * 0.5)  # SPD but det underflows below eps: one round
+    inflatediagonals(half)
+    assert np.array_equal(half, np.eye(n))
+    big = np.asfortranarray(np.eye(n) * 1e3)  # det overflows to Inf > eps: untouched
+    inflatediagonals(big)
+    assert np.array_equal(big, np.eye(n) * 1e3)
+    rng = np.random.default_rng(5)
+    B = rng.random((6, 6))
+    with pytest.raises(ArgumentError, match="not symmetric"):
+        inflatediagonals(np.asfortranarray(B))
+    S = B + B.T
+    S[2, 3] = S[3, 2] = np.nan
+    with pytest.raises(ArgumentError, match="not symmetric"):  # NaN != NaN, calc.jl:43
+        inflatediagonals(np.asfortranarray(S))
+    S = -(B @ B.T)
+    S[1, 4] = S[4, 1] = np.inf
+    with pytest.raises(ArgumentError, match="Inf"):
+        inflatediagonals(np.asfortranarray(S))
+    S = np.asfortranarray(-np.eye(4))
+    inflatediagonals(S, max_iter=0)
+    assert np.array_equal(S, -np.eye(4))
+    inflatediagonals(S)
+    assert O.np_isposdef(S)
+    one = np.array([[0.0]])
+    inflatediagonals(one)  # ϵ = max|X| = 0: the loop adds 0 until max_iter; no error (calc.jl:61)
+    assert one[0, 0] == 0.0
+
+
+# P7: error paths
+def test_error_paths():
+    A = synth.dosage(40, 300, 2, seed=11)
+    g = Genomes.from_matrix(synth.add_missing(A, 0.01, seed=1))
+    for fn in (grmsimple, grmploidyaware):
+        with pytest.raises(MissingDataError):
+            fn(g)
+    Ac = synth.add_missing(synth.continuous(40, 300, seed=11), 0.01, seed=1)
+    with pytest.raises(MissingDataError):
+        grmsimple(Genomes.from_matrix(Ac))
+    Ai = np.array(A, order="F")
+    Ai[3, 5] = np.inf
+    with pytest.raises(ArgumentError):
+        grmsimple(Genomes.from_matrix(Ai))
+    # all loci fixed: q(1-q) = 0 => d = 0 => NaN matrix => the reference's issymmetric check throws (calc.jl:43)
+    fixed = np.ones((5, 40), order="F")
+    with pytest.raises(ArgumentError, match="not symmetric"):
+        grmploidyaware(Genomes.from_matrix(fixed))
+    with pytest.raises(_lib.GrmCudaError) as e:
+        grm_call(synth.continuous(10, 50, seed=1), path=_lib.PATH_I8)
+    assert e.value.status == _lib.ERR_NOT_DOSAGE
+    # n = 1
+    G, info = grm_call(synth.dosage(1, 50, 2, seed=2), skip_repair=True)
+    assert G.shape == (1, 1)
+
+
+# P9: ordering follows the input order of entries
+def test_row_order_follows_entries():
+    A = synth.dosage(60, 500, 4, seed=13)
+    perm = np.random.default_rng(0).permutation(60)
+    G, _ = grm_call(A, 4, skip_repair=True)
+    Gp, _ = grm_call(np.asfortranarray(A[perm]), 4, skip_repair=True)
+    assert np.array_equal(Gp, G[np.ix_(perm, perm)])
+
+
+def test_leading_dimensions_and_chunked_streaming():
+    big = np.zeros((150, 900), order="F")
+    A = synth.dosage(130, 900, 2, seed=17)
+    big[:130] = A
+    view = big[:130]  # lda = 150
+    G0, _ = grm_call(A, 2, skip_repair=True)
+    G1, _ = grm_call(view, 2, skip_repair=True)
+    assert np.array_equal(G0, G1)
+    G2, i2 = grm_call(A, 2, skip_repair=True, chunk_loci=128)  # 8 chunks, double-buffered H2D
+    assert np.array_equal(G0, G2)
+    out = np.zeros((140, 130), order="F")[:130]  # ldg = 140
+    G3, _ = grm_call(A, 2, skip_repair=True, out=out)
+    assert np.array_equal(G0, G3)
+    Ac = synth.continuous(130, 900, seed=18)
+    F0, _ = grm_call(Ac, 2, skip_repair=True)
+    F1, _ = grm_call(Ac, 2, skip_repair=True, chunk_loci=128)
+    assert relerr(F1, F0) <= 1e-13
+
+
+def test_denominator_detection_fallbacks():
+    # first chunk looks diploid, a later chunk holds quarter dosages: retried at m = 64, still exact
+    A = np.asfortranarray(np.hstack([synth.dosage(70, 256, 2, seed=1), synth.dosage(70, 256, 4, seed=2)]))
+    G, info = grm_call(A, skip_repair=True, chunk_loci=128)
+    assert info["path"] == _lib.PATH_I8
+    assert np.array_equal(G, O.np_grmsimple_raw_dosage(A, 4))
+    # first chunk dosage, later chunk continuous: falls back to the FP64 path
+    B = np.asfortranarray(np.hstack([synth.dosage(70, 256, 2, seed=1), synth.continuous(70, 256, seed=2)]))
+    G, info = grm_call(B, skip_repair=True, chunk_loci=128)
+    assert info["path"] == _lib.PATH_F64
+    assert relerr(G, O.c_grmsimple_raw(B)[1]) <= RTOL_F64
+
+
+# P8: tile sharding, emulated ranks on one GPU
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_tiles_union_is_bit_identical(world):
+    A = synth.dosage(1100, 700, 4, seed=21)  # 5 x 5 tiles of 256
+    full, _ = grm_call(A, 4, skip_repair=True)
+    acc = np.zeros_like(full)
+    for r in range(world):
+        part, info = grm_call(A, 4, skip_repair=True, rank=r, world=world)
+        assert info["tiles"] == _lib.load().grm_cuda_tile_count(1100, r, world)
+        assert not (np.triu(acc != 0) & np.triu(part != 0)).any(), "tiles of different ranks overlap"
+        acc += part
+    iu = np.triu_indices(1100)
+    assert np.array_equal(acc[iu], full[iu])
+    Ac = synth.continuous(600, 500, seed=22)
+    fullc, info = grm_call(Ac, None, skip_repair=True)
+    accc = np.zeros_like(fullc)
+    for r in range(world):
+        part, _ = grm_call(Ac, None, skip_repair=True, rank=r, world=world)
+        accc += part
+    iu = np.triu_indices(600)
+    assert relerr(accc[iu] / 500.0, fullc[iu]) <= 1e-13  # sharded FP64 calls return raw sums
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size (BASELINE C2) properties: a checksum of checksums for the integer Gram matrix
+#   sum_j C_ij = sum_k c_ik S_k ,  C_ii = sum_k c_ik^2 ,  sum_ij C_ij = sum_k S_k^2      (S_k = column sums)
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_c2_integer_properties(ctx):
+    import torch
+
+    from grm_b200 import device as D
+
+    n, p, m = 5000, 100_000, 2
+    At = synth.dosage_device(n, p, m, 7, dev())
+    torch.cuda.synchronize()
+    codes, colsum, flags = D.pack_dosage(ctx, At, m)
+    C = D.syrk_i8(ctx, codes, p)
+    G, info = D.grm_device(ctx, At, None, skip_repair=True)
+    ctx.synchronize()
+    assert int(flags[0]) == 0 and info["path"] == _lib.PATH_I8 and info["denominator"] == 2
+    assert torch.equal(codes[:, :p].T.double() / m, At)  # round trip of the quantiser
+    Cfull = torch.triu(C.T.long()) + torch.triu(C.T.long(), 1).T  # mirror the upper triangle
+    S = colsum[:p].long()
+    assert torch.equal(S, codes[:, :p].long().sum(0))
+    cl = codes[:, :p].double()
+    rows = (cl @ S.double()).long()  # exact: all partial sums < 2^53
+    assert torch.equal(Cfull.sum(1), rows)
+    assert torch.equal(torch.diagonal(Cfull), (cl * cl).sum(1).long())
+    assert int(Cfull.sum()) == int((S * S).sum())
+    # independent library cross-check of every element (cuBLASLt int8 GEMM; comparator only)
+    ref = torch._int_mm(codes[:, :p].contiguous(), codes[:, :p].T.contiguous())
+    assert torch.equal(torch.triu(C.T), torch.triu(ref))
+    # final matrix: exactly C/m^2/p, exactly symmetric
+    assert torch.equal(G, (Cfull.double() / (m * m)) / p)
+    assert torch.equal(G, G.T)
