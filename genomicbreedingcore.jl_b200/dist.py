@@ -46,8 +46,9 @@ def exchange_codes(codes_slab, colsum_slab, group=None):
     world = dist.get_world_size(group)
     codes_all = torch.empty((world,) + tuple(codes_slab.shape), dtype=codes_slab.dtype, device=codes_slab.device)
     colsum_all = torch.empty((world,) + tuple(colsum_slab.shape), dtype=colsum_slab.dtype, device=colsum_slab.device)
-    dist.all_gather_into_tensor(codes_all, codes_slab.contiguous(), group=group)
-    dist.all_gather_into_tensor(colsum_all, colsum_slab.contiguous(), group=group)
+    # output viewed as the dim-0 concatenation of the inputs (the shape gloo insists on; NCCL only counts elements)
+    dist.all_gather_into_tensor(codes_all.view((-1,) + tuple(codes_slab.shape[1:])), codes_slab.contiguous(), group=group)
+    dist.all_gather_into_tensor(colsum_all.view(-1), colsum_slab.contiguous(), group=group)
     return codes_all, colsum_all
 
 
@@ -109,8 +110,8 @@ class ShardedGRM:
             if ev:
                 ev[1].record()
             if self.world > 1:
-                dist.all_gather_into_tensor(self.codes_all, self.codes_slab, group=self.group)
-                dist.all_gather_into_tensor(self.colsum_all, self.colsum_slab, group=self.group)
+                dist.all_gather_into_tensor(self.codes_all.view(-1, self.lds), self.codes_slab, group=self.group)
+                dist.all_gather_into_tensor(self.colsum_all.view(-1), self.colsum_slab, group=self.group)
             else:
                 self.codes_all[0].copy_(self.codes_slab)
                 self.colsum_all[0].copy_(self.colsum_slab)

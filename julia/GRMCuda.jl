@@ -1,0 +1,138 @@
+# GRMCuda.jl — Julia `ccall` shim over libgrm_cuda (include/grm_cuda.h).
+#
+# Gives the B200 backend the reference's exact signatures (GenomicBreedingCore.jl src/grm/calc.jl):
+#     grmsimple(genomes::Genomes; max_iter::Int64 = 1_000, verbose::Bool = false)::GRM                        # :115
+#     grmploidyaware(genomes::Genomes; ploidy::Int64 = 2, max_iter::Int64 = 1_000, verbose::Bool = false)::GRM # :189
+#     inflatediagonals!(X::Matrix{Float64}; max_iter::Int64 = 1_000, verbose::Bool = false)::Nothing          # :41
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image or on the GPU boxes.  The Python
+# ctypes binding (genomicbreedingcore.jl_b200/_lib.py) makes the same calls with the same argument order and is what
+# the tests drive.  julia/selftest.jl runs the reference and this shim side by side where Julia is available.
+module GRMCuda
+
+using GenomicBreedingCore: Genomes, GRM, checkdims
+
+const LIB = get(ENV, "GRM_CUDA_LIB", joinpath(@__DIR__, "..", "genomicbreedingcore.jl_b200", "libgrm_cuda.so"))
+
+# mirrors of grm_cuda_options / grm_cuda_info (include/grm_cuda.h)
+Base.@kwdef mutable struct Options
+    struct_size::Int32 = 48
+    path::Int32 = 0
+    denominator::Int32 = 0
+    max_iter::Int32 = 1000
+    skip_repair::Int32 = 0
+    input_location::Int32 = 0
+    output_location::Int32 = 0
+    rank::Int32 = 0
+    world::Int32 = 1
+    reserved0::Int32 = 0
+    chunk_loci::Int64 = 0
+end
+
+Base.@kwdef mutable struct Info
+    struct_size::Int32 = 80
+    path::Int32 = 0
+    denominator::Int32 = 0
+    repair_iters::Int32 = 0
+    eps_total::Float64 = 0.0
+    scale::Float64 = 0.0
+    tiles::Int64 = 0
+    ms_h2d::Float32 = 0
+    ms_pack::Float32 = 0
+    ms_rowdot::Float32 = 0
+    ms_syrk::Float32 = 0
+    ms_finalize::Float32 = 0
+    ms_repair::Float32 = 0
+    ms_d2h::Float32 = 0
+    ms_total::Float32 = 0
+    kernel_launches::Int32 = 0
+    reserved0::Int32 = 0
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function context()::Ptr{Cvoid}
+    if CTX[] == C_NULL
+        dev = parse(Int32, get(ENV, "GRM_CUDA_DEVICE", "0"))
+        st = ccall((:grm_cuda_ctx_create, LIB), Int32, (Int32, Ptr{Ptr{Cvoid}}), dev, CTX)
+        st == 0 || error("libgrm_cuda: " * unsafe_string(ccall((:grm_cuda_last_error, LIB), Cstring, ())))
+    end
+    CTX[]
+end
+
+lasterror() = unsafe_string(ccall((:grm_cuda_last_error, LIB), Cstring, ()))
+
+# status -> the exception type the reference raises at the corresponding place
+function throwstatus(st::Int32)
+    msg = lasterror()
+    if st == 2
+        # the reference fails with a MethodError(convert, (Float64, missing)) inside a TaskFailedException (calc.jl:127)
+        throw(MethodError(convert, (Float64, missing)))
+    elseif st in (1, 3, 4, 5, 6, 9, 10)
+        throw(ArgumentError(msg))
+    else
+        throw(ErrorException("libgrm_cuda status $st: $msg"))
+    end
+end
+
+# Matrix{Union{Float64,Missing}} has no zero-copy Ptr{Float64} view (payloads and selector bytes are stored
+# separately), so the shim makes one pass: missing -> NaN.  A Matrix{Float64} is passed as is.
+dense(A::Matrix{Float64}) = A
+dense(A::AbstractMatrix) = Float64[ismissing(x) ? NaN : Float64(x) for x in A]
+
+function rungrm(genomes::Genomes, centred::Bool, ploidy::Int64, max_iter::Int64, verbose::Bool)::GRM
+    if !checkdims(genomes)
+        throw(ArgumentError("The Genomes struct is corrupted ☹."))          # calc.jl:118-120, :191-193
+    end
+    A = dense(genomes.allele_frequencies)
+    n, p = size(A)
+    grm = GRM(genomes.entries, genomes.loci_alleles, Matrix{Float64}(undef, n, n))   # calc.jl:123, :196
+    G = grm.genomic_relationship_matrix
+    opts = Options(max_iter = Int32(max_iter))
+    info = Info()
+    st = GC.@preserve A G begin
+        if centred
+            ccall((:grm_cuda_ploidyaware, LIB), Int32,
+                  (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int32, Ptr{Float64}, Int64, Ref{Options}, Ref{Info}),
+                  context(), A, n, p, n, Int32(ploidy), G, n, opts, info)
+        else
+            ccall((:grm_cuda_simple, LIB), Int32,
+                  (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Options}, Ref{Info}),
+                  context(), A, n, p, n, G, n, opts, info)
+        end
+    end
+    st == 0 || throwstatus(st)
+    if verbose                                                                    # calc.jl:67-69
+        println("Performed $(info.repair_iters) iterations of diagonal inflation to ensure matrix invertibility (ϵ_total = $(info.eps_total)).")
+    end
+    if !centred && !checkdims(grm)
+        throw(ErrorException("Error computing a simple GRM."))                   # calc.jl:135-137
+    end
+    grm
+end
+
+grmsimple(genomes::Genomes; max_iter::Int64 = 1_000, verbose::Bool = false)::GRM =
+    rungrm(genomes, false, 0, max_iter, verbose)
+
+grmploidyaware(genomes::Genomes; ploidy::Int64 = 2, max_iter::Int64 = 1_000, verbose::Bool = false)::GRM =
+    rungrm(genomes, true, ploidy, max_iter, verbose)
+
+function inflatediagonals!(X::Matrix{Float64}; max_iter::Int64 = 1_000, verbose::Bool = false)::Nothing
+    if size(X, 1) != size(X, 2)
+        # calc.jl:43 runs issymmetric before the squareness check, so this is the message a caller sees
+        throw(ArgumentError("The input matrix is not symmetric."))
+    end
+    n = size(X, 1)
+    iters = Ref{Int32}(0)
+    total = Ref{Float64}(0.0)
+    st = GC.@preserve X ccall((:grm_cuda_inflate_diagonals, LIB), Int32,
+                              (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int32, Int32, Ref{Int32}, Ref{Float64}),
+                              context(), X, n, n, Int32(max_iter), Int32(0), iters, total)
+    st == 0 || throwstatus(st)
+    if verbose
+        println("Performed $(iters[]) iterations of diagonal inflation to ensure matrix invertibility (ϵ_total = $(total[])).")
+    end
+    nothing
+end
+
+end # module

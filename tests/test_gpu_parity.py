@@ -324,6 +324,11 @@ def test_full_size_c2_integer_properties(ctx):
     # independent library cross-check of every element (cuBLASLt int8 GEMM; comparator only)
     ref = torch._int_mm(codes[:, :p].contiguous(), codes[:, :p].T.contiguous())
     assert torch.equal(torch.triu(C.T), torch.triu(ref))
-    # final matrix: exactly C/m^2/p, exactly symmetric
-    assert torch.equal(G, (Cfull.double() / (m * m)) / p)
+    # final matrix: exactly fl(fl(C/m^2)/p), exactly symmetric.  (Tensor divisors: torch turns division by a Python
+    # scalar into a multiplication by its reciprocal on CUDA, which is not correctly rounded.)
+    four = torch.tensor(float(m * m), dtype=torch.float64, device=dev())
+    pp = torch.tensor(float(p), dtype=torch.float64, device=dev())
+    assert torch.equal(G, torch.div(torch.div(Cfull.double(), four), pp))
     assert torch.equal(G, G.T)
+    sub = Cfull[:64, :64].cpu().numpy().astype(np.float64)
+    assert np.array_equal(G[:64, :64].cpu().numpy(), (sub / (m * m)) / p)
