@@ -88,6 +88,8 @@ SIGNATURES = {
     "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
     "grm_cuda_syrk_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32]),
     "grm_cuda_syrk_i8_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
+    "grm_cuda_dosage_stats": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32]),
+    "grm_cuda_dosage_centre": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, C.POINTER(_f64)]),
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "grm_cuda_locus_stats_i8": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "grm_cuda_locus_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32]),

@@ -16,6 +16,12 @@ extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA,
 extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
                                      int32_t centred, double ploidy, const double *d_q, int32_t accumulate, double *d_G,
                                      int64_t ldg, int32_t rank, int32_t world);
+extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                         const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
+                                         int32_t accumulate);
+extern "C" int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_sums, const int64_t *d_r,
+                                          const int64_t *d_T, int64_t n, int64_t p, int32_t m, int32_t ploidy,
+                                          double *d_u, double *scalars);
 
 // ---------------------------------------------------------------------------------------------------------------
 // errors
@@ -127,7 +133,7 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     if (ctx->cusolver) grm_cusolver_destroy(ctx->cusolver);
     DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
                       &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->lu, &ctx->lu_work, &ctx->ipiv, &ctx->misc,
-                      &ctx->tiles_i8.buf, &ctx->tiles_f64.buf};
+                      &ctx->tiles_i8.buf, &ctx->tiles_f64.buf, &ctx->planes, &ctx->rT};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
@@ -430,19 +436,17 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, 1.0 / (static_cast<double>(m) * m), 0.0, 0.0,
                                              denom, nullptr, dG, ldG, o.rank, o.world));
             } else {
-                GRM_TRY(ctx->q.reserve(static_cast<size_t>(ldc) * sizeof(double)));
-                GRM_TRY(ctx->w.reserve(static_cast<size_t>(ldc) * sizeof(double)));
+                // exact integer statistics -> u, W2, d: no FP64 pass over the loci at all
                 GRM_TRY(ctx->u.reserve(static_cast<size_t>(n) * sizeof(double)));
-                GRM_TRY(grm_cuda_locus_stats_i8(ctx, d_colsum, p, n, m, ploidy, ctx->q.as<double>(),
-                                                ctx->w.as<double>(), d_stats));
-                GRM_TRY(grm_cuda_rowdot_i8(ctx, d_codes, n, p, ldc, ctx->w.as<double>(), ctx->u.as<double>()));
-                double h_stats[3];
-                GRM_CUDA_TRY(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
-                GRM_CUDA_TRY(cudaStreamSynchronize(st));
-                denom = static_cast<double>(ploidy) * h_stats[0];  // calc.jl:201
-                const double s = static_cast<double>(ploidy) / static_cast<double>(m);
+                GRM_TRY(ctx->rT.reserve(static_cast<size_t>(2 * n + 2) * sizeof(int64_t)));
+                uint64_t *d_sums = ctx->rT.as<uint64_t>();
+                int64_t *d_r = ctx->rT.as<int64_t>() + 2, *d_T = d_r + n;
+                GRM_TRY(grm_cuda_dosage_stats(ctx, d_codes, n, p, ldc, d_colsum, d_sums, d_r, d_T, 0));
+                double sc[4];
+                GRM_TRY(grm_cuda_dosage_centre(ctx, d_sums, d_r, d_T, n, p, m, ploidy, ctx->u.as<double>(), sc));
+                denom = sc[3];  // calc.jl:201
                 GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
-                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, s * s, s, h_stats[1], denom, ctx->u.as<double>(),
+                GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, sc[0], sc[1], sc[2], denom, ctx->u.as<double>(),
                                              dG, ldG, o.rank, o.world));
             }
             GRM_CUDA_TRY(cudaEventRecord(ev[3], st));

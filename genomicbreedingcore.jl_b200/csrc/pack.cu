@@ -286,6 +286,110 @@ rowdot_i8_kernel(const int8_t *__restrict__ codes, int64_t n, int64_t p, int64_t
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------
+// Exact integer statistics of the dosage codes (grmploidyaware on the int8 path).
+//   S_k = sum_i c_ik (column sums, from the pack pass)      r_i = sum_k c_ik      T_i = sum_k c_ik S_k
+//   sums = { sum_k S_k, sum_k S_k^2 }
+// With q_k = S_k/(m n) and w_k = ploidy/2 + q_k (calc.jl:197-198,205) every term of the rank-1 expansion
+//  is a ratio of these integers:  u_i = sum_k c_ik w_k = h r_i + T_i/(m n),
+// W2 = sum_k w_k^2 = p h^2 + 2 h sum(S)/(m n) + sum(S^2)/(m n)^2,  d = ploidy (sum(S)/(m n) - sum(S^2)/(m n)^2).
+// Integers are order-independent, so the result is bit-identical for any chunking or GPU count.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_planes_kernel(const int32_t *__restrict__ colsum, int64_t p, int64_t ldc, uint8_t *__restrict__ planes,
+                     unsigned long long *__restrict__ sums) {
+    unsigned long long s1 = 0, s2 = 0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < ldc; k += stride) {
+        const uint32_t S = k < p ? static_cast<uint32_t>(colsum[k]) : 0u;
+        planes[k] = static_cast<uint8_t>(S & 255u);            // S = b0 + 256 b1 + 65536 b2  (S < 2^24)
+        planes[ldc + k] = static_cast<uint8_t>((S >> 8) & 255u);
+        planes[2 * ldc + k] = static_cast<uint8_t>((S >> 16) & 255u);
+        s1 += S;
+        s2 += static_cast<unsigned long long>(S) * S;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[0], s1);
+        atomicAdd(&sums[1], s2);
+    }
+}
+
+// block = 256 threads x 8 entry rows; thread t owns 16-locus groups t, t+256, ...; 16 dp4a per row and group
+__global__ void __launch_bounds__(256)
+rowstats_i8_kernel(const int8_t *__restrict__ codes, int64_t n, int64_t p, int64_t ldc,
+                   const uint8_t *__restrict__ planes, long long *__restrict__ r_out, long long *__restrict__ T_out,
+                   int accumulate) {
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * RD_ROWS;
+    uint32_t t0[RD_ROWS], t1[RD_ROWS], t2[RD_ROWS], rs[RD_ROWS];
+#pragma unroll
+    for (int r = 0; r < RD_ROWS; ++r) t0[r] = t1[r] = t2[r] = rs[r] = 0u;
+    const int64_t groups = (p + 15) / 16;
+    for (int64_t g = threadIdx.x; g < groups; g += blockDim.x) {
+        const int64_t k = g * 16;
+        const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(planes + k));
+        const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(planes + ldc + k));
+        const uint4 b2 = __ldg(reinterpret_cast<const uint4 *>(planes + 2 * ldc + k));
+#pragma unroll
+        for (int r = 0; r < RD_ROWS; ++r) {
+            const int64_t row = r0 + r;
+            if (row < n) {
+                const uint4 c = __ldg(reinterpret_cast<const uint4 *>(codes + row * ldc + k));
+                t0[r] = __dp4a(c.x, b0.x, __dp4a(c.y, b0.y, __dp4a(c.z, b0.z, __dp4a(c.w, b0.w, t0[r]))));
+                t1[r] = __dp4a(c.x, b1.x, __dp4a(c.y, b1.y, __dp4a(c.z, b1.z, __dp4a(c.w, b1.w, t1[r]))));
+                t2[r] = __dp4a(c.x, b2.x, __dp4a(c.y, b2.y, __dp4a(c.z, b2.z, __dp4a(c.w, b2.w, t2[r]))));
+                rs[r] = __dp4a(c.x, 0x01010101u, __dp4a(c.y, 0x01010101u, __dp4a(c.z, 0x01010101u,
+                                                                                __dp4a(c.w, 0x01010101u, rs[r]))));
+            }
+        }
+    }
+    __shared__ unsigned long long shT[RD_ROWS][8], shR[RD_ROWS][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int r = 0; r < RD_ROWS; ++r) {
+        unsigned long long T = static_cast<unsigned long long>(t0[r]) + (static_cast<unsigned long long>(t1[r]) << 8) +
+                               (static_cast<unsigned long long>(t2[r]) << 16);
+        unsigned long long R = rs[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            T += __shfl_down_sync(0xffffffffu, T, o);
+            R += __shfl_down_sync(0xffffffffu, R, o);
+        }
+        if (lane == 0) {
+            shT[r][warp] = T;
+            shR[r][warp] = R;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < RD_ROWS && r0 + threadIdx.x < n) {
+        unsigned long long T = 0, R = 0;
+        for (int wi = 0; wi < 8; ++wi) {
+            T += shT[threadIdx.x][wi];
+            R += shR[threadIdx.x][wi];
+        }
+        const int64_t row = r0 + threadIdx.x;
+        if (accumulate) {
+            T_out[row] += static_cast<long long>(T);
+            r_out[row] += static_cast<long long>(R);
+        } else {
+            T_out[row] = static_cast<long long>(T);
+            r_out[row] = static_cast<long long>(R);
+        }
+    }
+}
+
+// u_i = h r_i + T_i/(m n)
+__global__ void centre_rows_kernel(const long long *__restrict__ r, const long long *__restrict__ T, int64_t n, double h,
+                                   double mn, double *__restrict__ u) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) u[i] = h * static_cast<double>(r[i]) + static_cast<double>(T[i]) / mn;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -393,6 +497,63 @@ extern "C" int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, 
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     rowdot_i8_kernel<<<static_cast<unsigned>((n + RD_ROWS - 1) / RD_ROWS), 256, 0, ctx->stream>>>(d_codes, n, p, ldc,
                                                                                                  d_w, d_u);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                         const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
+                                         int32_t accumulate) {
+    if (!ctx || !d_codes || !d_colsum || !d_sums || !d_r || !d_T || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p) {
+        grm_set_error("dosage_stats: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    if (n >= (1ll << 18)) {  // S_k <= 64 n must fit the three byte planes
+        grm_set_error("dosage_stats: n = %lld exceeds 2^18 entries", (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_TRY(ctx->planes.reserve(static_cast<size_t>(3 * ldc)));
+    uint8_t *planes = ctx->planes.as<uint8_t>();
+    if (!accumulate) GRM_CUDA_TRY(cudaMemsetAsync(d_sums, 0, 2 * sizeof(uint64_t), ctx->stream));
+    const int blocks = static_cast<int>(std::min<int64_t>((ldc + 255) / 256, 1024));
+    colsum_planes_kernel<<<blocks, 256, 0, ctx->stream>>>(d_colsum, p, ldc, planes,
+                                                          reinterpret_cast<unsigned long long *>(d_sums));
+    GRM_CUDA_TRY(cudaGetLastError());
+    rowstats_i8_kernel<<<static_cast<unsigned>((n + RD_ROWS - 1) / RD_ROWS), 256, 0, ctx->stream>>>(
+        d_codes, n, p, ldc, planes, reinterpret_cast<long long *>(d_r), reinterpret_cast<long long *>(d_T), accumulate);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 2;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_sums, const int64_t *d_r,
+                                          const int64_t *d_T, int64_t n, int64_t p, int32_t m, int32_t ploidy,
+                                          double *d_u, double *scalars /* host: alpha, beta, gamma, denom */) {
+    if (!ctx || !d_sums || !d_r || !d_T || !d_u || !scalars || n < 1 || p < 1 || m < 1) {
+        grm_set_error("dosage_centre: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t h_sums[2];
+    GRM_CUDA_TRY(cudaMemcpyAsync(h_sums, d_sums, sizeof(h_sums), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const double mn = static_cast<double>(m) * static_cast<double>(n);  // exact (< 2^24)
+    const double h = 0.5 * ploidy;
+    const double s = static_cast<double>(ploidy) / static_cast<double>(m);
+    // d = ploidy * (mn*sum(S) - sum(S^2)) / mn^2 with the numerator exact in 128-bit integers (calc.jl:201)
+    const unsigned __int128 num = static_cast<unsigned __int128>(static_cast<uint64_t>(m) * static_cast<uint64_t>(n)) *
+                                      h_sums[0] - static_cast<unsigned __int128>(h_sums[1]);
+    const double S1 = static_cast<double>(h_sums[0]), S2 = static_cast<double>(h_sums[1]);
+    const double denom = static_cast<double>(ploidy) * (static_cast<double>(num) / (mn * mn));
+    const double W2 = (static_cast<double>(p) * h * h + 2.0 * h * (S1 / mn)) + S2 / (mn * mn);
+    scalars[0] = s * s;
+    scalars[1] = s;
+    scalars[2] = W2;
+    scalars[3] = denom;
+    centre_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const long long *>(d_r), reinterpret_cast<const long long *>(d_T), n, h, mn, d_u);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

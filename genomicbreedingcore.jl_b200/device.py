@@ -21,11 +21,19 @@ def _torch():
 
 @contextmanager
 def on_ctx_stream(ctx: _lib.Context):
-    """Make the library stream torch's current stream (so torch.cuda.Event timings see the library's kernels)."""
+    """Make the library stream torch's current stream (so torch ops, NCCL collectives and torch.cuda.Event timings
+    are ordered with the library's kernels).  The library stream first waits for the work already enqueued on the
+    caller's stream, and the caller's stream waits for the library stream on exit — no host synchronisation."""
     torch = _torch()
-    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", ctx.device))
+    dev = torch.device("cuda", ctx.device)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    outer = torch.cuda.current_stream(dev)
+    if outer.cuda_stream != ext.cuda_stream:
+        ext.wait_stream(outer)
     with torch.cuda.stream(ext):
         yield ext
+    if outer.cuda_stream != ext.cuda_stream:
+        outer.wait_stream(ext)
 
 
 def _ptr(t):
@@ -101,6 +109,33 @@ def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_locus_stats_i8(ctx.handle, _ptr(colsum), p, n, m, ploidy, _ptr(q), _ptr(w), _ptr(stats)))
     return q, w, stats
+
+
+def dosage_stats(ctx, codes, p: int, colsum, sums=None, r=None, T=None, accumulate: bool = False):
+    """Exact integer r_i, T_i and {sum S, sum S^2} of one slab of codes (see grm_cuda_dosage_stats)."""
+    torch = _torch()
+    n, ldc = codes.shape
+    dev = codes.device
+    if sums is None:
+        sums = torch.zeros((2,), dtype=torch.int64, device=dev)
+        r = torch.zeros((n,), dtype=torch.int64, device=dev)
+        T = torch.zeros((n,), dtype=torch.int64, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_dosage_stats(ctx.handle, _ptr(codes), n, p, ldc, _ptr(colsum), _ptr(sums), _ptr(r),
+                                             _ptr(T), 1 if accumulate else 0))
+    return sums, r, T
+
+
+def dosage_centre(ctx, sums, r, T, p_total: int, m: int, ploidy: int):
+    """-> (u [n] float64 CUDA tensor, (alpha, beta, gamma, denom)) for syrk_i8_f64."""
+    torch = _torch()
+    n = r.shape[0]
+    u = torch.empty((n,), dtype=torch.float64, device=r.device)
+    sc = (C.c_double * 4)()
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_dosage_centre(ctx.handle, _ptr(sums), _ptr(r), _ptr(T), n, p_total, m, ploidy, _ptr(u),
+                                              sc))
+    return u, tuple(sc)
 
 
 def rowdot_i8(ctx, codes, p: int, w):

@@ -120,19 +120,16 @@ class ShardedGRM:
             if self.ploidy is None:
                 alpha, beta, gamma, denom, u = 1.0 / (m * m), 0.0, 0.0, float(p), None
             else:
-                stats = torch.zeros((3,), dtype=torch.float64, device=self.G.device)
-                u = torch.zeros((n,), dtype=torch.float64, device=self.G.device)
-                for r in range(self.world):  # fixed slab order => same bits on every rank
+                sums = r_ = T_ = None
+                for r in range(self.world):  # exact integers: any order gives the same bits
                     a, b = loci_range(p, r, self.world)
                     if b <= a:
                         continue
-                    q, w, st = D.locus_stats_i8(ctx, self.colsum_all[r], b - a, n, m, self.ploidy)
-                    stats += st
-                    u += D.rowdot_i8(ctx, self.codes_all[r], b - a, w)
-                    self.launches += 3
-                h = stats.cpu()
-                s = self.ploidy / m
-                alpha, beta, gamma, denom = s * s, s, float(h[1]), self.ploidy * float(h[0])
+                    sums, r_, T_ = D.dosage_stats(ctx, self.codes_all[r], b - a, self.colsum_all[r], sums, r_, T_,
+                                                  accumulate=sums is not None)
+                    self.launches += 2
+                u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r_, T_, p, m, self.ploidy)
+                self.launches += 1
             self.scale = denom
             if ev:
                 ev[3].record()

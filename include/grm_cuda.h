@@ -157,6 +157,21 @@ int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n
                              int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
                              double *d_G, int64_t ldg, int32_t rank, int32_t world);
 
+/* Exact integer statistics of the codes for the rank-1 centring of grmploidyaware:
+ *   r[i] = sum_k codes[i,k]      T[i] = sum_k codes[i,k]*colsum[k]      sums = { sum_k colsum[k], sum_k colsum[k]^2 }
+ * (dp4a against the byte planes of colsum; order-independent, hence bit-identical for any chunking / GPU count).
+ * accumulate != 0 adds to r, T and sums (loci held as several slabs).  Requires n < 2^18. */
+int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                              const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
+                              int32_t accumulate);
+
+/* From those integers (q_k = colsum_k/(m n), w_k = ploidy/2 + q_k; calc.jl:197-201,205), with p the total loci count:
+ *   u[i] = sum_k c_ik w_k = (ploidy/2) r[i] + T[i]/(m n)                                   (device, n doubles)
+ *   scalars (HOST, 4 doubles) = { alpha = (ploidy/m)^2, beta = ploidy/m, gamma = sum_k w_k^2, denom = d }
+ * ready to be passed to grm_cuda_syrk_i8_f64.  Synchronises the stream. */
+int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_sums, const int64_t *d_r, const int64_t *d_T,
+                               int64_t n, int64_t p, int32_t m, int32_t ploidy, double *d_u, double *scalars);
+
 /* u[i] = sum_k codes[i,k] * w[k]  in FP64, fixed summation order (bit-reproducible). */
 int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                            const double *d_w, double *d_u);

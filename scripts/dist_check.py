@@ -32,7 +32,7 @@ for (n, p, m, ploidy) in [(3000, 20000, 4, 4), (1100, 777, 2, None), (2049, 5001
     sym = torch.equal(G, G.T)
     print(f"[rank {rank}/{world}] n={n} p={p} ploidy={ploidy}: bit-identical={same} rel={rel:.2e} repeat={again} symmetric={sym}",
           flush=True)
-    ok = ok and rel <= 1e-12 and again and sym and (ploidy is not None or same)
+    ok = ok and same and again and sym  # integer statistics: bit-identical for any number of ranks
 t = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
