@@ -11,6 +11,9 @@
 //   warps 2..5  epilogue:     tcgen05.ld TMEM -> registers -> (int32 | FP64 formula) -> global, overlapped with the
 //                             next tile's main loop through two TMEM accumulator stages (2 x 256 columns)
 // Work items are 128 x 256 output tiles taken from a host-built list that covers only the upper triangle.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -38,6 +41,32 @@ struct EpiParams {
 };
 
 // EPI: 0 = store int32 C;  1 = G = (alpha*C)/denom;  2 = G = ((alpha*C - beta*(u_i+u_j)) + gamma)/denom
+// One thread = one output row, 32 consecutive columns: for each column the warp writes 32 consecutive rows
+// (column-major G => one coalesced 256-byte store per column).
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int64_t row, bool row_ok, int64_t col0, double ui,
+                                               const EpiParams &ep) {
+    if (row_ok && col0 < ep.n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int64_t col = col0 + j;
+            if (col < ep.n) {
+                const int32_t c = static_cast<int32_t>(r[j]);
+                if (EPI == 0) {
+                    ep.C[row + col * ep.ldC] = c;
+                } else {
+                    double v = static_cast<double>(c) * ep.alpha;
+                    if (EPI == 2) {
+                        const double uj = __ldg(ep.u + col);
+                        v = (v - ep.beta * (ui + uj)) + ep.gamma;
+                    }
+                    ep.G[row + col * ep.ldg] = v / ep.denom;
+                }
+            }
+        }
+    }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
@@ -150,26 +179,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict_
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + acc * BN + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
                 tmem_wait_ld();
-                const int64_t col0 = static_cast<int64_t>(tc.y) + c0;
-                if (row_ok && col0 < ep.n) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t col = col0 + j;
-                        if (col < ep.n) {
-                            const int32_t c = static_cast<int32_t>(r[j]);
-                            if (EPI == 0) {
-                                ep.C[row + col * ep.ldC] = c;
-                            } else {
-                                double v = static_cast<double>(c) * ep.alpha;
-                                if (EPI == 2) {
-                                    const double uj = __ldg(ep.u + col);
-                                    v = (v - ep.beta * (ui + uj)) + ep.gamma;
-                                }
-                                ep.G[row + col * ep.ldg] = v / ep.denom;
-                            }
-                        }
-                    }
-                }
+                epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
             }
             tc_fence_before();
             __syncwarp();
@@ -182,6 +192,146 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict_
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one TPC) computes one 256 x 256 tile with tcgen05.mma.cta_group::2
+// (UMMA M = 256, N = 256).  CTA r stages rows [row0 + 128 r, +128) as A and rows [col0 + 128 r, +128) as its half of
+// B, so every operand byte is read from L2 and from shared memory once per PAIR: 1/3 less L2 traffic and 1/3 less
+// shared-memory traffic per MAC than the 128 x 256 single-CTA tile, and a 6-stage 32 KB ring instead of 4 x 48 KB.
+// Only the leader CTA (rank 0) issues MMAs; its tcgen05.commit multicasts to the barriers of both CTAs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr uint32_t STAGE2_BYTES = 2 * A_BYTES;  // A (16 KiB) + this CTA's half of B (16 KiB)
+constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
+                    int kb_per_slab, EpiParams ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES2;
+    uint64_t *tmem_full = empty_bar + STAGES2;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const bool leader = cta == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(&full_bar[s], 2);   // leader: arrive.expect_tx ; peer: remote arrive  (used in the leader only)
+            mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit per use, in each CTA
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);   // multicast commit, in each CTA
+            mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps of each CTA (used in the leader only)
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                const int2 tc = tiles[t];
+                int slab = 0, kin = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *sA = smem + stage * STAGE2_BYTES;
+                    uint8_t *sB = sA + A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+                    else mbar_arrive_cluster(&full_bar[stage], 0);
+                    tma_load_3d_2cta(sA, &tmap, &full_bar[stage], kin * BK, tc.x + 128 * static_cast<int>(cta), slab);
+                    tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, tc.y + 128 * static_cast<int>(cta), slab);
+                    if (++kin == kb_per_slab) {
+                        kin = 0;
+                        ++slab;
+                    }
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(256, 256);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint64_t adesc = umma_desc_k_sw128(sA);
+                    const uint64_t bdesc = umma_desc_k_sw128(sA + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_i8_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2cta(&empty_bar[stage], 0b11);
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_2cta(&tmem_full[acc], 0b11);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 of both CTAs; CTA r owns rows 128 r .. 128 r + 127) ===========
+        const int quarter = warp & 3;
+        int local = 0;
+        for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int2 tc = tiles[t];
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int64_t row = static_cast<int64_t>(tc.x) + 128 * cta + quarter * 32 + lane;
+            const bool row_ok = row < ep.n;
+            double ui = 0.0;
+            if (EPI == 2 && row_ok) ui = ep.u[row];
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+                tmem_wait_ld();
+                epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory and TMEM stay alive until the leader's last MMA has retired
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
     }
 }
 
@@ -250,6 +400,38 @@ int32_t get_tile_list(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world,
     return GRM_CUDA_OK;
 }
 
+// 256 x 256 tiles (one per CTA pair) of the owned sharding tiles
+int32_t get_tile_list_2cta(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_tiles, int *count) {
+    TileListCache &tc = ctx->tiles_i8_2cta;
+    if (tc.n != n || tc.rank != rank || tc.world != world) {
+        std::vector<int2> order;
+        grm_tile_order(n, order);
+        int64_t b, e;
+        grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
+        std::vector<int2> tl;
+        for (int64_t t = b; t < e; ++t) tl.push_back(make_int2(order[t].x * GRM_TILE, order[t].y * GRM_TILE));
+        GRM_TRY(tc.buf.reserve(std::max<size_t>(tl.size(), 1) * sizeof(int2)));
+        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, tl.data(), tl.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        tc.n = n;
+        tc.rank = rank;
+        tc.world = world;
+        tc.count = static_cast<int32_t>(tl.size());
+    }
+    *d_tiles = tc.buf.as<int2>();
+    *count = tc.count;
+    return GRM_CUDA_OK;
+}
+
+bool use_2cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("GRM_CUDA_SYRK_I8");
+        v = (e && (!strcmp(e, "2cta") || !strcmp(e, "2"))) ? 1 : 0;  // default: single-CTA tiles
+    }
+    return v == 1;
+}
+
 template <int EPI>
 int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs,
                const EpiParams &ep, int32_t rank, int32_t world) {
@@ -262,6 +444,25 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     CUtensorMap tmap;
     GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
+    const int kbs = static_cast<int>((p + BK - 1) / BK);
+    if (use_2cta()) {
+        const int2 *d_tiles;
+        int count;
+        GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+        if (count == 0) return GRM_CUDA_OK;
+        static bool attr2_set[3] = {false, false, false};
+        if (!attr2_set[EPI]) {
+            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(SMEM2_BYTES)));
+            attr2_set[EPI] = true;
+        }
+        const int pairs = std::min(count, ctx->num_sms / 2);
+        syrk_i8_2cta_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(
+            tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
     const int2 *d_tiles;
     int count;
     GRM_TRY(get_tile_list(ctx, n, rank, world, &d_tiles, &count));

@@ -131,6 +131,39 @@ def test_ploidyaware_dosage(ctx, n, p, m, ploidy):
     assert np.array_equal(q.cpu().numpy(), qc)
 
 
+def test_integer_centring_statistics(ctx):
+    """r_i, T_i, sum S, sum S^2 are exact integers; u, W2 and d follow from them."""
+    from grm_b200 import device as D
+
+    n, p, m, ploidy = 300, 4097, 4, 4
+    A = synth.dosage(n, p, m, seed=31)
+    c = O.dosage_codes(A, m)
+    S = c.sum(0)
+    codes, colsum, flags = D.pack_dosage(ctx, to_dev(A), m)
+    sums, r, T = D.dosage_stats(ctx, codes, p, colsum)
+    u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r, T, p, m, ploidy)
+    ctx.synchronize()
+    assert np.array_equal(r.cpu().numpy(), c.sum(1))
+    assert np.array_equal(T.cpu().numpy(), c @ S)
+    assert sums.cpu().numpy().tolist() == [int(S.sum()), int((S * S).sum())]
+    q = S / (m * n)
+    w = ploidy / 2 + q
+    assert np.allclose(u.cpu().numpy(), c @ w, rtol=1e-14, atol=0)
+    assert (alpha, beta) == ((ploidy / m) ** 2, ploidy / m)
+    assert abs(gamma - float((w * w).sum())) <= 1e-14 * gamma
+    assert abs(denom - ploidy * float((q * (1 - q)).sum())) <= 1e-14 * denom
+    # accumulate over two slabs == one pass
+    h = 2048
+    c1, cs1, _ = D.pack_dosage(ctx, to_dev(A[:, :h]), m)
+    c2, cs2, _ = D.pack_dosage(ctx, to_dev(A[:, h:]), m)
+    s2, r2, T2 = D.dosage_stats(ctx, c1, h, cs1)
+    s2, r2, T2 = D.dosage_stats(ctx, c2, p - h, cs2, s2, r2, T2, accumulate=True)
+    ctx.synchronize()
+    import torch
+
+    assert torch.equal(s2, sums) and torch.equal(r2, r) and torch.equal(T2, T)
+
+
 # P5: continuous FP64 path
 @pytest.mark.parametrize("n,p,gen", [(100, 10_000, "continuous"), (257, 1000, "continuous"), (123, 5000, "uniform"),
                                      (130, 17, "continuous")])
@@ -284,7 +317,7 @@ def test_sharded_tiles_union_is_bit_identical(world):
         assert not (np.triu(acc != 0) & np.triu(part != 0)).any(), "tiles of different ranks overlap"
         acc += part
     iu = np.triu_indices(1100)
-    assert np.array_equal(acc[iu], full[iu])
+    assert np.array_equal(acc[iu], full[iu])  # bit-identical: integer Gram + integer centring statistics
     Ac = synth.continuous(600, 500, seed=22)
     fullc, info = grm_call(Ac, None, skip_repair=True)
     accc = np.zeros_like(fullc)
