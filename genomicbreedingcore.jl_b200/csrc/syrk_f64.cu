@@ -6,21 +6,26 @@
 // staged into shared memory, with the reference's rounding sequence: no FMA contraction).
 //
 // tcgen05 has no FP64 kind, so the contraction runs on the FP64 tensor path that exists on sm_100:
-// mma.sync.m8n8k4.f64 (DMMA).  Block tile 128 x 128 entries, 8 warps (2 x 4), warp tile 64 x 32, K slab of 16
+// mma.sync.m16n8k8.f64 (DMMA).  Block tile 128 x 128 entries, 8 warps (2 x 4), warp tile 64 x 32, K slab of 16
 // loci, double-buffered shared memory with register prefetch.  Only tiles that touch the upper triangle run.
 #include "common.cuh"
 
 namespace {
 
 constexpr int FB = 128;          // block tile edge (entries)
-constexpr int FK = 16;           // loci per slab
+constexpr int FK = 32;           // loci per slab (staged in two halves of 16: one barrier per 32 loci)
+constexpr int FH = 16;           // loci per half-slab
 constexpr int FLD = FB + 4;      // padded row length: 4a + b (a,b in 0..3) hits 16 distinct 8-byte banks
 constexpr size_t F64_SMEM = 2ull * 2 * FK * FLD * sizeof(double);
 
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
+// D(16x8) += A(16x8, row) * B(8x8, col), FP64.  Fragments (g = lane >> 2, t = lane & 3):
+//   a0:(g, t) a1:(g+8, t) a2:(g, t+4) a3:(g+8, t+4)   b0:(k = t, n = g) b1:(k = t+4, n = g)
+//   c0,c1:(g, 2t + {0,1})   c2,c3:(g+8, 2t + {0,1})
+__device__ __forceinline__ void dmma_m16n8k8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
 template <bool CENTRED>
@@ -38,21 +43,24 @@ syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda,
     const int wm = warp >> 2, wn = warp & 3;
 
     // staging map: thread -> entry e (0..127) and 8 consecutive loci of the slab
-    const int e = tid & 127, kh = (tid >> 7) * 8;
+    const int e = tid & 127, kh = (tid >> 7) * 8;  // 2 x 8 loci of a 16-locus half-slab
     const int64_t ra = row0 + e, rb = col0 + e;
     const bool va = ra < n, vb = rb < n;
 
-    double acc[8][4][2];
+    double acc[4][4][4];  // [m16 tile][n8 tile][fragment]
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[i][j][f] = 0.0;
 
     double pa[8], pb[8];
-    auto fetch = [&](int64_t k0) {
+    // half-slab h of the slab starting at k0: loci k0 + 16 h + kh + (0..7) for this thread
+    auto fetch = [&](int64_t k0, int h) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int64_t k = k0 + kh + j;
+            const int64_t k = k0 + h * FH + kh + j;
             const bool vk = k < p;
             double xa = (vk && va) ? __ldg(A + ra + k * lda) : 0.0;
             double xb = (vk && vb) ? __ldg(A + rb + k * lda) : 0.0;
@@ -66,51 +74,75 @@ syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda,
             pb[j] = xb;
         }
     };
-    auto stash = [&](int buf) {
+    auto stash = [&](int buf, int h) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            sA[buf][kh + j][e] = pa[j];
-            sB[buf][kh + j][e] = pb[j];
+            sA[buf][h * FH + kh + j][e] = pa[j];
+            sB[buf][h * FH + kh + j][e] = pb[j];
+        }
+    };
+    const int fr = lane >> 2, fk = lane & 3;
+    auto compute = [&](int buf, int h) {
+#pragma unroll
+        for (int kk = 0; kk < FH / 8; ++kk) {
+            const int kb = h * FH + kk * 8;
+            double a[4][4], b[4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int r = wm * 64 + mi * 16 + fr;
+                a[mi][0] = sA[buf][kb + fk][r];
+                a[mi][1] = sA[buf][kb + fk][r + 8];
+                a[mi][2] = sA[buf][kb + fk + 4][r];
+                a[mi][3] = sA[buf][kb + fk + 4][r + 8];
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int c = wn * 32 + ni * 8 + fr;
+                b[ni][0] = sB[buf][kb + fk][c];
+                b[ni][1] = sB[buf][kb + fk + 4][c];
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma_m16n8k8(acc[mi][ni], a[mi], b[ni]);
         }
     };
 
     const int64_t nslab = (p + FK - 1) / FK;
-    fetch(0);
-    stash(0);
+    fetch(0, 0);
+    stash(0, 0);
+    fetch(0, 1);
+    stash(0, 1);
     __syncthreads();
 
-    const int fr = lane >> 2, fk = lane & 3;
     for (int64_t s = 0; s < nslab; ++s) {
         const int buf = static_cast<int>(s & 1);
-        if (s + 1 < nslab) fetch((s + 1) * FK);
+        const bool more = s + 1 < nslab;
 #pragma unroll
-        for (int kk = 0; kk < FK / 4; ++kk) {
-            double a[8], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi) a[mi] = sA[buf][kk * 4 + fk][wm * 64 + mi * 8 + fr];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = sB[buf][kk * 4 + fk][wn * 32 + ni * 8 + fr];
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        for (int h = 0; h < 2; ++h) {
+            if (more) fetch((s + 1) * FK, h);
+            compute(buf, h);
+            if (more) stash(buf ^ 1, h);
         }
-        if (s + 1 < nslab) stash(buf ^ 1);
         __syncthreads();
     }
 
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-        const int64_t row = row0 + wm * 64 + mi * 8 + fr;
-        if (row >= n) continue;
+    for (int mi = 0; mi < 4; ++mi) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+        for (int hr = 0; hr < 2; ++hr) {
+            const int64_t row = row0 + wm * 64 + mi * 16 + fr + 8 * hr;
+            if (row >= n) continue;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t col = col0 + wn * 32 + ni * 8 + 2 * fk + h;
-                if (col < n) {
-                    double *dst = G + row + col * ldg;
-                    *dst = accumulate ? (*dst + acc[mi][ni][h]) : acc[mi][ni][h];
+            for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t col = col0 + wn * 32 + ni * 8 + 2 * fk + h;
+                    if (col < n) {
+                        double *dst = G + row + col * ldg;
+                        const double v = acc[mi][ni][2 * hr + h];
+                        *dst = accumulate ? (*dst + v) : v;
+                    }
                 }
             }
         }
