@@ -5,12 +5,15 @@
 // contraction is done in int8 x int8 -> int32 and the FP64 scaling / rank-1 centring is applied
 // in the epilogue.
 //
-// Kernel shape (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0      TMA producer: operand tiles (K-major int8, 128-byte swizzle) global -> shared, 4-stage ring
-//   warp 1      MMA issuer:   tcgen05.mma.kind::i8, M=128 x N=256 x K=32 per instruction, accumulators in TMEM
+// Kernel shape (persistent, one CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: operand tiles (K-major int8, 128-byte swizzle) global -> shared ring
+//   warp 1      MMA issuer:   one thread issues tcgen05.mma.kind::i8, accumulators (int32) in TMEM
 //   warps 2..5  epilogue:     tcgen05.ld TMEM -> registers -> (int32 | FP64 formula) -> global, overlapped with the
 //                             next tile's main loop through two TMEM accumulator stages (2 x 256 columns)
-// Work items are 128 x 256 output tiles taken from a host-built list that covers only the upper triangle.
+// Two variants of the same pipeline:
+//   syrk_i8_2cta_kernel (default)  CTA pairs, cta_group::2, UMMA 256 x 256 x 32, 256 x 256 tiles, 6 x 32 KB stages
+//   syrk_i8_kernel (GRM_CUDA_SYRK_I8=1cta)  single CTA, UMMA 128 x 256 x 32, 128 x 256 tiles, 4 x 48 KB stages
+// Work items come from a host-built list that covers only the upper triangle.
 #include <stdlib.h>
 #include <string.h>
 
@@ -227,7 +230,7 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < STAGES2; ++s) {
-            mbar_init(&full_bar[s], 2);   // leader: arrive.expect_tx ; peer: remote arrive  (used in the leader only)
+            mbar_init(&full_bar[s], 1);   // the leader's arrive.expect_tx covers the bytes of BOTH CTAs (leader only)
             mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit per use, in each CTA
         }
         for (int a = 0; a < 2; ++a) {
@@ -254,8 +257,9 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *sA = smem + stage * STAGE2_BYTES;
                     uint8_t *sB = sA + A_BYTES;
+                    // The peer's bytes may land before the leader arms the barrier: the tx-count goes transiently
+                    // negative, the phase cannot complete before the leader's (only) arrival.
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
-                    else mbar_arrive_cluster(&full_bar[stage], 0);
                     tma_load_3d_2cta(sA, &tmap, &full_bar[stage], kin * BK, tc.x + 128 * static_cast<int>(cta), slab);
                     tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, tc.y + 128 * static_cast<int>(cta), slab);
                     if (++kin == kb_per_slab) {
@@ -427,7 +431,7 @@ bool use_2cta() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("GRM_CUDA_SYRK_I8");
-        v = (e && (!strcmp(e, "2cta") || !strcmp(e, "2"))) ? 1 : 0;  // default: single-CTA tiles
+        v = (e && (!strcmp(e, "1cta") || !strcmp(e, "1"))) ? 0 : 1;  // default: CTA pairs (measured +18 % on C3)
     }
     return v == 1;
 }
