@@ -279,7 +279,7 @@ def run_b200(args, wl):
     int8_peak = 2.0 * peaks["bf16_sustained"]
     tr = ncu_traffic()
     roofline = {
-        "bound": "tensor", "kernel": "syrk_i8_kernel (tcgen05.mma kind::i8, TMA, TMEM)", "achieved": achieved,
+        "bound": "tensor", "kernel": "syrk_i8_2cta_kernel (tcgen05.mma cta_group::2 kind::i8, TMA, TMEM)", "achieved": achieved,
         "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
         "traffic": tr.get("syrk_i8_dram_bytes_per_launch"),
         "peak_note": f"int8 dense = 2 x measured sustained bf16 ({peaks['source']}); unit counts int8 ops (1 MAC = 2 ops); "
@@ -289,7 +289,7 @@ def run_b200(args, wl):
     pack_ms = stage_ms.get("ms_pack", float("nan"))
     pack_bytes = 9.0 * n * pc  # 8 B read + 1 B written per cell
     roofline_pack = {
-        "bound": "hbm", "kernel": "pack_dosage_kernel (+ detect sample)", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
+        "bound": "hbm", "kernel": "pack_dosage_kernel", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
         "peak": peaks["hbm"], "unit": "GB/s", "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / peaks["hbm"],
         "traffic": tr.get("pack_dram_bytes_per_launch"), "ms_per_launch": pack_ms,
     }

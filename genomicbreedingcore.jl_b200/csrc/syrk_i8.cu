@@ -14,6 +14,7 @@
 //   syrk_i8_2cta_kernel (default)  CTA pairs, cta_group::2, UMMA 256 x 256 x 32, 256 x 256 tiles, 6 x 32 KB stages
 //   syrk_i8_kernel (GRM_CUDA_SYRK_I8=1cta)  single CTA, UMMA 128 x 256 x 32, 128 x 256 tiles, 4 x 48 KB stages
 // Work items come from a host-built list that covers only the upper triangle.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -40,8 +41,22 @@ struct EpiParams {
     double *G;       // modes 1, 2
     int64_t ldg;
     double alpha, beta, gamma, denom;
+    double rcp;  // RN(1/denom) when the fast exact division applies, else 0
     const double *u;
 };
+
+// Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
+// (Markstein).  After the first correction q is within 1/2 ulp + 2^-51 ulp of v/d, i.e. faithful; the second one
+// then yields RN(v/d).  For grmsimple (v = C/m^2 with C < 2^31, d = p < 2^31) a quotient is at least 2^-32 ulp away
+// from any rounding midpoint, far more than the 2^-54 ulp the corrected value can be off — the result is
+// bit-identical to IEEE division (checked against `/` in tests/test_gpu_parity.py).  5 FP64 ops instead of ~30.
+__device__ __forceinline__ double div_const(double v, double d, double rcp) {
+    double q = v * rcp;
+    double r = fma(-q, d, v);
+    q = fma(r, rcp, q);
+    r = fma(-q, d, v);
+    return fma(r, rcp, q);
+}
 
 // EPI: 0 = store int32 C;  1 = G = (alpha*C)/denom;  2 = G = ((alpha*C - beta*(u_i+u_j)) + gamma)/denom
 // One thread = one output row, 32 consecutive columns: for each column the warp writes 32 consecutive rows
@@ -63,7 +78,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int64_t 
                         const double uj = __ldg(ep.u + col);
                         v = (v - ep.beta * (ui + uj)) + ep.gamma;
                     }
-                    ep.G[row + col * ep.ldg] = v / ep.denom;
+                    ep.G[row + col * ep.ldg] = (ep.rcp != 0.0) ? div_const(v, ep.denom, ep.rcp) : v / ep.denom;
                 }
             }
         }
@@ -516,6 +531,13 @@ extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes
     ep.beta = beta;
     ep.gamma = gamma;
     ep.denom = denom;
+    {
+        // fast exact division only for ordinary divisors; d = 0 (all loci fixed -> NaN GRM, calc.jl:52-54), Inf, NaN
+        // or extreme magnitudes take the IEEE divide so that the special values come out exactly as in the reference
+        const double a = fabs(denom);
+        const char *no_fast = getenv("GRM_CUDA_IEEE_DIV");
+        ep.rcp = (a > 1e-200 && a < 1e200 && !(no_fast && no_fast[0] == '1')) ? 1.0 / denom : 0.0;
+    }
     ep.u = d_u;
     if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
     return launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);

@@ -131,6 +131,34 @@ def test_ploidyaware_dosage(ctx, n, p, m, ploidy):
     assert np.array_equal(q.cpu().numpy(), qc)
 
 
+def test_epilogue_division_is_correctly_rounded(ctx):
+    """The epilogue divides by a launch constant with a reciprocal + two FMA corrections; it must equal IEEE `/`."""
+    from grm_b200 import device as D
+
+    n, p, m = 513, 1900, 4
+    A = synth.dosage(n, p, m, seed=41)
+    c = O.dosage_codes(A, m)
+    Cint = O.np_gram_int(c).astype(np.float64)
+    codes, colsum, flags = D.pack_dosage(ctx, to_dev(A), m)
+    iu = np.triu_indices(n)
+    for alpha, denom in [(1.0, 3.0), (1.0 / 16, float(p)), (1.0, 99991.0), (0.25, 100000.0), (1.0, np.pi), (1.0, 1.0 / 3),
+                         (1.0, 7e-3), (1.0, 2.0 ** 31 - 1), (1.0, -1237.0)]:
+        G = D.syrk_i8_f64(ctx, codes, p, alpha, 0.0, 0.0, denom)
+        ctx.synchronize()
+        want = (Cint * alpha) / denom
+        assert np.array_equal(G.cpu().numpy().T[iu], want[iu]), (alpha, denom)
+    # rank-1 mode with arbitrary FP64 terms
+    rng = np.random.default_rng(3)
+    import torch
+
+    u = rng.standard_normal(n) * 1e3
+    for beta, gamma, denom in [(0.5, 123.456, 24944.479067879984), (1.0, -7.0, 0.37)]:
+        G = D.syrk_i8_f64(ctx, codes, p, 0.25, beta, gamma, denom, u=torch.from_numpy(u).cuda())
+        ctx.synchronize()
+        want = ((Cint * 0.25 - beta * (u[:, None] + u[None, :])) + gamma) / denom
+        assert np.array_equal(G.cpu().numpy().T[iu], want[iu]), (beta, gamma, denom)
+
+
 def test_integer_centring_statistics(ctx):
     """r_i, T_i, sum S, sum S^2 are exact integers; u, W2 and d follow from them."""
     from grm_b200 import device as D
