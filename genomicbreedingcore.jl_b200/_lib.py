@@ -25,6 +25,7 @@ ERR_NOT_DOSAGE = 9
 ERR_OVERFLOW = 10
 
 PATH_AUTO, PATH_I8, PATH_F64 = 0, 1, 2
+MISSING_ERROR, MISSING_MEANFILL = 0, 1
 LOC_HOST, LOC_DEVICE = 0, 1
 
 
@@ -39,7 +40,7 @@ class Options(C.Structure):
         ("output_location", C.c_int32),
         ("rank", C.c_int32),
         ("world", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("missing_policy", C.c_int32),
         ("chunk_loci", C.c_int64),
     ]
 
@@ -92,8 +93,8 @@ SIGNATURES = {
     "grm_cuda_dosage_centre": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, C.POINTER(_f64)]),
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "grm_cuda_locus_stats_i8": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "grm_cuda_locus_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32]),
-    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _vp, _i64, _i32, _i32]),
+    "grm_cuda_locus_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32]),
+    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _i64, _i32, _i32]),
     "grm_cuda_scale_mirror": (_i32, [_vp, _vp, _i64, _i64, _f64]),
     "grm_cuda_mirror": (_i32, [_vp, _vp, _i64, _i64]),
     "grm_cuda_tile_edge": (_i32, []),

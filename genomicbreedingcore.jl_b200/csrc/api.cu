@@ -12,10 +12,11 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
                           double *eps_total);
 extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom);
 extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                            double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate);
+                                            double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate,
+                                            int32_t skip_missing);
 extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                     int32_t centred, double ploidy, const double *d_q, int32_t accumulate, double *d_G,
-                                     int64_t ldg, int32_t rank, int32_t world);
+                                     int32_t centred, double ploidy, const double *d_q, int32_t accumulate,
+                                     int32_t fill_missing, double *d_G, int64_t ldg, int32_t rank, int32_t world);
 extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                          const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
                                          int32_t accumulate);
@@ -302,6 +303,10 @@ struct Timer {
 };
 
 int32_t flags_to_status(uint32_t f) {
+    if (f & 8u) {
+        grm_set_error("a locus has no valid (non-missing) cell: its mean fill is undefined");
+        return GRM_CUDA_ERR_MISSING;
+    }
     if (f & 1u) {
         grm_set_error("allele_frequencies contains missing (NaN) values; the reference GRM functions throw on missing data "
                       "(src/grm/calc.jl:127,205) — filter or impute first");
@@ -335,6 +340,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
     const bool in_host = o.input_location == GRM_CUDA_LOC_HOST;
     const bool out_host = o.output_location == GRM_CUDA_LOC_HOST;
     const bool sharded = o.world > 1;
+    const bool meanfill = o.missing_policy == GRM_CUDA_MISSING_MEANFILL;
     cudaStream_t st = ctx->stream;
     cudaEvent_t *ev = ctx->ev;
 
@@ -414,6 +420,17 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             uint32_t h_flags = 0;
             GRM_CUDA_TRY(cudaMemcpyAsync(&h_flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             GRM_CUDA_TRY(cudaStreamSynchronize(st));
+            if (meanfill && (h_flags & 1u) && !(h_flags & 2u)) {
+                // missing cells + mean-fill policy: the filled values are not dosages -> FP64 path
+                if (o.path == GRM_CUDA_PATH_I8) {
+                    grm_set_error("int8 path requested but missing cells must be mean-filled (FP64 path)");
+                    return GRM_CUDA_ERR_NOT_DOSAGE;
+                }
+                path = GRM_CUDA_PATH_F64;
+                GRM_CUDA_TRY(cudaMemsetAsync(d_flags, 0, 16 * sizeof(uint32_t), st));
+                feed.issued = 0;
+                continue;
+            }
             GRM_TRY(flags_to_status(h_flags));
             if (h_flags & 4u) {
                 // a later chunk broke the denominator guessed from the first one
@@ -461,10 +478,10 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 const double *dc;
                 GRM_TRY(feed.acquire(c, &dc));
                 GRM_TRY(grm_cuda_locus_stats_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), ctx->q.as<double>() + feed.k0(c),
-                                                 d_stats, d_flags, c > 0));
+                                                 d_stats, d_flags, c > 0, meanfill ? 1 : 0));
                 GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), centred ? 1 : 0,
-                                          static_cast<double>(ploidy), ctx->q.as<double>() + feed.k0(c), c > 0, dG, ldG,
-                                          o.rank, o.world));
+                                          static_cast<double>(ploidy), ctx->q.as<double>() + feed.k0(c), c > 0,
+                                          meanfill ? 1 : 0, dG, ldG, o.rank, o.world));
                 GRM_TRY(feed.release(c));
             }
             GRM_CUDA_TRY(cudaEventRecord(ev[1], st));

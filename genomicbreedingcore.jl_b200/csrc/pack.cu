@@ -185,29 +185,43 @@ locus_stats_i8_kernel(const int32_t *__restrict__ colsum, int64_t p, double n, d
 // one warp per locus column, lanes stride over entries with a fixed shuffle tree: bit-reproducible column means
 __global__ void __launch_bounds__(256)
 colmean_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, double *__restrict__ q,
-                   uint32_t *__restrict__ flags) {
+                   uint32_t *__restrict__ flags, int skip_missing) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t k = static_cast<int64_t>(blockIdx.x) * 8 + warp;
     if (k >= p) return;
     const double *col = A + k * lda;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     uint32_t bad = 0;
+    int cnt = 0;  // valid cells seen by this lane (skip_missing only)
     int64_t i = lane;
-    for (; i + 96 < n; i += 128) {
-        const double a = __ldg(col + i), b = __ldg(col + i + 32), c = __ldg(col + i + 64), d = __ldg(col + i + 96);
-        s0 += a;
-        s1 += b;
-        s2 += c;
-        s3 += d;
+    if (skip_missing) {
+        // mean(skipmissing(column)) (src/genomes/filter.jl:632-635): a NaN cell contributes nothing
+        for (; i < n; i += 32) {
+            const double a = __ldg(col + i);
+            if (a == a) {
+                s0 += a;
+                ++cnt;
+            }
+        }
+    } else {
+        for (; i + 96 < n; i += 128) {
+            const double a = __ldg(col + i), b = __ldg(col + i + 32), c = __ldg(col + i + 64), d = __ldg(col + i + 96);
+            s0 += a;
+            s1 += b;
+            s2 += c;
+            s3 += d;
+        }
+        for (; i < n; i += 32) s0 += __ldg(col + i);
     }
-    for (; i < n; i += 32) s0 += __ldg(col + i);
     double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) {
         if (s != s) bad |= FLAG_NAN;  // NaN anywhere (or Inf-Inf) poisons the column sum
         else if (isinf(s)) bad |= FLAG_INF;
-        q[k] = s / static_cast<double>(n);
+        if (skip_missing && cnt == 0) bad |= 8u;  // no valid cell: the fill value is undefined
+        q[k] = s / static_cast<double>(skip_missing ? cnt : n);
         if (bad) atomicOr(flags, bad);
     }
 }
@@ -471,14 +485,16 @@ extern "C" int32_t grm_cuda_locus_stats_i8(grm_cuda_ctx *ctx, const int32_t *d_c
 }
 
 extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                            double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate) {
+                                            double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate,
+                                            int32_t skip_missing) {
     if (!ctx || !dA || !d_q || !d_stats || !d_flags || p < 1 || n < 1 || lda < n) {
         grm_set_error("locus_stats_f64: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     GRM_TRY(ctx->partials.reserve(3 * RED_BLOCKS * sizeof(double)));
-    colmean_f64_kernel<<<static_cast<unsigned>((p + 7) / 8), 256, 0, ctx->stream>>>(dA, n, p, lda, d_q, d_flags);
+    colmean_f64_kernel<<<static_cast<unsigned>((p + 7) / 8), 256, 0, ctx->stream>>>(dA, n, p, lda, d_q, d_flags,
+                                                                                    skip_missing);
     GRM_CUDA_TRY(cudaGetLastError());
     locus_stats_f64_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_q, p, ctx->partials.as<double>());
     GRM_CUDA_TRY(cudaGetLastError());

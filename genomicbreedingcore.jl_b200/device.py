@@ -147,7 +147,7 @@ def rowdot_i8(ctx, codes, p: int, w):
     return u
 
 
-def locus_stats_f64(ctx, A_pn, accumulate: bool = False, q=None, stats=None, flags=None):
+def locus_stats_f64(ctx, A_pn, accumulate: bool = False, q=None, stats=None, flags=None, skip_missing: bool = False):
     torch = _torch()
     p, n = A_pn.shape
     dev = A_pn.device
@@ -159,20 +159,20 @@ def locus_stats_f64(ctx, A_pn, accumulate: bool = False, q=None, stats=None, fla
         flags = torch.zeros((16,), dtype=torch.int32, device=dev)
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_locus_stats_f64(ctx.handle, _ptr(A_pn), n, p, n, _ptr(q), _ptr(stats), _ptr(flags),
-                                                1 if accumulate else 0))
+                                                1 if accumulate else 0, 1 if skip_missing else 0))
     return q, stats, flags
 
 
 def syrk_f64(ctx, A_pn, centred: bool, ploidy: float = 2.0, q=None, accumulate: bool = False, rank: int = 0,
-             world: int = 1, out=None):
+             world: int = 1, out=None, fill_missing: bool = False):
     torch = _torch()
     p, n = A_pn.shape
     if out is None:
         out = torch.zeros((n, n), dtype=torch.float64, device=A_pn.device)
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_syrk_f64(ctx.handle, _ptr(A_pn), n, p, n, 1 if centred else 0, float(ploidy),
-                                         _ptr(q) if q is not None else None, 1 if accumulate else 0, _ptr(out), n,
-                                         rank, world))
+                                         _ptr(q) if q is not None else None, 1 if accumulate else 0,
+                                         1 if fill_missing else 0, _ptr(out), n, rank, world))
     return out
 
 

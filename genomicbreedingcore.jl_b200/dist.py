@@ -120,14 +120,19 @@ class ShardedGRM:
             if self.ploidy is None:
                 alpha, beta, gamma, denom, u = 1.0 / (m * m), 0.0, 0.0, float(p), None
             else:
-                sums = r_ = T_ = None
-                for r in range(self.world):  # exact integers: any order gives the same bits
-                    a, b = loci_range(p, r, self.world)
-                    if b <= a:
-                        continue
-                    sums, r_, T_ = D.dosage_stats(ctx, self.codes_all[r], b - a, self.colsum_all[r], sums, r_, T_,
-                                                  accumulate=sums is not None)
+                # integer statistics of the rank's OWN loci, then an exact integer all-reduce (r, T and the two sums
+                # are additive over loci): no rank re-reads the other slabs, and any rank count gives the same bits
+                if pc > 0:
+                    sums, r_, T_ = D.dosage_stats(ctx, self.codes_slab, pc, self.colsum_slab)
                     self.launches += 2
+                else:
+                    sums = torch.zeros((2,), dtype=torch.int64, device=self.G.device)
+                    r_ = torch.zeros((n,), dtype=torch.int64, device=self.G.device)
+                    T_ = torch.zeros((n,), dtype=torch.int64, device=self.G.device)
+                if self.world > 1:
+                    packed = torch.cat([sums, r_, T_])
+                    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+                    sums, r_, T_ = packed[:2].contiguous(), packed[2:2 + n].contiguous(), packed[2 + n:].contiguous()
                 u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r_, T_, p, m, self.ploidy)
                 self.launches += 1
             self.scale = denom

@@ -29,7 +29,8 @@ def _raise_for(err: _lib.GrmCudaError):
 
 def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.Context] = None,
              path: int = _lib.PATH_AUTO, denominator: int = 0, max_iter: int = 1_000, skip_repair: bool = False,
-             chunk_loci: int = 0, rank: int = 0, world: int = 1, out: Optional[np.ndarray] = None):
+             chunk_loci: int = 0, rank: int = 0, world: int = 1, out: Optional[np.ndarray] = None,
+             missing: str = "error"):
     """The C-ABI call a Julia `ccall` shim makes, on host buffers: grm_cuda_simple (ploidy is None) or
     grm_cuda_ploidyaware.  `A` is n x p (NaN = missing); a strided view of a larger Fortran array is passed with its
     leading dimension, no copy.  Returns (G, info dict).  Raises GrmCudaError with the library status."""
@@ -50,6 +51,7 @@ def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.
     o.skip_repair = 1 if skip_repair else 0
     o.chunk_loci = int(chunk_loci)
     o.rank, o.world = rank, world
+    o.missing_policy = {"error": _lib.MISSING_ERROR, "meanfill": _lib.MISSING_MEANFILL}[missing]
     info = _lib.new_info()
     if ploidy is None:
         st = ctx.lib.grm_cuda_simple(ctx.handle, A.ctypes.data, n, p, lda, out.ctypes.data, ldg, C.byref(o),
@@ -62,12 +64,12 @@ def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.
 
 
 def _run(genomes: Genomes, centred: bool, ploidy: int, max_iter: int, verbose: bool, ctx, path, denominator,
-         skip_repair) -> GRM:
+         skip_repair, missing="error") -> GRM:
     if not checkdims(genomes):
         raise ArgumentError("The Genomes struct is corrupted ☹.")  # calc.jl:118-120, :191-193
     try:
         G, info = grm_call(genomes.allele_frequencies, ploidy if centred else None, ctx=ctx, path=path,
-                           denominator=denominator, max_iter=max_iter, skip_repair=skip_repair)
+                           denominator=denominator, max_iter=max_iter, skip_repair=skip_repair, missing=missing)
     except _lib.GrmCudaError as e:
         _raise_for(e)
     if verbose:  # calc.jl:67-69
@@ -81,17 +83,19 @@ def _run(genomes: Genomes, centred: bool, ploidy: int, max_iter: int, verbose: b
 
 
 def grmsimple(genomes: Genomes, max_iter: int = 1_000, verbose: bool = False, *, ctx: Optional[_lib.Context] = None,
-              path: int = _lib.PATH_AUTO, denominator: int = 0, skip_repair: bool = False) -> GRM:
-    """G = A*A'/p then inflatediagonals! (calc.jl:115-142).  Keyword-only extras select the backend path."""
-    return _run(genomes, False, 0, max_iter, verbose, ctx, path, denominator, skip_repair)
+              path: int = _lib.PATH_AUTO, denominator: int = 0, skip_repair: bool = False,
+              missing: str = "error") -> GRM:
+    """G = A*A'/p then inflatediagonals! (calc.jl:115-142).  Keyword-only extras select the backend path;
+    missing="meanfill" (extension) fills missing cells with mean(skipmissing(locus)) instead of raising."""
+    return _run(genomes, False, 0, max_iter, verbose, ctx, path, denominator, skip_repair, missing)
 
 
 def grmploidyaware(genomes: Genomes, ploidy: int = 2, max_iter: int = 1_000, verbose: bool = False, *,
                    ctx: Optional[_lib.Context] = None, path: int = _lib.PATH_AUTO, denominator: int = 0,
-                   skip_repair: bool = False) -> GRM:
+                   skip_repair: bool = False, missing: str = "error") -> GRM:
     """q = colmean(A); Z = ploidy*(A-0.5) - 1q'; G = Z*Z'/(ploidy*sum(q(1-q))) then inflatediagonals!
     (calc.jl:189-217)."""
-    return _run(genomes, True, ploidy, max_iter, verbose, ctx, path, denominator, skip_repair)
+    return _run(genomes, True, ploidy, max_iter, verbose, ctx, path, denominator, skip_repair, missing)
 
 
 def inflatediagonals(X: np.ndarray, max_iter: int = 1_000, verbose: bool = False, *,

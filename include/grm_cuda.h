@@ -56,6 +56,14 @@ typedef enum grm_cuda_status {
 #define GRM_CUDA_PATH_I8   1 /* exact int8 tcgen05 SYRK + FP64 epilogue                                        */
 #define GRM_CUDA_PATH_F64  2 /* FP64 upper-triangular SYRK (pool-seq / continuous frequencies)                 */
 
+/* What a NaN ("missing") cell does.  The reference's GRM functions have no missing-value handling: any `missing`
+ * makes them throw (calc.jl:127,205).  MEANFILL is an extension for pool-seq data with scattered missing cells
+ * (BASELINE config 4): a missing x_ik is replaced by mean(skipmissing(column k)) — the per-locus quantity
+ * filterbymaf uses (src/genomes/filter.jl:632-635) — i.e. the result equals the reference GRM of the mean-imputed
+ * matrix.  It runs on the FP64 path (filled values are not dosages). */
+#define GRM_CUDA_MISSING_ERROR    0
+#define GRM_CUDA_MISSING_MEANFILL 1
+
 #define GRM_CUDA_LOC_HOST   0
 #define GRM_CUDA_LOC_DEVICE 1
 
@@ -71,7 +79,7 @@ typedef struct grm_cuda_options {
     int32_t output_location; /* GRM_CUDA_LOC_*: where G lives                                                  */
     int32_t rank;            /* tile sharding: this process computes tiles t with owner(t) == rank ...         */
     int32_t world;           /* ... out of `world` ranks (1 = everything).  Sharded calls imply skip_repair.   */
-    int32_t reserved0;
+    int32_t missing_policy;  /* GRM_CUDA_MISSING_*                                                             */
     int64_t chunk_loci;      /* loci per host->device streaming chunk; 0 = automatic                           */
 } grm_cuda_options;
 
@@ -182,17 +190,21 @@ int32_t grm_cuda_locus_stats_i8(grm_cuda_ctx *ctx, const int32_t *d_colsum, int6
                                 int32_t ploidy, double *d_q, double *d_w, double *d_stats);
 
 /* FP64 path: q[k] = mean_i A[i,k] with a fixed summation order; flags as in grm_cuda_pack_dosage (bits 1,2);
- * stats = { sum q(1-q), 0, sum q }; accumulate != 0 adds to the existing stats (loci streamed in chunks). */
+ * stats = { sum q(1-q), 0, sum q }; accumulate != 0 adds to the existing stats (loci streamed in chunks).
+ * skip_missing != 0: q[k] = mean over the non-NaN cells (NaN no longer raises flag 1; a locus with no valid cell
+ * raises flag 8). */
 int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                 double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate);
+                                 double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate,
+                                 int32_t skip_missing);
 
 /* FP64 upper-triangular SYRK over owned tiles, raw sums (no division):
  *   centred == 0: G (+)= A*A'            (grmsimple, calc.jl:127)
  *   centred == 1: G (+)= Z*Z', z_ik = fl(fl(ploidy*fl(A_ik - 0.5)) - q_k) formed on operand load (calc.jl:198,205)
- * accumulate != 0 adds to G (loci streamed in chunks).  FP64 tensor path (mma.sync m8n8k4.f64). */
+ * accumulate != 0 adds to G (loci streamed in chunks).  fill_missing != 0 replaces a NaN A_ik by q_k before anything
+ * else (d_q required).  FP64 tensor path (DMMA). */
 int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int32_t centred,
-                          double ploidy, const double *d_q, int32_t accumulate, double *d_G, int64_t ldg,
-                          int32_t rank, int32_t world);
+                          double ploidy, const double *d_q, int32_t accumulate, int32_t fill_missing, double *d_G,
+                          int64_t ldg, int32_t rank, int32_t world);
 
 /* G[i,j] = G[i,j]/denom for i <= j, then G[j,i] = G[i,j] for i < j (whole matrix; exact symmetry). */
 int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom);

@@ -25,7 +25,7 @@ Base.@kwdef mutable struct Options
     output_location::Int32 = 0
     rank::Int32 = 0
     world::Int32 = 1
-    reserved0::Int32 = 0
+    missing_policy::Int32 = 0
     chunk_loci::Int64 = 0
 end
 

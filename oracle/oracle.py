@@ -186,6 +186,20 @@ def np_truth_ploidyaware(A, ploidy=2):
     return np.asarray((L @ L.T) / np.longdouble(d), dtype=np.float64), q, d
 
 
+def np_meanfill(A):
+    """Extension oracle: replace each missing (NaN) cell by mean(skipmissing(column)) — the per-locus mean the
+    reference's filterbymaf uses (src/genomes/filter.jl:632-635).  The mean-fill policy of the CUDA path must equal
+    the reference GRM functions applied to this matrix."""
+    A = np.array(A, dtype=np.float64, order="F", copy=True)
+    valid = ~np.isnan(A)
+    cnt = valid.sum(axis=0)
+    s = np.where(valid, A, 0.0).sum(axis=0)
+    fill = s / cnt
+    idx = np.where(~valid)
+    A[idx] = fill[idx[1]]
+    return A
+
+
 def np_det_julia(X):
     """det(X) the way Julia evaluates it: LAPACK getrf, sequential product of diag(U), sign from the pivots."""
     from scipy.linalg import lapack

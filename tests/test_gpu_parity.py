@@ -292,6 +292,40 @@ def test_error_paths():
     assert G.shape == (1, 1)
 
 
+# Extension (BASELINE config 4: pool-seq with missing cells): mean-fill policy == reference GRM of the imputed matrix
+@pytest.mark.parametrize("gen,sparsity", [("continuous", 0.01), ("continuous", 0.2), ("dosage", 0.05)])
+def test_meanfill_policy_matches_reference_on_mean_imputed_matrix(gen, sparsity):
+    base = synth.continuous(150, 2000, seed=51) if gen == "continuous" else synth.dosage(150, 2000, 2, seed=51)
+    A = synth.add_missing(base, sparsity, seed=52)
+    F = O.np_meanfill(A)
+    assert np.isnan(A).any() and not np.isnan(F).any()
+    for ploidy in (None, 2):
+        with pytest.raises(_lib.GrmCudaError) as e:  # default policy = the reference's behaviour: throw
+            grm_call(A, ploidy, skip_repair=True)
+        assert e.value.status == _lib.ERR_MISSING
+        G, info = grm_call(A, ploidy, skip_repair=True, missing="meanfill")
+        assert info["path"] == _lib.PATH_F64
+        ref = O.c_grmsimple_raw(F, nthreads=4)[1] if ploidy is None else O.c_grmploidyaware_raw(F, ploidy, nthreads=4)[1]
+        assert relerr(G, ref) <= RTOL_F64
+        assert np.array_equal(G, G.T)
+        G2, _ = grm_call(A, ploidy, skip_repair=True, missing="meanfill", chunk_loci=256)
+        assert relerr(G2, G) <= 1e-13
+        Gf, infof = grm_call(A, ploidy, missing="meanfill")  # with the repair
+        st, X, it, tot = O.np_inflatediagonals(G)
+        assert infof["repair_iters"] == it and np.array_equal(Gf, X)
+    # a locus with no valid cell has no defined fill
+    B = np.array(A, order="F")
+    B[:, 7] = np.nan
+    with pytest.raises(_lib.GrmCudaError) as e:
+        grm_call(B, 2, skip_repair=True, missing="meanfill")
+    assert e.value.status == _lib.ERR_MISSING
+    # without missing cells the policy changes nothing (dosages stay on the int8 path)
+    if gen == "dosage":
+        G0, i0 = grm_call(base, 2, skip_repair=True)
+        G1, i1 = grm_call(base, 2, skip_repair=True, missing="meanfill")
+        assert i1["path"] == _lib.PATH_I8 and np.array_equal(G0, G1)
+
+
 # P9: ordering follows the input order of entries
 def test_row_order_follows_entries():
     A = synth.dosage(60, 500, 4, seed=13)
