@@ -284,7 +284,7 @@ def run_b200(args, wl):
         "traffic": tr.get("syrk_i8_dram_bytes_per_launch"),
         "peak_note": f"int8 dense = 2 x measured sustained bf16 ({peaks['source']}); unit counts int8 ops (1 MAC = 2 ops); "
                      f"cuBLASLt int8 8192^3 measured on this pool: 3213 burst / 2579 sustained TOP/s (profiles/)",
-        "ms_per_launch": syrk_ms, "algorithmic_ops_per_launch": alg_ops, "tiles_per_launch": int(tiles_rank),
+        "ms_per_launch": syrk_ms, "algorithmic_ops_per_launch": alg_ops, "tiles_owned": int(tiles_rank),
     }
     pack_ms = stage_ms.get("ms_pack", float("nan"))
     pack_bytes = 9.0 * n * pc  # 8 B read + 1 B written per cell
@@ -389,7 +389,7 @@ def run_b200(args, wl):
                    "step": "FP64 A resident in HBM -> pack/stats -> rowdot -> SYRK -> mirror (raw GRM); the "
                            "inflatediagonals! repair is in e2e, not in value",
                    "l2": "inputs larger than L2 (FP64 input and int8 codes >> 126 MB)",
-                   "parallelism": f"loci-split pack + int8 all-gather + upper-triangular tile sharding x{world}" if world > 1
+                   "parallelism": f"loci-split pack + tcgen05 SYRK over own loci + int32 reduce-scatter onto tile owners x{world} ({sharded.mode})" if world > 1
                    else "single GPU", "macs_per_step": macs(n, p)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack,
         "cpu_baseline": cpu, "stage_ms": stage_ms,

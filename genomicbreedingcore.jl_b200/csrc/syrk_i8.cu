@@ -43,6 +43,7 @@ struct EpiParams {
     double alpha, beta, gamma, denom;
     double rcp;  // RN(1/denom) when the fast exact division applies, else 0
     const double *u;
+    const int32_t *slots;  // mode 3: slot of tile t in the packed int32 tile buffer C ([slot][256 cols][256 rows])
 };
 
 // Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
@@ -64,6 +65,7 @@ __device__ __forceinline__ double div_const(double v, double d, double rcp) {
 template <int EPI>
 __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int64_t row, bool row_ok, int64_t col0, double ui,
                                                const EpiParams &ep) {
+    if (EPI == 3) return;  // packed tiles are stored by epilogue_store_packed
     if (row_ok && col0 < ep.n) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -83,6 +85,13 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int64_t 
             }
         }
     }
+}
+
+// mode 3: the raw int32 tile, contiguous ([col][row] inside the tile; rows/cols beyond n hold exact zeros), for the
+// loci-split multi-GPU path where partial tiles of different GPUs are summed by a reduce-scatter
+__device__ __forceinline__ void epilogue_store_packed(const uint32_t (&r)[32], int32_t *tile, int row_local, int c0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tile[(c0 + j) * 256 + row_local] = static_cast<int32_t>(r[j]);
 }
 
 template <int EPI>
@@ -333,12 +342,15 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             const bool row_ok = row < ep.n;
             double ui = 0.0;
             if (EPI == 2 && row_ok) ui = ep.u[row];
+            int32_t *packed = nullptr;
+            if (EPI == 3) packed = ep.C + static_cast<int64_t>(ep.slots[t]) * 65536;
 #pragma unroll 1
             for (int c0 = 0; c0 < 256; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
                 tmem_wait_ld();
-                epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
+                if (EPI == 3) epilogue_store_packed(r, packed, 128 * static_cast<int>(cta) + quarter * 32 + lane, c0);
+                else epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
             }
             tc_fence_before();
             __syncwarp();
@@ -541,4 +553,140 @@ extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes
     ep.u = d_u;
     if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
     return launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// loci-split (K-split) multi-GPU support: every GPU contracts ITS loci over ALL upper-triangular tiles and writes raw
+// int32 tiles into a buffer laid out for a reduce-scatter ([destination rank][slot][256 x 256]); after the exchange
+// each GPU finalises the tiles it owns.  Exchange volume 4 n^2 / 2 bytes per GPU instead of n p for the all-gather of
+// the codes — the better choice whenever p > 4 n (BASELINE C2, C3).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PackedPlan {
+    std::vector<int2> tiles;     // all upper-triangular tiles, global order
+    std::vector<int32_t> slots;  // slot in [world][tiles_max] of each tile
+    int64_t tiles_max = 0;
+};
+
+void make_packed_plan(int64_t n, int32_t world, PackedPlan &pl) {
+    std::vector<int2> order;
+    grm_tile_order(n, order);
+    const int64_t total = static_cast<int64_t>(order.size());
+    pl.tiles_max = (total + world - 1) / world;
+    pl.tiles.clear();
+    pl.slots.clear();
+    for (int32_t r = 0; r < world; ++r) {
+        int64_t b, e;
+        grm_tile_range(total, r, world, &b, &e);
+        for (int64_t t = b; t < e; ++t) {
+            pl.tiles.push_back(make_int2(order[t].x * GRM_TILE, order[t].y * GRM_TILE));
+            pl.slots.push_back(static_cast<int32_t>(r * pl.tiles_max + (t - b)));
+        }
+    }
+}
+
+// G tile <- formula(reduced int32 tile): block = one owned tile, same arithmetic as the fused SYRK epilogue
+template <int EPI>
+__global__ void __launch_bounds__(256)
+finalize_tiles_kernel(const int32_t *__restrict__ packed, const int2 *__restrict__ tiles, EpiParams ep) {
+    const int2 tc = tiles[blockIdx.x];
+    const int32_t *tile = packed + static_cast<int64_t>(blockIdx.x) * 65536;
+    for (int idx = threadIdx.x; idx < 65536; idx += 256) {
+        const int cl = idx >> 8, rl = idx & 255;
+        const int64_t row = tc.x + rl, col = tc.y + cl;
+        if (row < ep.n && col < ep.n) {
+            double v = static_cast<double>(tile[idx]) * ep.alpha;
+            if (EPI == 2) v = (v - ep.beta * (__ldg(ep.u + row) + __ldg(ep.u + col))) + ep.gamma;
+            ep.G[row + col * ep.ldg] = (ep.rcp != 0.0) ? div_const(v, ep.denom, ep.rcp) : v / ep.denom;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world) {
+    if (n < 1 || world < 1) return -1;
+    const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
+    return (T * (T + 1) / 2 + world - 1) / world;
+}
+
+extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                           int32_t world, int32_t *d_packed) {
+    if (!ctx || !d_codes || !d_packed || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1) {
+        grm_set_error("syrk_i8_packed: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    CUtensorMap tmap;
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, 1, &tmap));
+    TileListCache &tc = ctx->tiles_packed;
+    if (tc.n != n || tc.world != world) {
+        PackedPlan pl;
+        make_packed_plan(n, world, pl);
+        const size_t nt = pl.tiles.size();
+        GRM_TRY(tc.buf.reserve(nt * (sizeof(int2) + sizeof(int32_t))));
+        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, pl.tiles.data(), nt * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.as<int2>() + nt, pl.slots.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        tc.n = n;
+        tc.world = world;
+        tc.rank = 0;
+        tc.count = static_cast<int32_t>(nt);
+    }
+    const int count = tc.count;
+    EpiParams ep{};
+    ep.n = n;
+    ep.C = d_packed;
+    ep.slots = reinterpret_cast<const int32_t *>(tc.buf.as<int2>() + count);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(SMEM2_BYTES)));
+        attr_set = true;
+    }
+    // unused slots of the reduce-scatter layout must be defined (they are summed too)
+    const int64_t tiles_max = grm_cuda_packed_tiles_max(n, world);
+    if (static_cast<int64_t>(count) != tiles_max * world)
+        GRM_CUDA_TRY(cudaMemsetAsync(d_packed, 0, static_cast<size_t>(tiles_max) * world * 65536 * sizeof(int32_t),
+                                     ctx->stream));
+    const int kbs = static_cast<int>((p + BK - 1) / BK);
+    const int pairs = std::min(count, ctx->num_sms / 2);
+    syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), count, kbs, kbs,
+                                                                                 ep);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha,
+                                           double beta, double gamma, double denom, const double *d_u, double *d_G,
+                                           int64_t ldg, int32_t rank, int32_t world) {
+    if (!ctx || !d_reduced || !d_G || n < 1 || ldg < n || world < 1 || rank < 0 || rank >= world ||
+        (beta != 0.0 && !d_u)) {
+        grm_set_error("finalize_tiles: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int2 *d_tiles;
+    int count;
+    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+    if (count == 0) return GRM_CUDA_OK;
+    EpiParams ep{};
+    ep.n = n;
+    ep.G = d_G;
+    ep.ldg = ldg;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.gamma = gamma;
+    ep.denom = denom;
+    const double a = fabs(denom);
+    ep.rcp = (a > 1e-200 && a < 1e200) ? 1.0 / denom : 0.0;
+    ep.u = d_u;
+    if (beta == 0.0 && gamma == 0.0) finalize_tiles_kernel<1><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep);
+    else finalize_tiles_kernel<2><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
 }

@@ -100,6 +100,27 @@ def syrk_i8_f64(ctx, codes, p: int, alpha: float, beta: float, gamma: float, den
     return out
 
 
+def syrk_i8_packed(ctx, codes, p: int, world: int, out=None):
+    """Raw int32 tiles of ALL upper-triangular tiles over this GPU's loci, in reduce-scatter layout
+    [world * tiles_max, 65536]."""
+    torch = _torch()
+    n, ldc = codes.shape
+    tmax = ctx.lib.grm_cuda_packed_tiles_max(n, world)
+    if out is None:
+        out = torch.zeros((world * tmax, 65536), dtype=torch.int32, device=codes.device)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_syrk_i8_packed(ctx.handle, _ptr(codes), n, p, ldc, world, _ptr(out)))
+    return out
+
+
+def finalize_tiles(ctx, reduced, n: int, alpha: float, beta: float, gamma: float, denom: float, u, G, rank: int,
+                   world: int):
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_finalize_tiles(ctx.handle, _ptr(reduced), n, alpha, beta, gamma, denom,
+                                               _ptr(u) if u is not None else None, _ptr(G), n, rank, world))
+    return G
+
+
 def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
     torch = _torch()
     dev = colsum.device

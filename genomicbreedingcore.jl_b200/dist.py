@@ -1,6 +1,19 @@
 """Multi-GPU GRM: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
 
-Decomposition (north_star):
+Two decompositions of the int8 path; both start from loci-split input (rank r holds, and end to end uploads over its
+own PCIe link, only the FP64 columns of its loci range and packs them on its GPU) and both END with the finished
+upper-triangular 256 x 256 tiles sharded over the ranks in contiguous runs of an L2-friendly order (grm_cuda_tile_*):
+
+  "ksplit" (p > 4n: BASELINE C2, C3) — every rank contracts ITS loci over ALL tiles (tcgen05 SYRK, raw int32 tiles),
+      then ONE reduce-scatter (int32 sum, exact) leaves each rank with the tiles it owns, which it finalises in FP64.
+      Exchange: 2 n^2 bytes per GPU, independent of p.
+  "gather" (otherwise, e.g. C5) — the packed int8 slabs are all-gathered (n p bytes in total) and each rank runs the
+      SYRK over its own tiles with all loci (3-D tensor map over [slab][entry][locus]).
+
+The integer Gram matrix and the integer centring statistics are exact under any partition, so both give bit-identical
+results for any number of ranks.
+
+Decomposition details (north_star):
   * loci are split into `world` contiguous ranges; rank r holds (and, end to end, uploads over its own PCIe link)
     only the FP64 columns of its range and packs them to int8 on its GPU — every input byte crosses PCIe once;
   * the packed int8 slabs (n*p bytes in total — 1/8 of the FP64 input) and the integer column sums are all-gathered:
@@ -63,7 +76,8 @@ def gather_tiles_sum(G_local, group=None):
 class ShardedGRM:
     """Per-rank driver of the sharded int8 path on device-resident loci slabs."""
 
-    def __init__(self, n: int, p: int, ploidy: Optional[int], denominator: int, ctx: _lib.Context, group=None):
+    def __init__(self, n: int, p: int, ploidy: Optional[int], denominator: int, ctx: _lib.Context, group=None,
+                 mode: str = "auto"):
         torch = _torch()
         import torch.distributed as dist
 
@@ -76,10 +90,18 @@ class ShardedGRM:
         self.lds = slab_stride(p, self.world)
         self.L = (p + self.world - 1) // self.world
         dev = torch.device("cuda", ctx.device)
+        if mode == "auto":
+            mode = "ksplit" if (p > 4 * n and self.world > 1) else "gather"
+        self.mode = mode
         self.codes_slab = torch.zeros((n, self.lds), dtype=torch.int8, device=dev)
         self.colsum_slab = torch.zeros((self.lds,), dtype=torch.int32, device=dev)
-        self.codes_all = torch.zeros((self.world, n, self.lds), dtype=torch.int8, device=dev)
-        self.colsum_all = torch.zeros((self.world, self.lds), dtype=torch.int32, device=dev)
+        if mode == "gather":
+            self.codes_all = torch.zeros((self.world, n, self.lds), dtype=torch.int8, device=dev)
+            self.colsum_all = torch.zeros((self.world, self.lds), dtype=torch.int32, device=dev)
+        else:
+            self.tiles_max = ctx.lib.grm_cuda_packed_tiles_max(n, self.world)
+            self.packed = torch.zeros((self.world * self.tiles_max, 65536), dtype=torch.int32, device=dev)
+            self.reduced = torch.zeros((self.tiles_max, 65536), dtype=torch.int32, device=dev)
         self.flags = torch.zeros((16,), dtype=torch.int32, device=dev)
         self.G = torch.zeros((n, n), dtype=torch.float64, device=dev)
         self.launches = 0
@@ -109,12 +131,13 @@ class ShardedGRM:
                 self.launches += 1
             if ev:
                 ev[1].record()
-            if self.world > 1:
-                dist.all_gather_into_tensor(self.codes_all.view(-1, self.lds), self.codes_slab, group=self.group)
-                dist.all_gather_into_tensor(self.colsum_all.view(-1), self.colsum_slab, group=self.group)
-            else:
-                self.codes_all[0].copy_(self.codes_slab)
-                self.colsum_all[0].copy_(self.colsum_slab)
+            if self.mode == "gather":
+                if self.world > 1:
+                    dist.all_gather_into_tensor(self.codes_all.view(-1, self.lds), self.codes_slab, group=self.group)
+                    dist.all_gather_into_tensor(self.colsum_all.view(-1), self.colsum_slab, group=self.group)
+                else:
+                    self.codes_all[0].copy_(self.codes_slab)
+                    self.colsum_all[0].copy_(self.colsum_slab)
             if ev:
                 ev[2].record()
             if self.ploidy is None:
@@ -138,14 +161,36 @@ class ShardedGRM:
             self.scale = denom
             if ev:
                 ev[3].record()
-            D.syrk_i8_f64(ctx, self.codes_all, min(self.L, p), alpha, beta, gamma, denom, u, rank=self.rank,
-                          world=self.world, out=self.G)
-            self.launches += 1
+            if self.mode == "gather":
+                D.syrk_i8_f64(ctx, self.codes_all, min(self.L, p), alpha, beta, gamma, denom, u, rank=self.rank,
+                              world=self.world, out=self.G)
+                self.launches += 1
+                if ev:
+                    ev[4].record()
+            else:
+                D.syrk_i8_packed(ctx, self.codes_slab, max(pc, 1), self.world, out=self.packed)
+                self.launches += 1
+                if ev:
+                    ev[4].record()
+                    ev5, ev6 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if self.world > 1:
+                    dist.reduce_scatter_tensor(self.reduced.view(-1), self.packed.view(-1), op=dist.ReduceOp.SUM,
+                                               group=self.group)
+                else:
+                    self.reduced.copy_(self.packed[:self.tiles_max])
+                if ev:
+                    ev5.record()
+                D.finalize_tiles(ctx, self.reduced, n, alpha, beta, gamma, denom, u, self.G, self.rank, self.world)
+                self.launches += 1
+                if ev:
+                    ev6.record()
             if ev:
-                ev[4].record()
-                ev[4].synchronize()
+                torch.cuda.current_stream().synchronize()
                 for name, i in (("ms_pack", 0), ("ms_exchange", 1), ("ms_rowdot", 2), ("ms_syrk", 3)):
                     timings[name] = timings.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
+                if self.mode == "ksplit":
+                    timings["ms_exchange"] = timings.get("ms_exchange", 0.0) + ev[4].elapsed_time(ev5)
+                    timings["ms_finalize"] = timings.get("ms_finalize", 0.0) + ev5.elapsed_time(ev6)
         flags = int(self.flags[0])
         if flags:
             raise _lib.GrmCudaError(_lib.ERR_MISSING if flags & 1 else _lib.ERR_NONFINITE if flags & 2

@@ -165,6 +165,19 @@ int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n
                              int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
                              double *d_G, int64_t ldg, int32_t rank, int32_t world);
 
+/* Loci-split (K-split) multi-GPU path: each GPU contracts ITS loci over ALL upper-triangular tiles and writes the raw
+ * int32 tiles into d_packed, laid out for a reduce-scatter: [world][tiles_max][256 cols][256 rows] int32, where the
+ * tiles owned by rank r (grm_cuda_tile_at) occupy slots 0.. of block r and unused slots are zero.  After the
+ * reduce-scatter (sum) rank r holds its owned tiles; grm_cuda_finalize_tiles turns them into G tiles with the same
+ * arithmetic as the fused epilogue of grm_cuda_syrk_i8_f64.  Exchange volume 2 n^2 bytes per GPU instead of the n p
+ * bytes of all-gathering the codes: preferable when p > 4 n. */
+int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world);
+int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                int32_t world, int32_t *d_packed);
+int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha, double beta,
+                                double gamma, double denom, const double *d_u, double *d_G, int64_t ldg,
+                                int32_t rank, int32_t world);
+
 /* Exact integer statistics of the codes for the rank-1 centring of grmploidyaware:
  *   r[i] = sum_k codes[i,k]      T[i] = sum_k codes[i,k]*colsum[k]      sums = { sum_k colsum[k], sum_k colsum[k]^2 }
  * (dp4a against the byte planes of colsum; order-independent, hence bit-identical for any chunking / GPU count).

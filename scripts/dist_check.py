@@ -16,10 +16,11 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ctx = grm_b200.Context(local)
 ok = True
+MODE = os.environ.get("GRM_DIST_MODE", "auto")
 for (n, p, m, ploidy) in [(3000, 20000, 4, 4), (1100, 777, 2, None), (2049, 5001, 4, 2)]:
     A = synth.dosage_device(n, p, m, 5, dev)  # same seed on every rank => identical matrix
     k0, k1 = GD.loci_range(p, rank, world)
-    sh = GD.ShardedGRM(n, p, ploidy, m, ctx)
+    sh = GD.ShardedGRM(n, p, ploidy, m, ctx, mode=MODE)
     sh.step(A[k0:k1].contiguous())
     G = sh.gather().clone()
     sh.step(A[k0:k1].contiguous())  # second step after a gather must start from zeros again

@@ -390,6 +390,41 @@ def test_sharded_tiles_union_is_bit_identical(world):
     assert relerr(accc[iu] / 500.0, fullc[iu]) <= 1e-13  # sharded FP64 calls return raw sums
 
 
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("ploidy", [None, 4])
+def test_loci_split_packed_tiles_emulated_ranks(ctx, world, ploidy):
+    """The "ksplit" multi-GPU decomposition with the ranks emulated on one GPU: every rank contracts its own loci
+    over all tiles (raw int32 tiles in reduce-scatter layout), the tile buffers are summed (what the NCCL
+    reduce-scatter does), every rank finalises the tiles it owns; the union must be bit-identical to one call."""
+    import torch
+
+    from grm_b200 import device as D, dist as GD
+
+    n, p, m = 1100, 3001, 4
+    A = synth.dosage(n, p, m, seed=61)
+    full, info = grm_call(A, ploidy, skip_repair=True)
+    At = to_dev(A)
+    tmax = ctx.lib.grm_cuda_packed_tiles_max(n, world)
+    total = torch.zeros((world * tmax, 65536), dtype=torch.int32, device=dev())
+    sums = r = T = None
+    for rk in range(world):
+        k0, k1 = GD.loci_range(p, rk, world)
+        codes, colsum, flags = D.pack_dosage(ctx, At[k0:k1].contiguous(), m)
+        total += D.syrk_i8_packed(ctx, codes, k1 - k0, world)
+        sums, r, T = D.dosage_stats(ctx, codes, k1 - k0, colsum, sums, r, T, accumulate=sums is not None)
+        ctx.synchronize()
+    if ploidy is None:
+        u, (alpha, beta, gamma, denom) = None, (1.0 / (m * m), 0.0, 0.0, float(p))
+    else:
+        u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r, T, p, m, ploidy)
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev())
+    for rk in range(world):
+        D.finalize_tiles(ctx, total[rk * tmax:(rk + 1) * tmax].contiguous(), n, alpha, beta, gamma, denom, u, G, rk, world)
+    D.scale_mirror(ctx, G, 1.0)
+    ctx.synchronize()
+    assert np.array_equal(G.cpu().numpy(), full)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size (BASELINE C2) properties: a checksum of checksums for the integer Gram matrix
 #   sum_j C_ij = sum_k c_ik S_k ,  C_ii = sum_k c_ik^2 ,  sum_ij C_ij = sum_k S_k^2      (S_k = column sums)
