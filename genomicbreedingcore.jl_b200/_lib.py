@@ -23,6 +23,7 @@ ERR_CUDA = 7
 ERR_OOM = 8
 ERR_NOT_DOSAGE = 9
 ERR_OVERFLOW = 10
+ERR_ALL_FILTERED = 11
 
 PATH_AUTO, PATH_I8, PATH_F64 = 0, 1, 2
 MISSING_ERROR, MISSING_MEANFILL = 0, 1
@@ -42,6 +43,8 @@ class Options(C.Structure):
         ("world", C.c_int32),
         ("missing_policy", C.c_int32),
         ("chunk_loci", C.c_int64),
+        ("maf", C.c_double),
+        ("max_locus_sparsity", C.c_double),
     ]
 
 
@@ -63,7 +66,7 @@ class Info(C.Structure):
         ("ms_d2h", C.c_float),
         ("ms_total", C.c_float),
         ("kernel_launches", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("loci_kept", C.c_int32),
     ]
 
     def as_dict(self):
@@ -85,8 +88,9 @@ SIGNATURES = {
     "grm_cuda_simple": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
     "grm_cuda_ploidyaware": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
     "grm_cuda_inflate_diagonals": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
-    "grm_cuda_detect_denominator": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, C.POINTER(_i32)]),
-    "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
+    "grm_cuda_detect_denominator": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
+    "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "grm_cuda_locus_qc": (_i32, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "grm_cuda_syrk_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32]),
     "grm_cuda_syrk_i8_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
     "grm_cuda_packed_tiles_max": (_i64, [_i64, _i32]),
@@ -97,7 +101,7 @@ SIGNATURES = {
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "grm_cuda_locus_stats_i8": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "grm_cuda_locus_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32]),
-    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _i64, _i32, _i32]),
+    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _i32]),
     "grm_cuda_scale_mirror": (_i32, [_vp, _vp, _i64, _i64, _f64]),
     "grm_cuda_mirror": (_i32, [_vp, _vp, _i64, _i64]),
     "grm_cuda_tile_edge": (_i32, []),

@@ -16,7 +16,11 @@ extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA,
                                             int32_t skip_missing);
 extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
                                      int32_t centred, double ploidy, const double *d_q, int32_t accumulate,
-                                     int32_t fill_missing, double *d_G, int64_t ldg, int32_t rank, int32_t world);
+                                     int32_t fill_missing, const uint8_t *d_keep, double *d_G, int64_t ldg, int32_t rank,
+                                     int32_t world);
+extern "C" int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, double maf,
+                                     double max_locus_sparsity, int32_t error_on_missing, double *d_q, uint8_t *d_keep,
+                                     uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags);
 extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                          const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
                                          int32_t accumulate);
@@ -52,6 +56,7 @@ extern "C" const char *grm_cuda_status_string(int32_t s) {
         case GRM_CUDA_ERR_OOM: return "out of memory";
         case GRM_CUDA_ERR_NOT_DOSAGE: return "input is not dosage-quantised";
         case GRM_CUDA_ERR_OVERFLOW: return "int32 accumulator overflow";
+        case GRM_CUDA_ERR_ALL_FILTERED: return "All loci filtered out";
         default: return "unknown status";
     }
 }
@@ -63,6 +68,8 @@ extern "C" void grm_cuda_options_default(grm_cuda_options *o) {
     o->path = GRM_CUDA_PATH_AUTO;
     o->max_iter = 1000;  // calc.jl:41,115,189
     o->world = 1;
+    o->maf = 0.0;
+    o->max_locus_sparsity = 1.0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -135,7 +142,7 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
                       &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->lu, &ctx->lu_work, &ctx->ipiv, &ctx->misc,
                       &ctx->tiles_i8.buf, &ctx->tiles_i8_2cta.buf, &ctx->tiles_f64.buf, &ctx->tiles_packed.buf, &ctx->planes,
-                      &ctx->rT};
+                      &ctx->rT, &ctx->cnt, &ctx->keep};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
@@ -342,6 +349,20 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
     const bool out_host = o.output_location == GRM_CUDA_LOC_HOST;
     const bool sharded = o.world > 1;
     const bool meanfill = o.missing_policy == GRM_CUDA_MISSING_MEANFILL;
+    const bool masked = o.maf > 0.0 || o.max_locus_sparsity < 1.0;
+    if (!(o.maf >= 0.0 && o.maf <= 0.5) || !(o.max_locus_sparsity >= 0.0 && o.max_locus_sparsity <= 1.0)) {
+        grm_set_error("maf must be in [0, 0.5] and max_locus_sparsity in [0, 1]");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    uint8_t *d_keep = nullptr;
+    uint64_t *d_kept = nullptr;
+    if (masked) {
+        GRM_TRY(ctx->keep.reserve(static_cast<size_t>(p) + 64));
+        d_keep = ctx->keep.as<uint8_t>() + 16;
+        d_kept = ctx->keep.as<uint64_t>();
+        GRM_TRY(ctx->q.reserve(static_cast<size_t>((p + 127) / 128 * 128) * sizeof(double)));
+    }
+    int64_t p_eff = p;  // loci that enter the GRM
     cudaStream_t st = ctx->stream;
     cudaEvent_t *ev = ctx->ev;
 
@@ -380,7 +401,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             GRM_TRY(feed.acquire(0, &d0));
             // a sample decides (the first 2^22 cells); the pack pass verifies every cell against it and the loop
             // below retries with m = 64 / falls back to FP64 if a later locus disagrees
-            GRM_TRY(grm_cuda_detect_denominator(ctx, d0, n, feed.len(0), feed.ld_dev(), 1ll << 22, &m));
+            GRM_TRY(grm_cuda_detect_denominator(ctx, d0, n, feed.len(0), feed.ld_dev(), 1ll << 22, masked ? 1 : 0, &m));
         } else if (m < 1 || m > 64 || (m & (m - 1)) != 0) {
             grm_set_error("denominator must be a power of two in [1,64], got %d", m);
             return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -410,16 +431,32 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             int8_t *d_codes = ctx->codes.as<int8_t>();
             int32_t *d_colsum = ctx->colsum.as<int32_t>();
             GRM_CUDA_TRY(cudaMemsetAsync(d_colsum, 0, static_cast<size_t>(ldc) * sizeof(int32_t), st));
+            if (masked) GRM_CUDA_TRY(cudaMemsetAsync(d_kept, 0, sizeof(uint64_t), st));
             for (int64_t c = 0; c < feed.nchunks; ++c) {
                 const double *dc;
                 GRM_TRY(feed.acquire(c, &dc));
+                if (masked)  // the mask of a locus depends on its own column only: decide it while the chunk is staged
+                    GRM_TRY(grm_cuda_locus_qc(ctx, dc, n, feed.len(c), feed.ld_dev(), o.maf, o.max_locus_sparsity, 0,
+                                              ctx->q.as<double>() + feed.k0(c), d_keep + feed.k0(c), d_kept, nullptr, 0,
+                                              d_flags));
                 GRM_TRY(grm_cuda_pack_dosage(ctx, dc, n, feed.len(c), feed.ld_dev(), m, d_codes + feed.k0(c), ldc,
-                                             d_colsum + feed.k0(c), d_flags));
+                                             d_colsum + feed.k0(c), d_flags, masked ? d_keep + feed.k0(c) : nullptr));
                 GRM_TRY(feed.release(c));
             }
             GRM_CUDA_TRY(cudaEventRecord(ev[1], st));
             uint32_t h_flags = 0;
             GRM_CUDA_TRY(cudaMemcpyAsync(&h_flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (masked) {
+                uint64_t h_kept = 0;
+                GRM_CUDA_TRY(cudaMemcpyAsync(&h_kept, d_kept, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+                GRM_CUDA_TRY(cudaStreamSynchronize(st));
+                p_eff = static_cast<int64_t>(h_kept);
+                if (p_eff == 0) {
+                    grm_set_error("All loci filtered out at maf = %g, maximum locus sparsity = %g.", o.maf,
+                                  o.max_locus_sparsity);
+                    return GRM_CUDA_ERR_ALL_FILTERED;
+                }
+            }
             GRM_CUDA_TRY(cudaStreamSynchronize(st));
             if (meanfill && (h_flags & 1u) && !(h_flags & 2u)) {
                 // missing cells + mean-fill policy: the filled values are not dosages -> FP64 path
@@ -449,7 +486,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 continue;
             }
             if (!centred) {
-                denom = static_cast<double>(p);  // calc.jl:127
+                denom = static_cast<double>(p_eff);  // calc.jl:127
                 GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
                 GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, 1.0 / (static_cast<double>(m) * m), 0.0, 0.0,
                                              denom, nullptr, dG, ldG, o.rank, o.world));
@@ -461,7 +498,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 int64_t *d_r = ctx->rT.as<int64_t>() + 2, *d_T = d_r + n;
                 GRM_TRY(grm_cuda_dosage_stats(ctx, d_codes, n, p, ldc, d_colsum, d_sums, d_r, d_T, 0));
                 double sc[4];
-                GRM_TRY(grm_cuda_dosage_centre(ctx, d_sums, d_r, d_T, n, p, m, ploidy, ctx->u.as<double>(), sc));
+                GRM_TRY(grm_cuda_dosage_centre(ctx, d_sums, d_r, d_T, n, p_eff, m, ploidy, ctx->u.as<double>(), sc));
                 denom = sc[3];  // calc.jl:201
                 GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
                 GRM_TRY(grm_cuda_syrk_i8_f64(ctx, d_codes, n, p, ldc, 1, sc[0], sc[1], sc[2], denom, ctx->u.as<double>(),
@@ -472,17 +509,23 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             done = true;
         } else {
             // ---- FP64 path: per chunk, column means (+ validity) then accumulate Z_c * Z_c' into G ------------
-            GRM_TRY(ctx->q.reserve(static_cast<size_t>(p) * sizeof(double)));
-            float syrk_ms = 0.f;
-            (void)syrk_ms;
+            GRM_TRY(ctx->q.reserve(static_cast<size_t>((p + 127) / 128 * 128) * sizeof(double)));
+            if (masked) GRM_CUDA_TRY(cudaMemsetAsync(d_kept, 0, sizeof(uint64_t), st));
             for (int64_t c = 0; c < feed.nchunks; ++c) {
                 const double *dc;
                 GRM_TRY(feed.acquire(c, &dc));
-                GRM_TRY(grm_cuda_locus_stats_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), ctx->q.as<double>() + feed.k0(c),
-                                                 d_stats, d_flags, c > 0, meanfill ? 1 : 0));
+                if (masked)
+                    GRM_TRY(grm_cuda_locus_qc(ctx, dc, n, feed.len(c), feed.ld_dev(), o.maf, o.max_locus_sparsity,
+                                              meanfill ? 0 : 1, ctx->q.as<double>() + feed.k0(c), d_keep + feed.k0(c),
+                                              d_kept, d_stats, c > 0, d_flags));
+                else
+                    GRM_TRY(grm_cuda_locus_stats_f64(ctx, dc, n, feed.len(c), feed.ld_dev(),
+                                                     ctx->q.as<double>() + feed.k0(c), d_stats, d_flags, c > 0,
+                                                     meanfill ? 1 : 0));
                 GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), centred ? 1 : 0,
                                           static_cast<double>(ploidy), ctx->q.as<double>() + feed.k0(c), c > 0,
-                                          meanfill ? 1 : 0, dG, ldG, o.rank, o.world));
+                                          meanfill ? 1 : 0, masked ? d_keep + feed.k0(c) : nullptr, dG, ldG, o.rank,
+                                          o.world));
                 GRM_TRY(feed.release(c));
             }
             GRM_CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -491,9 +534,17 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             double h_stats[3];
             GRM_CUDA_TRY(cudaMemcpyAsync(&h_flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             GRM_CUDA_TRY(cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+            uint64_t h_kept = static_cast<uint64_t>(p);
+            if (masked) GRM_CUDA_TRY(cudaMemcpyAsync(&h_kept, d_kept, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
             GRM_CUDA_TRY(cudaStreamSynchronize(st));
+            p_eff = static_cast<int64_t>(h_kept);
+            if (masked && p_eff == 0) {
+                grm_set_error("All loci filtered out at maf = %g, maximum locus sparsity = %g.", o.maf,
+                              o.max_locus_sparsity);
+                return GRM_CUDA_ERR_ALL_FILTERED;
+            }
             GRM_TRY(flags_to_status(h_flags));
-            denom = centred ? static_cast<double>(ploidy) * h_stats[0] : static_cast<double>(p);
+            denom = centred ? static_cast<double>(ploidy) * h_stats[0] : static_cast<double>(p_eff);
             GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
             if (!sharded) GRM_TRY(grm_cuda_scale_mirror(ctx, dG, n, ldG, denom));
             // sharded FP64 calls return raw sums scaled by the caller (it owns the exchange of d)
@@ -562,6 +613,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
     inf.ms_h2d = in_host ? inf.ms_pack : 0.f;  // host input: the ingest stage is the H2D stream with the pack hidden under it
     inf.ms_total = wall.ms();
     inf.kernel_launches = ctx->launches;
+    inf.loci_kept = static_cast<int32_t>(p_eff);
     if (info) memcpy(info, &inf, std::min<size_t>(sizeof(inf), static_cast<size_t>(std::max(info->struct_size, 0))));
     return GRM_CUDA_OK;
 }

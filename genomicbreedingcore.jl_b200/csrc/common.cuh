@@ -55,7 +55,7 @@ struct grm_cuda_ctx {
     cudaEvent_t copy_done[2] = {}, stage_free[2] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
-    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, planes, rT;
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, planes, rT, cnt, keep;
     TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed;
     int32_t launches = 0;  // kernels launched since last reset
 };
@@ -67,7 +67,7 @@ void grm_tile_range(int64_t total, int32_t rank, int32_t world, int64_t *begin, 
 
 // kernels' host launchers (implemented across the .cu files)
 int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,
-                          uint32_t *d_out /* [0]=OR of code64, [1]=flags */);
+                          uint32_t *d_out /* [0]=OR of code64, [1]=flags */, int ignore_nan);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------

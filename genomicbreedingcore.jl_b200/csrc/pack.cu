@@ -17,7 +17,7 @@ constexpr uint32_t FLAG_NAN = 1u, FLAG_INF = 2u, FLAG_NOT_DOSAGE = 4u;
 // detection: OR of round(64*x) over the sampled cells; any cell that is not k/64 in [0,1] raises a flag.
 // -------------------------------------------------------------------------------------------------------------
 __global__ void detect_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, int64_t cells,
-                              uint32_t *__restrict__ out) {
+                              uint32_t *__restrict__ out, int ignore_nan) {
     uint32_t bits = 0, flags = 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < cells; idx += stride) {
@@ -28,7 +28,7 @@ __global__ void detect_kernel(const double *__restrict__ A, int64_t n, int64_t p
         const int c = __double2int_rn(t);
         if (static_cast<double>(c) == t && c >= 0 && c <= 64) {
             bits |= static_cast<uint32_t>(c);
-        } else {
+        } else if (!(ignore_nan && x != x)) {
             flags |= (x != x) ? FLAG_NAN : (isinf(x) ? FLAG_INF : FLAG_NOT_DOSAGE);
         }
     }
@@ -60,7 +60,8 @@ constexpr int PK_SLAB = 64;
 template <int EITERS>
 __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__restrict__ A, int64_t n, int64_t pc,
                                                           int64_t lda, int m, int8_t *__restrict__ codes, int64_t ldc,
-                                                          int32_t *__restrict__ colsum, uint32_t *__restrict__ flags) {
+                                                          int32_t *__restrict__ colsum, uint32_t *__restrict__ flags,
+                                                          const uint8_t *__restrict__ keep) {
     __shared__ uint32_t tile[PK_SLAB][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t k0 = static_cast<int64_t>(blockIdx.x) * PK_LOCI;
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__res
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int64_t k = k0 + warp * 16 + j;
-            const bool vk = k < pc;
+            // a locus dropped by the QC mask is packed as zeros (it then contributes nothing to any integer sum)
+            const bool vk = k < pc && (keep == nullptr || keep[k] != 0);
             xa[j] = (vk && va) ? ld_stream(A + ea + k * lda) : 0.0;
             xb[j] = (vk && vb) ? ld_stream(A + eb + k * lda) : 0.0;
         }
@@ -185,7 +187,7 @@ locus_stats_i8_kernel(const int32_t *__restrict__ colsum, int64_t p, double n, d
 // one warp per locus column, lanes stride over entries with a fixed shuffle tree: bit-reproducible column means
 __global__ void __launch_bounds__(256)
 colmean_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, double *__restrict__ q,
-                   uint32_t *__restrict__ flags, int skip_missing) {
+                   uint32_t *__restrict__ flags, int skip_missing, int32_t *__restrict__ cnt_out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t k = static_cast<int64_t>(blockIdx.x) * 8 + warp;
     if (k >= p) return;
@@ -220,18 +222,50 @@ colmean_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t l
     if (lane == 0) {
         if (s != s) bad |= FLAG_NAN;  // NaN anywhere (or Inf-Inf) poisons the column sum
         else if (isinf(s)) bad |= FLAG_INF;
-        if (skip_missing && cnt == 0) bad |= 8u;  // no valid cell: the fill value is undefined
+        if (skip_missing && cnt == 0 && cnt_out == nullptr) bad |= 8u;  // no valid cell: the fill value is undefined
+        if (cnt_out) {
+            cnt_out[k] = cnt;
+            bad = 0;  // QC mode: a non-finite mean fails the MAF test and drops the locus; the mask kernel reports
+                      // missing cells of KEPT loci
+        }
         q[k] = s / static_cast<double>(skip_missing ? cnt : n);
         if (bad) atomicOr(flags, bad);
     }
 }
 
+// QC locus mask, the reference's filter semantics (src/genomes/filter.jl):
+//   sparsity_k = mean(ismissing(column))            keep iff sparsity_k <= max_locus_sparsity     (:202-213, :361-368)
+//   q_k = mean(skipmissing(column))                 keep iff maf <= q_k <= 1 - maf                (:632-635)
+// A kept locus that still holds missing cells raises FLAG_NAN when the missing policy is "error".
+__global__ void locus_mask_kernel(const double *__restrict__ q, const int32_t *__restrict__ cnt, int64_t n, int64_t p,
+                                  double maf, double max_sparsity, int error_on_missing, uint8_t *__restrict__ keep,
+                                  unsigned long long *__restrict__ kept, uint32_t *__restrict__ flags) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int kp = 0;
+    uint32_t bad = 0;
+    if (k < p) {
+        const double sparsity = static_cast<double>(n - cnt[k]) / static_cast<double>(n);
+        const double qk = q[k];
+        kp = (sparsity <= max_sparsity) && (qk >= maf) && (qk <= (1.0 - maf));
+        keep[k] = static_cast<uint8_t>(kp);
+        if (kp && error_on_missing && cnt[k] < n) bad = FLAG_NAN;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, kp);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicAdd(kept, static_cast<unsigned long long>(__popc(m)));
+        if (bad) atomicOr(flags, bad);
+    }
+}
+
 __global__ void __launch_bounds__(RED_THREADS)
-locus_stats_f64_kernel(const double *__restrict__ q, int64_t p, double *__restrict__ partials) {
+locus_stats_f64_kernel(const double *__restrict__ q, int64_t p, double *__restrict__ partials,
+                       const uint8_t *__restrict__ keep) {
     const int64_t per = (p + gridDim.x - 1) / gridDim.x;
     const int64_t b = static_cast<int64_t>(blockIdx.x) * per, e = min(p, b + per);
     double v[3] = {0.0, 0.0, 0.0};
     for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) {
+        if (keep && !keep[k]) continue;
         const double qk = q[k];
         v[0] += qk * (1.0 - qk);
         v[2] += qk;
@@ -410,19 +444,19 @@ __global__ void centre_rows_kernel(const long long *__restrict__ r, const long l
 // host launchers / C ABI
 // ---------------------------------------------------------------------------------------------------------------
 int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,
-                          uint32_t *d_out) {
+                          uint32_t *d_out, int ignore_nan) {
     int64_t cells = n * p;
     if (max_cells > 0 && max_cells < cells) cells = max_cells;
     GRM_CUDA_TRY(cudaMemsetAsync(d_out, 0, 2 * sizeof(uint32_t), ctx->stream));
     const int blocks = static_cast<int>(std::min<int64_t>((cells + 255) / 256, static_cast<int64_t>(ctx->num_sms) * 16));
-    detect_kernel<<<blocks, 256, 0, ctx->stream>>>(dA, n, p, lda, cells, d_out);
+    detect_kernel<<<blocks, 256, 0, ctx->stream>>>(dA, n, p, lda, cells, d_out, ignore_nan);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
 }
 
 extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                               int64_t max_cells, int32_t *m_out) {
+                                               int64_t max_cells, int32_t ignore_missing, int32_t *m_out) {
     if (!ctx || !dA || !m_out || n < 1 || p < 1 || lda < n) {
         grm_set_error("detect_denominator: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -430,7 +464,7 @@ extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     GRM_TRY(ctx->misc.reserve(64));
     uint32_t *d_out = ctx->misc.as<uint32_t>();
-    GRM_TRY(grm_launch_detect(ctx, dA, n, p, lda, max_cells, d_out));
+    GRM_TRY(grm_launch_detect(ctx, dA, n, p, lda, max_cells, d_out, ignore_missing));
     uint32_t h[2];
     GRM_CUDA_TRY(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -449,7 +483,8 @@ extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *
 }
 
 extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
-                                        int32_t m, int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags) {
+                                        int32_t m, int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
+                                        const uint8_t *d_keep) {
     if (!ctx || !dA || !d_codes || !d_colsum || !d_flags || n < 1 || pc < 1 || lda < n || m < 1 || m > 64 ||
         (m & (m - 1)) != 0 || (ldc % 128) != 0 || ldc < ((pc + 127) / 128) * 128) {
         grm_set_error("pack_dosage: bad argument (n=%lld pc=%lld lda=%lld m=%d ldc=%lld)", (long long)n, (long long)pc,
@@ -460,7 +495,8 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
     constexpr int EITERS = 4;
     dim3 grid(static_cast<unsigned>((pc + PK_LOCI - 1) / PK_LOCI),
               static_cast<unsigned>((n + PK_SLAB * EITERS - 1) / (PK_SLAB * EITERS)));
-    pack_dosage_kernel<EITERS><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum, d_flags);
+    pack_dosage_kernel<EITERS><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum, d_flags,
+                                                              d_keep);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
@@ -494,9 +530,9 @@ extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA,
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     GRM_TRY(ctx->partials.reserve(3 * RED_BLOCKS * sizeof(double)));
     colmean_f64_kernel<<<static_cast<unsigned>((p + 7) / 8), 256, 0, ctx->stream>>>(dA, n, p, lda, d_q, d_flags,
-                                                                                    skip_missing);
+                                                                                    skip_missing, nullptr);
     GRM_CUDA_TRY(cudaGetLastError());
-    locus_stats_f64_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_q, p, ctx->partials.as<double>());
+    locus_stats_f64_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_q, p, ctx->partials.as<double>(), nullptr);
     GRM_CUDA_TRY(cudaGetLastError());
     final_stats_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partials.as<double>(), RED_BLOCKS, d_stats, accumulate);
     GRM_CUDA_TRY(cudaGetLastError());
@@ -572,5 +608,35 @@ extern "C" int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_s
         reinterpret_cast<const long long *>(d_r), reinterpret_cast<const long long *>(d_T), n, h, mn, d_u);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+// QC locus mask in one call: q[k] = mean(skipmissing(column k)), keep[k] per the reference's filter rules, the number
+// of kept loci added to *d_kept, and (d_stats != NULL) {sum q(1-q), 0, sum q} over the kept loci.
+extern "C" int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, double maf,
+                                     double max_locus_sparsity, int32_t error_on_missing, double *d_q, uint8_t *d_keep,
+                                     uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags) {
+    if (!ctx || !dA || !d_q || !d_keep || !d_kept || !d_flags || n < 1 || p < 1 || lda < n) {
+        grm_set_error("locus_qc: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_TRY(ctx->cnt.reserve(static_cast<size_t>(p) * sizeof(int32_t)));
+    GRM_TRY(ctx->partials.reserve(3 * RED_BLOCKS * sizeof(double)));
+    colmean_f64_kernel<<<static_cast<unsigned>((p + 7) / 8), 256, 0, ctx->stream>>>(dA, n, p, lda, d_q, d_flags, 1,
+                                                                                    ctx->cnt.as<int32_t>());
+    GRM_CUDA_TRY(cudaGetLastError());
+    locus_mask_kernel<<<static_cast<unsigned>((p + 255) / 256), 256, 0, ctx->stream>>>(
+        d_q, ctx->cnt.as<int32_t>(), n, p, maf, max_locus_sparsity, error_on_missing, d_keep,
+        reinterpret_cast<unsigned long long *>(d_kept), d_flags);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 2;
+    if (d_stats) {
+        locus_stats_f64_kernel<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(d_q, p, ctx->partials.as<double>(), d_keep);
+        GRM_CUDA_TRY(cudaGetLastError());
+        final_stats_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partials.as<double>(), RED_BLOCKS, d_stats, accumulate_stats);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 2;
+    }
     return GRM_CUDA_OK;
 }

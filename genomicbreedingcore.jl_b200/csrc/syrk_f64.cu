@@ -32,7 +32,7 @@ template <bool CENTRED, bool FILL>
 __global__ void __launch_bounds__(256, 1)
 syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, double ploidy,
                 const double *__restrict__ q, const int2 *__restrict__ tiles, double *__restrict__ G, int64_t ldg,
-                int accumulate) {
+                int accumulate, const uint8_t *__restrict__ keep) {
     extern __shared__ double sm[];
     double(*sA)[FK][FLD] = reinterpret_cast<double(*)[FK][FLD]>(sm);
     double(*sB)[FK][FLD] = reinterpret_cast<double(*)[FK][FLD]>(sm + 2 * FK * FLD);
@@ -61,7 +61,7 @@ syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int64_t k = k0 + h * FH + kh + j;
-            const bool vk = k < p;
+            const bool vk = k < p && (keep == nullptr || keep[k] != 0);  // loci dropped by the QC mask contribute 0
             double xa = (vk && va) ? __ldg(A + ra + k * lda) : 0.0;
             double xb = (vk && vb) ? __ldg(A + rb + k * lda) : 0.0;
             double qk = 0.0;
@@ -222,7 +222,8 @@ int32_t get_tile_list_f64(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t wo
 
 extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
                                      int32_t centred, double ploidy, const double *d_q, int32_t accumulate,
-                                     int32_t fill_missing, double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+                                     int32_t fill_missing, const uint8_t *d_keep, double *d_G, int64_t ldg, int32_t rank,
+                                     int32_t world) {
     if (!ctx || !dA || !d_G || n < 1 || p < 1 || lda < n || ldg < n || ((centred || fill_missing) && !d_q) || world < 1 ||
         rank < 0 || rank >= world) {
         grm_set_error("syrk_f64: bad argument (n=%lld p=%lld lda=%lld ldg=%lld)", (long long)n, (long long)p,
@@ -235,7 +236,7 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_
     GRM_TRY(get_tile_list_f64(ctx, n, rank, world, &d_tiles, &count));
     if (count == 0) return GRM_CUDA_OK;
     typedef void (*KernelFn)(const double *, int64_t, int64_t, int64_t, double, const double *, const int2 *, double *,
-                             int64_t, int);
+                             int64_t, int, const uint8_t *);
     static const KernelFn kernels[4] = {syrk_f64_kernel<false, false>, syrk_f64_kernel<true, false>,
                                         syrk_f64_kernel<false, true>, syrk_f64_kernel<true, true>};
     static bool attr_set = false;
@@ -245,7 +246,7 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_
         attr_set = true;
     }
     const KernelFn kernel = kernels[(centred ? 1 : 0) + (fill_missing ? 2 : 0)];
-    kernel<<<count, 256, F64_SMEM, ctx->stream>>>(dA, n, p, lda, ploidy, d_q, d_tiles, d_G, ldg, accumulate);
+    kernel<<<count, 256, F64_SMEM, ctx->stream>>>(dA, n, p, lda, ploidy, d_q, d_tiles, d_G, ldg, accumulate, d_keep);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

@@ -44,14 +44,34 @@ def padded_loci(p: int) -> int:
     return (p + 127) // 128 * 128
 
 
-def detect_denominator(ctx, A_pn, max_cells: int = 0) -> int:
+def detect_denominator(ctx, A_pn, max_cells: int = 0, ignore_missing: bool = False) -> int:
     p, n = A_pn.shape
     m = C.c_int32(0)
-    _lib.check(ctx.lib.grm_cuda_detect_denominator(ctx.handle, _ptr(A_pn), n, p, n, max_cells, C.byref(m)))
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_detect_denominator(ctx.handle, _ptr(A_pn), n, p, n, max_cells,
+                                                   1 if ignore_missing else 0, C.byref(m)))
     return m.value
 
 
-def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int = 0):
+def locus_qc(ctx, A_pn, maf: float, max_locus_sparsity: float, error_on_missing: bool = True, with_stats: bool = False):
+    """QC locus mask (filterbysparsity + filterbymaf rules): returns (q, keep uint8, kept count, stats, flags)."""
+    torch = _torch()
+    p, n = A_pn.shape
+    dev = A_pn.device
+    q = torch.empty((p,), dtype=torch.float64, device=dev)
+    keep = torch.zeros((p,), dtype=torch.uint8, device=dev)
+    kept = torch.zeros((1,), dtype=torch.int64, device=dev)
+    stats = torch.zeros((3,), dtype=torch.float64, device=dev) if with_stats else None
+    flags = torch.zeros((16,), dtype=torch.int32, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_locus_qc(ctx.handle, _ptr(A_pn), n, p, n, float(maf), float(max_locus_sparsity),
+                                         1 if error_on_missing else 0, _ptr(q), _ptr(keep), _ptr(kept),
+                                         _ptr(stats) if with_stats else None, 0, _ptr(flags)))
+    ctx.order_torch_after()
+    return q, keep, kept, stats, flags
+
+
+def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int = 0, keep=None):
     """Quantise + transpose A (loci k0..k0+pc of the full problem) into codes[:, k0:k0+pc]; returns
     (codes[n, ldc] int8, colsum[ldc] int32, flags[16] uint32-as-int32)."""
     torch = _torch()
@@ -67,7 +87,9 @@ def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int 
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_pack_dosage(ctx.handle, _ptr(A_pn), n, pc, n, m,
                                             C.c_void_p(codes.data_ptr() + k0), ldc,
-                                            C.c_void_p(colsum.data_ptr() + 4 * k0), _ptr(flags)))
+                                            C.c_void_p(colsum.data_ptr() + 4 * k0), _ptr(flags),
+                                            _ptr(keep) if keep is not None else None))
+    ctx.order_torch_after()
     return codes, colsum, flags
 
 
@@ -85,6 +107,7 @@ def syrk_i8(ctx, codes, p: int, rank: int = 0, world: int = 1, out=None):
         out = torch.zeros((n, n), dtype=torch.int32, device=codes.device)
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_syrk_i8(ctx.handle, _ptr(codes), n, p, ldc, nslabs, _ptr(out), n, rank, world))
+    ctx.order_torch_after()
     return out
 
 
@@ -97,6 +120,7 @@ def syrk_i8_f64(ctx, codes, p: int, alpha: float, beta: float, gamma: float, den
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_syrk_i8_f64(ctx.handle, _ptr(codes), n, p, ldc, nslabs, alpha, beta, gamma, denom,
                                             _ptr(u) if u is not None else None, _ptr(out), n, rank, world))
+    ctx.order_torch_after()
     return out
 
 
@@ -110,6 +134,7 @@ def syrk_i8_packed(ctx, codes, p: int, world: int, out=None):
         out = torch.zeros((world * tmax, 65536), dtype=torch.int32, device=codes.device)
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_syrk_i8_packed(ctx.handle, _ptr(codes), n, p, ldc, world, _ptr(out)))
+    ctx.order_torch_after()
     return out
 
 
@@ -118,6 +143,7 @@ def finalize_tiles(ctx, reduced, n: int, alpha: float, beta: float, gamma: float
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_finalize_tiles(ctx.handle, _ptr(reduced), n, alpha, beta, gamma, denom,
                                                _ptr(u) if u is not None else None, _ptr(G), n, rank, world))
+    ctx.order_torch_after()
     return G
 
 
@@ -129,6 +155,7 @@ def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
     stats = torch.zeros((3,), dtype=torch.float64, device=dev)
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_locus_stats_i8(ctx.handle, _ptr(colsum), p, n, m, ploidy, _ptr(q), _ptr(w), _ptr(stats)))
+    ctx.order_torch_after()
     return q, w, stats
 
 
@@ -144,6 +171,7 @@ def dosage_stats(ctx, codes, p: int, colsum, sums=None, r=None, T=None, accumula
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_dosage_stats(ctx.handle, _ptr(codes), n, p, ldc, _ptr(colsum), _ptr(sums), _ptr(r),
                                              _ptr(T), 1 if accumulate else 0))
+    ctx.order_torch_after()
     return sums, r, T
 
 
@@ -156,6 +184,7 @@ def dosage_centre(ctx, sums, r, T, p_total: int, m: int, ploidy: int):
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_dosage_centre(ctx.handle, _ptr(sums), _ptr(r), _ptr(T), n, p_total, m, ploidy, _ptr(u),
                                               sc))
+    ctx.order_torch_after()
     return u, tuple(sc)
 
 
@@ -165,6 +194,7 @@ def rowdot_i8(ctx, codes, p: int, w):
     u = torch.empty((n,), dtype=torch.float64, device=codes.device)
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_rowdot_i8(ctx.handle, _ptr(codes), n, p, ldc, _ptr(w), _ptr(u)))
+    ctx.order_torch_after()
     return u
 
 
@@ -181,11 +211,12 @@ def locus_stats_f64(ctx, A_pn, accumulate: bool = False, q=None, stats=None, fla
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_locus_stats_f64(ctx.handle, _ptr(A_pn), n, p, n, _ptr(q), _ptr(stats), _ptr(flags),
                                                 1 if accumulate else 0, 1 if skip_missing else 0))
+    ctx.order_torch_after()
     return q, stats, flags
 
 
 def syrk_f64(ctx, A_pn, centred: bool, ploidy: float = 2.0, q=None, accumulate: bool = False, rank: int = 0,
-             world: int = 1, out=None, fill_missing: bool = False):
+             world: int = 1, out=None, fill_missing: bool = False, keep=None):
     torch = _torch()
     p, n = A_pn.shape
     if out is None:
@@ -193,7 +224,9 @@ def syrk_f64(ctx, A_pn, centred: bool, ploidy: float = 2.0, q=None, accumulate: 
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_syrk_f64(ctx.handle, _ptr(A_pn), n, p, n, 1 if centred else 0, float(ploidy),
                                          _ptr(q) if q is not None else None, 1 if accumulate else 0,
-                                         1 if fill_missing else 0, _ptr(out), n, rank, world))
+                                         1 if fill_missing else 0, _ptr(keep) if keep is not None else None, _ptr(out),
+                                         n, rank, world))
+    ctx.order_torch_after()
     return out
 
 
@@ -201,6 +234,7 @@ def scale_mirror(ctx, G, denom: float = 1.0):
     n = G.shape[0]
     ctx.synchronize_with_torch()
     _lib.check(ctx.lib.grm_cuda_scale_mirror(ctx.handle, _ptr(G), n, n, float(denom)))
+    ctx.order_torch_after()
     return G
 
 
@@ -227,7 +261,21 @@ def grm_device(ctx, A_pn, ploidy=None, *, path=_lib.PATH_AUTO, denominator=0, sk
         st = ctx.lib.grm_cuda_ploidyaware(ctx.handle, _ptr(A_pn), n, p, n, int(ploidy), _ptr(out), n, C.byref(o),
                                           C.byref(info))
     _lib.check(st)
+    ctx.order_torch_after()
     return out, info.as_dict()
+
+
+def _order_torch_after(self):
+    """Make torch's current stream wait (on the device, no host sync) for what the library has enqueued so far, so
+    that torch ops on the results are ordered after the kernels that produce them."""
+    torch = _torch()
+    dev = torch.device("cuda", self.device)
+    cur = torch.cuda.current_stream(dev)
+    if cur.cuda_stream != self.stream:
+        ext = torch.cuda.ExternalStream(self.stream, device=dev)
+        ev = torch.cuda.Event()
+        ev.record(ext)
+        cur.wait_event(ev)
 
 
 def _synchronize_with_torch(self):
@@ -239,3 +287,4 @@ def _synchronize_with_torch(self):
 
 
 _lib.Context.synchronize_with_torch = _synchronize_with_torch
+_lib.Context.order_torch_after = _order_torch_after

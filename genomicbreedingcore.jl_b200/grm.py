@@ -21,6 +21,8 @@ def _raise_for(err: _lib.GrmCudaError):
     s = err.status
     if s == _lib.ERR_MISSING:
         raise MissingDataError(err.message) from None
+    if s == _lib.ERR_ALL_FILTERED:
+        raise ErrorException(err.message) from None  # filter.jl:363-365, :644-646 throw ErrorException
     if s in (_lib.ERR_BAD_ARGUMENT, _lib.ERR_NOT_SYMMETRIC, _lib.ERR_NAN_MATRIX, _lib.ERR_INF_MATRIX,
              _lib.ERR_NONFINITE, _lib.ERR_NOT_DOSAGE, _lib.ERR_OVERFLOW):
         raise ArgumentError(err.message) from None
@@ -30,7 +32,7 @@ def _raise_for(err: _lib.GrmCudaError):
 def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.Context] = None,
              path: int = _lib.PATH_AUTO, denominator: int = 0, max_iter: int = 1_000, skip_repair: bool = False,
              chunk_loci: int = 0, rank: int = 0, world: int = 1, out: Optional[np.ndarray] = None,
-             missing: str = "error"):
+             missing: str = "error", maf: float = 0.0, max_locus_sparsity: float = 1.0):
     """The C-ABI call a Julia `ccall` shim makes, on host buffers: grm_cuda_simple (ploidy is None) or
     grm_cuda_ploidyaware.  `A` is n x p (NaN = missing); a strided view of a larger Fortran array is passed with its
     leading dimension, no copy.  Returns (G, info dict).  Raises GrmCudaError with the library status."""
@@ -52,6 +54,7 @@ def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.
     o.chunk_loci = int(chunk_loci)
     o.rank, o.world = rank, world
     o.missing_policy = {"error": _lib.MISSING_ERROR, "meanfill": _lib.MISSING_MEANFILL}[missing]
+    o.maf, o.max_locus_sparsity = float(maf), float(max_locus_sparsity)
     info = _lib.new_info()
     if ploidy is None:
         st = ctx.lib.grm_cuda_simple(ctx.handle, A.ctypes.data, n, p, lda, out.ctypes.data, ldg, C.byref(o),

@@ -48,7 +48,8 @@ typedef enum grm_cuda_status {
     GRM_CUDA_ERR_CUDA = 7,           /* CUDA runtime/driver/cuSOLVER failure, or no sm_100 device                    */
     GRM_CUDA_ERR_OOM = 8,            /* device or pinned-host allocation failed                                      */
     GRM_CUDA_ERR_NOT_DOSAGE = 9,     /* int8 path forced but the frequencies are not k/m with m a power of two <= 64 */
-    GRM_CUDA_ERR_OVERFLOW = 10       /* m*m*p would overflow the int32 accumulators                                  */
+    GRM_CUDA_ERR_OVERFLOW = 10,      /* m*m*p would overflow the int32 accumulators                                  */
+    GRM_CUDA_ERR_ALL_FILTERED = 11   /* QC mask: "All loci filtered out ..." (src/genomes/filter.jl:363-365, :644-646) */
 } grm_cuda_status;
 
 /* Which contraction ran (grm_cuda_info.path) / may run (grm_cuda_options.path). */
@@ -81,6 +82,13 @@ typedef struct grm_cuda_options {
     int32_t world;           /* ... out of `world` ranks (1 = everything).  Sharded calls imply skip_repair.   */
     int32_t missing_policy;  /* GRM_CUDA_MISSING_*                                                             */
     int64_t chunk_loci;      /* loci per host->device streaming chunk; 0 = automatic                           */
+    /* Fused QC locus mask (extension; the step before the GRM in the reference's documented workflow).  A locus is
+     * kept iff  mean(ismissing(col)) <= max_locus_sparsity  (filterbysparsity, src/genomes/filter.jl:361-368) and
+     * maf <= mean(skipmissing(col)) <= 1 - maf  (filterbymaf, :632-635).  The result equals the reference GRM of
+     * slice(genomes, idx_loci_alleles = kept): p and d are taken over the kept loci only.  maf = 0 and
+     * max_locus_sparsity = 1 (the defaults) switch the mask off = the bare reference functions. */
+    double maf;
+    double max_locus_sparsity;
 } grm_cuda_options;
 
 typedef struct grm_cuda_info {
@@ -101,7 +109,7 @@ typedef struct grm_cuda_info {
     float ms_d2h;
     float ms_total;        /* wall time of the whole call, host clock                                          */
     int32_t kernel_launches; /* kernels of this library launched by the call                                   */
-    int32_t reserved0;
+    int32_t loci_kept;       /* loci that entered the GRM (= p without the QC mask)                            */
 } grm_cuda_info;
 
 /* ---- library / context ------------------------------------------------------------------------------------ */
@@ -139,16 +147,25 @@ int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int6
 /* Smallest power-of-two m <= 64 such that m*x is an integer in [0,m] for every sampled cell; 0 if none
  * (continuous data).  Reads at most `max_cells` cells (<=0: all).  Synchronises the stream. */
 int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                    int64_t max_cells, int32_t *m_out);
+                                    int64_t max_cells, int32_t ignore_missing, int32_t *m_out);
 
 /* Column statistics + quantise + transpose in ONE pass over A (n x pc, column-major):
  *   codes[i*ldc + k] = int8(m * A[i + k*lda])   (row-major, locus fastest; columns [pc, ldc) are zero-filled
  *                                                 when ldc covers them up to the next multiple of 128)
  *   colsum[k]        = sum_i codes[i,k]           (int32, exact)
  *   flags[0]        |= 1 if a cell is NaN, 2 if +-Inf, 4 if m*x is not an integer in [0,m]
- * ldc (bytes per packed row) must be a multiple of 128. */
+ * ldc (bytes per packed row) must be a multiple of 128.  d_keep (optional, pc bytes): loci with keep == 0 are packed
+ * as zeros and not validated (QC mask). */
 int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda, int32_t m,
-                             int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags);
+                             int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
+                             const uint8_t *d_keep);
+
+/* QC locus mask in one pass over A: q[k] = mean(skipmissing(column k)); keep[k] = 1 iff the locus passes the
+ * sparsity and MAF rules above; *d_kept += number of kept loci; d_stats (optional) (+)= {sum q(1-q), 0, sum q} over
+ * the kept loci.  error_on_missing != 0 raises flag 1 if a KEPT locus still holds a missing cell. */
+int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, double maf,
+                          double max_locus_sparsity, int32_t error_on_missing, double *d_q, uint8_t *d_keep,
+                          uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags);
 
 /* Exact integer Gram matrix of the packed codes over the tiles owned by (rank, world):
  *   C[i + j*ldC] = sum_k codes[i,k]*codes[j,k]   for every (i,j) inside an owned upper-triangular tile.
@@ -216,8 +233,9 @@ int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n,
  * accumulate != 0 adds to G (loci streamed in chunks).  fill_missing != 0 replaces a NaN A_ik by q_k before anything
  * else (d_q required).  FP64 tensor path (DMMA). */
 int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int32_t centred,
-                          double ploidy, const double *d_q, int32_t accumulate, int32_t fill_missing, double *d_G,
-                          int64_t ldg, int32_t rank, int32_t world);
+                          double ploidy, const double *d_q, int32_t accumulate, int32_t fill_missing,
+                          const uint8_t *d_keep /* optional QC mask */, double *d_G, int64_t ldg, int32_t rank,
+                          int32_t world);
 
 /* G[i,j] = G[i,j]/denom for i <= j, then G[j,i] = G[i,j] for i < j (whole matrix; exact symmetry). */
 int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom);

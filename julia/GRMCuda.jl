@@ -16,7 +16,7 @@ const LIB = get(ENV, "GRM_CUDA_LIB", joinpath(@__DIR__, "..", "genomicbreedingco
 
 # mirrors of grm_cuda_options / grm_cuda_info (include/grm_cuda.h)
 Base.@kwdef mutable struct Options
-    struct_size::Int32 = 48
+    struct_size::Int32 = 64
     path::Int32 = 0
     denominator::Int32 = 0
     max_iter::Int32 = 1000
@@ -27,6 +27,8 @@ Base.@kwdef mutable struct Options
     world::Int32 = 1
     missing_policy::Int32 = 0
     chunk_loci::Int64 = 0
+    maf::Float64 = 0.0
+    max_locus_sparsity::Float64 = 1.0
 end
 
 Base.@kwdef mutable struct Info
@@ -46,7 +48,7 @@ Base.@kwdef mutable struct Info
     ms_d2h::Float32 = 0
     ms_total::Float32 = 0
     kernel_launches::Int32 = 0
-    reserved0::Int32 = 0
+    loci_kept::Int32 = 0
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)

@@ -200,6 +200,20 @@ def np_meanfill(A):
     return A
 
 
+def np_qc_keep(A, maf=0.0, max_locus_sparsity=1.0):
+    """Loci the reference's QC filters keep: filterbysparsity (src/genomes/filter.jl:202-213, :361-368:
+    mean(ismissing(col)) <= max_locus_sparsity) and filterbymaf (:632-635: maf <= mean(skipmissing(col)) <= 1-maf).
+    The masked CUDA call must equal the reference GRM functions applied to A[:, keep]."""
+    A = np.asarray(A, dtype=np.float64)
+    miss = np.isnan(A)
+    sparsity = miss.mean(axis=0)
+    cnt = (~miss).sum(axis=0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        q = np.where(miss, 0.0, A).sum(axis=0) / cnt
+        keep = (sparsity <= max_locus_sparsity) & (q >= maf) & (q <= (1.0 - maf))
+    return keep
+
+
 def np_det_julia(X):
     """det(X) the way Julia evaluates it: LAPACK getrf, sequential product of diag(U), sign from the pivots."""
     from scipy.linalg import lapack

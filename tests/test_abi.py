@@ -28,10 +28,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert C.sizeof(_lib.Options) == 48
+    assert C.sizeof(_lib.Options) == 64
     assert C.sizeof(_lib.Info) == 80
     o = _lib.default_options()
-    assert (o.struct_size, o.path, o.max_iter, o.world, o.rank, o.skip_repair) == (48, 0, 1000, 1, 0, 0)
+    assert (o.struct_size, o.path, o.max_iter, o.world, o.rank, o.skip_repair) == (64, 0, 1000, 1, 0, 0)
+    assert (o.maf, o.max_locus_sparsity, o.missing_policy) == (0.0, 1.0, 0)
 
 
 def test_version_and_status_strings():

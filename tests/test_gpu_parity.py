@@ -326,6 +326,67 @@ def test_meanfill_policy_matches_reference_on_mean_imputed_matrix(gen, sparsity)
         assert i1["path"] == _lib.PATH_I8 and np.array_equal(G0, G1)
 
 
+# Row (f1): fused QC locus mask == reference GRM of slice(genomes, idx_loci_alleles = kept)
+def _qc_input(kind, n=140, p=1500):
+    rng = np.random.default_rng(71)
+    A = synth.dosage(n, p, 2, seed=72) if kind == "dosage" else synth.continuous(n, p, seed=72)
+    A[:, rng.choice(p, 40, replace=False)] = 0.0   # fixed loci: fail the MAF rule
+    A[:, rng.choice(p, 25, replace=False)] = 1.0
+    for k in rng.choice(p, 60, replace=False):      # loci with missing cells of varying sparsity
+        A[rng.choice(n, rng.integers(1, n // 3), replace=False), k] = np.nan
+    A[:, 5] = np.nan                                 # one locus without any valid cell
+    return np.asfortranarray(A)
+
+
+@pytest.mark.parametrize("kind", ["dosage", "continuous"])
+def test_qc_locus_mask_equals_reference_on_sliced_genomes(kind):
+    A = _qc_input(kind)
+    tol = RTOL_I8 if kind == "dosage" else RTOL_F64
+    # (1) drop every locus with a missing cell (max_locus_sparsity = 0) and rare alleles: no missing data remains
+    keep = O.np_qc_keep(A, maf=0.05, max_locus_sparsity=0.0)
+    assert 0 < keep.sum() < A.shape[1] and not np.isnan(A[:, keep]).any()
+    S = np.asfortranarray(A[:, keep])
+    for ploidy in (None, 2):
+        G, info = grm_call(A, ploidy, skip_repair=True, maf=0.05, max_locus_sparsity=0.0)
+        assert info["loci_kept"] == int(keep.sum())
+        assert info["path"] == (_lib.PATH_I8 if kind == "dosage" else _lib.PATH_F64)
+        ref = O.c_grmsimple_raw(S, nthreads=4)[1] if ploidy is None else O.c_grmploidyaware_raw(S, ploidy, nthreads=4)[1]
+        assert relerr(G, ref) <= tol
+        if kind == "dosage" and ploidy is None:
+            assert np.array_equal(G, ref)
+        G2, i2 = grm_call(A, ploidy, skip_repair=True, maf=0.05, max_locus_sparsity=0.0, chunk_loci=256)
+        assert i2["loci_kept"] == info["loci_kept"] and relerr(G2, G) <= 1e-13
+        Gr, ir = grm_call(A, ploidy, maf=0.05, max_locus_sparsity=0.0)  # with the repair
+        st, X, it, tot = O.np_inflatediagonals(G)
+        assert ir["repair_iters"] == it and np.array_equal(Gr, X)
+    # (2) tolerate up to 10 % missing per locus: kept loci still hold missing cells
+    keep = O.np_qc_keep(A, maf=0.05, max_locus_sparsity=0.1)
+    assert np.isnan(A[:, keep]).any()
+    with pytest.raises(_lib.GrmCudaError) as e:  # reference behaviour on the sliced genomes: missing => throw
+        grm_call(A, 2, skip_repair=True, maf=0.05, max_locus_sparsity=0.1)
+    assert e.value.status == _lib.ERR_MISSING
+    G, info = grm_call(A, 2, skip_repair=True, maf=0.05, max_locus_sparsity=0.1, missing="meanfill")
+    assert info["loci_kept"] == int(keep.sum()) and info["path"] == _lib.PATH_F64
+    ref = O.c_grmploidyaware_raw(O.np_meanfill(np.asfortranarray(A[:, keep])), 2, nthreads=4)[1]
+    assert relerr(G, ref) <= RTOL_F64
+    # (3) everything filtered: the reference's filters throw ErrorException
+    with pytest.raises(_lib.GrmCudaError) as e:
+        grm_call(np.asfortranarray(np.ones((6, 40))), 2, maf=0.01)
+    assert e.value.status == _lib.ERR_ALL_FILTERED
+
+
+def test_qc_mask_kernel_matches_filter_rules(ctx):
+    from grm_b200 import device as D
+
+    A = _qc_input("continuous")
+    for maf, tau in [(0.01, 1.0), (0.05, 0.0), (0.2, 0.1), (0.0, 0.05)]:
+        q, keep, kept, stats, flags = D.locus_qc(ctx, to_dev(A), maf, tau, error_on_missing=False)
+        ctx.synchronize()
+        want = O.np_qc_keep(A, maf, tau)
+        assert np.array_equal(keep.cpu().numpy().astype(bool), want)
+        assert int(kept[0]) == int(want.sum())
+
+
 # P9: ordering follows the input order of entries
 def test_row_order_follows_entries():
     A = synth.dosage(60, 500, 4, seed=13)
