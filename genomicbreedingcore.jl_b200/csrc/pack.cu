@@ -57,7 +57,7 @@ __device__ __forceinline__ double ld_stream(const double *p) {
 constexpr int PK_LOCI = 128;
 constexpr int PK_SLAB = 64;
 
-template <int EITERS>
+template <int EITERS, bool MASK>
 __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__restrict__ A, int64_t n, int64_t pc,
                                                           int64_t lda, int m, int8_t *__restrict__ codes, int64_t ldc,
                                                           int32_t *__restrict__ colsum, uint32_t *__restrict__ flags,
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__res
         for (int j = 0; j < 16; ++j) {
             const int64_t k = k0 + warp * 16 + j;
             // a locus dropped by the QC mask is packed as zeros (it then contributes nothing to any integer sum)
-            const bool vk = k < pc && (keep == nullptr || keep[k] != 0);
+            bool vk = k < pc;
+            if (MASK) vk = vk && keep[k] != 0;
             xa[j] = (vk && va) ? ld_stream(A + ea + k * lda) : 0.0;
             xb[j] = (vk && vb) ? ld_stream(A + eb + k * lda) : 0.0;
         }
@@ -378,6 +379,7 @@ rowstats_i8_kernel(const int8_t *__restrict__ codes, int64_t n, int64_t p, int64
 #pragma unroll
     for (int r = 0; r < RD_ROWS; ++r) t0[r] = t1[r] = t2[r] = rs[r] = 0u;
     const int64_t groups = (p + 15) / 16;
+#pragma unroll 2
     for (int64_t g = threadIdx.x; g < groups; g += blockDim.x) {
         const int64_t k = g * 16;
         const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(planes + k));
@@ -495,8 +497,12 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
     constexpr int EITERS = 4;
     dim3 grid(static_cast<unsigned>((pc + PK_LOCI - 1) / PK_LOCI),
               static_cast<unsigned>((n + PK_SLAB * EITERS - 1) / (PK_SLAB * EITERS)));
-    pack_dosage_kernel<EITERS><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum, d_flags,
-                                                              d_keep);
+    if (d_keep)
+        pack_dosage_kernel<EITERS, true><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
+                                                                        d_flags, d_keep);
+    else
+        pack_dosage_kernel<EITERS, false><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
+                                                                         d_flags, nullptr);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

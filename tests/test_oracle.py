@@ -128,3 +128,22 @@ def test_threaded_oracle_equals_single_thread():
     A = synth.continuous(37, 211, seed=9)
     assert np.array_equal(O.c_grmsimple_raw(A, nthreads=1)[1], O.c_grmsimple_raw(A, nthreads=5)[1])
     assert np.array_equal(O.c_grmploidyaware_raw(A, 4, nthreads=1)[1], O.c_grmploidyaware_raw(A, 4, nthreads=3)[1])
+
+
+def test_qc_keep_and_meanfill_follow_the_filter_rules():
+    """np_qc_keep / np_meanfill restate filterbysparsity (src/genomes/filter.jl:202-213, :361-368) and filterbymaf
+    (:632-635); they are the oracles of the mask / mean-fill extensions."""
+    A = np.array([[0.0, 0.5, np.nan, 1.0, np.nan],
+                  [0.0, 1.0, 0.5, 1.0, np.nan],
+                  [0.0, 0.0, 0.5, 1.0, np.nan],
+                  [0.0, 0.5, 1.0, np.nan, np.nan]])
+    # column means over valid cells: 0, 0.5, 2/3, 1, NaN ; sparsities: 0, 0, .25, .25, 1
+    assert O.np_qc_keep(A, 0.0, 1.0).tolist() == [True, True, True, True, False]  # all-missing locus never passes
+    assert O.np_qc_keep(A, 0.01, 1.0).tolist() == [False, True, True, False, False]
+    assert O.np_qc_keep(A, 0.01, 0.0).tolist() == [False, True, False, False, False]
+    assert O.np_qc_keep(A, 0.0, 0.25).tolist() == [True, True, True, True, False]
+    assert O.np_qc_keep(A, 0.0, 0.2).tolist() == [True, True, False, False, False]
+    F = O.np_meanfill(A[:, :4])
+    assert not np.isnan(F).any()
+    assert F[0, 2] == (0.5 + 0.5 + 1.0) / 3 and F[3, 3] == 1.0
+    assert np.array_equal(F[~np.isnan(A[:, :4])], A[:, :4][~np.isnan(A[:, :4])])
