@@ -72,6 +72,22 @@ extern "C" void grm_cuda_options_default(grm_cuda_options *o) {
     o->max_locus_sparsity = 1.0;
 }
 
+int32_t grm_tmap_encoder(GrmEncodeTiledFn *out) {
+    static GrmEncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GRM_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            grm_set_error("cuTensorMapEncodeTiled not available from the driver");
+            return GRM_CUDA_ERR_CUDA;
+        }
+        encode = reinterpret_cast<GrmEncodeTiledFn>(fn);
+    }
+    *out = encode;
+    return GRM_CUDA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // buffers / context
 // ---------------------------------------------------------------------------------------------------------------

@@ -65,6 +65,12 @@ constexpr int GRM_TILE = 256;  // edge, in entries, of the unit of multi-GPU sha
 void grm_tile_order(int64_t n, std::vector<int2> &tiles);  // all upper-triangular (ti<=tj) tiles, L2-friendly order
 void grm_tile_range(int64_t total, int32_t rank, int32_t world, int64_t *begin, int64_t *end);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
+typedef CUresult (*GrmEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int32_t grm_tmap_encoder(GrmEncodeTiledFn *fn);
+
 // kernels' host launchers (implemented across the .cu files)
 int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,
                           uint32_t *d_out /* [0]=OR of code64, [1]=flags */, int ignore_nan);

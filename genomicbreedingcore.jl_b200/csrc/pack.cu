@@ -7,6 +7,9 @@
 //                        calc.jl:197, and the implicit "any missing => throw", calc.jl:127)
 //   locus_stats_*        q_k, w_k = ploidy/2 + q_k, sum q(1-q) (calc.jl:197,201), fixed-order reductions
 //   rowdot_i8_kernel     u_i = sum_k c_ik w_k for the rank-1 centring correction
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -133,6 +136,138 @@ __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__res
         const int64_t k = k0 + warp * 16 + i;
         if (lane == 0 && k < pc && s != 0) atomicAdd(&colsum[k], s);
     }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) atomicOr(flags, bad);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// pack, TMA-staged variant (used whenever the rows of A are 16-byte aligned: lda even).
+// Persistent CTAs; a producer warp keeps a 3-stage ring of 32 KB boxes (32 entries x 128 loci of FP64) in flight
+// with cp.async.bulk.tensor, so HBM requests are issued continuously instead of in per-block load phases; eight
+// consumer warps quantise from shared memory (warp = 16 loci, lane = entry: conflict-free 256-byte rows), transpose
+// through a double-buffered 32 x 33 word tile and write one 128-byte line per entry row.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int PT_LOCI = 128, PT_ENT = 32, PT_STAGES = 3;
+constexpr uint32_t PT_STAGE_BYTES = PT_LOCI * PT_ENT * sizeof(double);  // 32 KiB
+constexpr size_t PT_SMEM = PT_STAGES * PT_STAGE_BYTES + 2 * PT_ENT * 33 * sizeof(uint32_t) + 64 + 128;
+
+template <bool MASK>
+__global__ void __launch_bounds__(288, 2)
+pack_dosage_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n, int64_t pc, int m, int8_t *__restrict__ codes,
+                       int64_t ldc, int32_t *__restrict__ colsum, uint32_t *__restrict__ flags,
+                       const uint8_t *__restrict__ keep, int64_t ent_blocks, int64_t units) {
+    extern __shared__ uint8_t pt_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(pt_raw) + 127) & ~uintptr_t(127));
+    double *stage = reinterpret_cast<double *>(base);
+    uint32_t(*tile)[PT_ENT][33] = reinterpret_cast<uint32_t(*)[PT_ENT][33]>(base + PT_STAGES * PT_STAGE_BYTES);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(base + PT_STAGES * PT_STAGE_BYTES + 2 * PT_ENT * 33 * sizeof(uint32_t));
+    uint64_t *empty_bar = full_bar + PT_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous run of (locus block, entry block) units, entry block fastest: column sums stay in registers
+    // until the locus block changes
+    const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < PT_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int64_t u = u0; u < u1; ++u) {
+                const int64_t kb = u / ent_blocks, eb = u - kb * ent_blocks;
+                mbar_wait(&empty_bar[s], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], PT_STAGE_BYTES);
+                tma_load_2d(stage + static_cast<size_t>(s) * (PT_STAGE_BYTES / sizeof(double)), &tmap, &full_bar[s],
+                            static_cast<int32_t>(eb * PT_ENT), static_cast<int32_t>(kb * PT_LOCI));
+                if (++s == PT_STAGES) {
+                    s = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    const double mf = static_cast<double>(m);
+    int32_t acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0;
+    uint32_t bad = 0;
+    int64_t cur_kb = -1;
+    int s = 0;
+    uint32_t phase = 0;
+    int tb = 0;
+    auto flush = [&](int64_t kb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int32_t sum = __reduce_add_sync(0xffffffffu, acc[i]);
+            const int64_t k = kb * PT_LOCI + warp * 16 + i;
+            if (lane == 0 && k < pc && sum != 0) atomicAdd(&colsum[k], sum);
+            acc[i] = 0;
+        }
+    };
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t kb = u / ent_blocks, eb = u - kb * ent_blocks;
+        if (kb != cur_kb) {
+            if (cur_kb >= 0) flush(cur_kb);
+            cur_kb = kb;
+        }
+        const int64_t k0 = kb * PT_LOCI, e0 = eb * PT_ENT;
+        mbar_wait(&full_bar[s], phase);
+        const double *st = stage + static_cast<size_t>(s) * (PT_STAGE_BYTES / sizeof(double));
+        double x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = st[(warp * 16 + j) * PT_ENT + lane];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp's 16 rows of the stage are in registers
+        if (++s == PT_STAGES) {
+            s = 0;
+            phase ^= 1;
+        }
+        const bool ve = e0 + lane < n;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int64_t k = k0 + warp * 16 + g * 4 + kk;
+                bool vk = k < pc && ve;  // out-of-range cells were zero-filled by TMA
+                if (MASK) vk = vk && keep[k < pc ? k : 0] != 0;
+                const double v = x[g * 4 + kk];
+                const double t = v * mf;
+                int c = __double2int_rn(t);
+                if (!vk) {
+                    c = 0;
+                } else if (!(static_cast<double>(c) == t && c >= 0 && c <= m)) {
+                    bad |= (v != v) ? FLAG_NAN : (isinf(v) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    c = 0;
+                }
+                w |= static_cast<uint32_t>(c) << (8 * kk);
+                acc[g * 4 + kk] += c;
+            }
+            tile[tb][lane][warp * 4 + g] = w;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps only
+        {
+            const int r = threadIdx.x >> 3, c = (threadIdx.x & 7) * 4;
+            const int64_t e = e0 + r;
+            if (e < n) {
+                const uint4 v = make_uint4(tile[tb][r][c], tile[tb][r][c + 1], tile[tb][r][c + 2], tile[tb][r][c + 3]);
+                *reinterpret_cast<uint4 *>(codes + e * ldc + k0 + c * 4) = v;
+            }
+        }
+        tb ^= 1;  // double-buffered tile: the next unit's writes cannot overtake this unit's reads (see pack.cu notes)
+    }
+    if (cur_kb >= 0) flush(cur_kb);
     bad = __reduce_or_sync(0xffffffffu, bad);
     if (lane == 0 && bad) atomicOr(flags, bad);
 }
@@ -494,6 +629,48 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char *e = getenv("GRM_CUDA_PACK");
+        use_tma = (e && !strcmp(e, "ldg")) ? 0 : 1;
+    }
+    if (use_tma && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(dA) % 16) == 0 && n < (1ll << 31) && pc < (1ll << 31)) {
+        // TMA-staged variant: needs 16-byte aligned rows of A (global strides are multiples of 16 bytes)
+        GrmEncodeTiledFn encode = nullptr;
+        GRM_TRY(grm_tmap_encoder(&encode));
+        CUtensorMap tmap;
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(pc)};
+        cuuint64_t gstride[1] = {static_cast<cuuint64_t>(lda) * sizeof(double)};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(PT_ENT), static_cast<cuuint32_t>(PT_LOCI)};
+        cuuint32_t estr[2] = {1u, 1u};
+        const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(dA), gdim, gstride, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            grm_set_error("cuTensorMapEncodeTiled (FP64 input) failed with CUresult %d", static_cast<int>(r));
+            return GRM_CUDA_ERR_CUDA;
+        }
+        static bool attr_set = false;
+        if (!attr_set) {
+            GRM_CUDA_TRY(cudaFuncSetAttribute(pack_dosage_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(PT_SMEM)));
+            GRM_CUDA_TRY(cudaFuncSetAttribute(pack_dosage_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(PT_SMEM)));
+            attr_set = true;
+        }
+        const int64_t ent_blocks = (n + PT_ENT - 1) / PT_ENT, loc_blocks = (pc + PT_LOCI - 1) / PT_LOCI;
+        const int64_t units = ent_blocks * loc_blocks;
+        const int grid = static_cast<int>(std::min<int64_t>(units, 2ll * ctx->num_sms));
+        if (d_keep)
+            pack_dosage_tma_kernel<true><<<grid, 288, PT_SMEM, ctx->stream>>>(tmap, n, pc, m, d_codes, ldc, d_colsum,
+                                                                             d_flags, d_keep, ent_blocks, units);
+        else
+            pack_dosage_tma_kernel<false><<<grid, 288, PT_SMEM, ctx->stream>>>(tmap, n, pc, m, d_codes, ldc, d_colsum,
+                                                                              d_flags, nullptr, ent_blocks, units);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
     constexpr int EITERS = 4;
     dim3 grid(static_cast<unsigned>((pc + PK_LOCI - 1) / PK_LOCI),
               static_cast<unsigned>((n + PK_SLAB * EITERS - 1) / (PK_SLAB * EITERS)));

@@ -366,23 +366,9 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
     }
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        GRM_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn) {
-            grm_set_error("cuTensorMapEncodeTiled not available from the driver");
-            return GRM_CUDA_ERR_CUDA;
-        }
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
+    GrmEncodeTiledFn encode = nullptr;
+    GRM_TRY(grm_tmap_encoder(&encode));
     // dim0 = loci of one slab (bytes, contiguous), dim1 = entries, dim2 = slab.  Out-of-range rows/loci are
     // zero-filled by TMA, so ragged n (not a multiple of 128) and p (not a multiple of 128) contribute exact zeros
     // to the integer sums.
