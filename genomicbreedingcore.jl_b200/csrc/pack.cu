@@ -629,11 +629,8 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
-    static int use_tma = -1;
-    if (use_tma < 0) {
-        const char *e = getenv("GRM_CUDA_PACK");
-        use_tma = (e && !strcmp(e, "ldg")) ? 0 : 1;
-    }
+    const char *pack_env = getenv("GRM_CUDA_PACK");  // "ldg" forces the non-TMA variant (read per call: A/B timing)
+    const bool use_tma = !(pack_env && !strcmp(pack_env, "ldg"));
     if (use_tma && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(dA) % 16) == 0 && n < (1ll << 31) && pc < (1ll << 31)) {
         // TMA-staged variant: needs 16-byte aligned rows of A (global strides are multiples of 16 bytes)
         GrmEncodeTiledFn encode = nullptr;

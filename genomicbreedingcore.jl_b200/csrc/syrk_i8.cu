@@ -441,12 +441,8 @@ int32_t get_tile_list_2cta(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t w
 }
 
 bool use_2cta() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("GRM_CUDA_SYRK_I8");
-        v = (e && (!strcmp(e, "1cta") || !strcmp(e, "1"))) ? 0 : 1;  // default: CTA pairs (measured +18 % on C3)
-    }
-    return v == 1;
+    const char *e = getenv("GRM_CUDA_SYRK_I8");  // read per call so that both variants can be timed in one process
+    return !(e && (!strcmp(e, "1cta") || !strcmp(e, "1")));  // default: CTA pairs (measured +18 % on C3)
 }
 
 template <int EPI>

@@ -249,7 +249,26 @@ def stage_host():
     print("[host] rank-1 10x10 det after:", np.linalg.det(X))
 
 
-STAGES = {"env": stage_env, "int_small": stage_int_small, "int_c2": stage_int_c2, "peaks": stage_peaks,
+def stage_pack_ab():
+    """TMA-staged vs LDG pack kernel, alternating in one process, at C3's entry count."""
+    ctx = grm_b200.default_context(0)
+    n, p, m = 20000, 200000, 4
+    At = synth.dosage_device(n, p, m, 9, dev)
+    torch.cuda.synchronize()
+    codes, colsum, flags = D.pack_dosage(ctx, At, m)
+    res = {"tma": [], "ldg": []}
+    for rep in range(4):
+        for var in ("tma", "ldg"):
+            os.environ["GRM_CUDA_PACK"] = var
+            t, _ = ev_time(lambda: D.pack_dosage(ctx, At, m, codes=codes, colsum=colsum, flags=flags), ctx, reps=3)
+            res[var].append(t)
+    os.environ.pop("GRM_CUDA_PACK", None)
+    for var, ts in res.items():
+        best = min(ts)
+        print(f"[pack n={n} p={p}] {var}: best {best:.3f} ms -> {9*n*p/best/1e6:.0f} GB/s r+w; all {['%.3f' % t for t in ts]}")
+
+
+STAGES = {"pack_ab": stage_pack_ab, "env": stage_env, "int_small": stage_int_small, "int_c2": stage_int_c2, "peaks": stage_peaks,
           "f64": stage_f64, "host": stage_host}
 
 if __name__ == "__main__":
