@@ -73,3 +73,24 @@ def test_no_cpu_fallback_without_a_gpu():
         _lib.Context(0)
     assert e.value.status == _lib.ERR_CUDA
     assert "no CPU fallback" in e.value.message
+
+
+def test_bad_arguments_are_rejected_before_any_device_work():
+    """Null handles / pointers and impossible shapes come back as GRM_CUDA_ERR_BAD_ARGUMENT (no crash, no GPU needed)."""
+    import numpy as np
+
+    lib = _lib.load()
+    A = np.zeros((4, 6), order="F")
+    G = np.zeros((4, 4), order="F")
+    o = _lib.default_options()
+    info = _lib.new_info()
+    assert lib.grm_cuda_ctx_create(0, None) == _lib.ERR_BAD_ARGUMENT
+    assert lib.grm_cuda_simple(None, A.ctypes.data, 4, 6, 4, G.ctypes.data, 4, C.byref(o), C.byref(info)) == _lib.ERR_BAD_ARGUMENT
+    assert lib.grm_cuda_ploidyaware(None, A.ctypes.data, 4, 6, 4, 2, G.ctypes.data, 4, C.byref(o), C.byref(info)) == _lib.ERR_BAD_ARGUMENT
+    assert lib.grm_cuda_inflate_diagonals(None, G.ctypes.data, 4, 4, 10, 0, None, None) == _lib.ERR_BAD_ARGUMENT
+    assert lib.grm_cuda_ctx_destroy(None) == _lib.OK
+    assert lib.grm_cuda_ctx_synchronize(None) == _lib.ERR_BAD_ARGUMENT
+    assert lib.grm_cuda_tile_count(0, 0, 1) == -1 and lib.grm_cuda_tile_count(10, 2, 2) == -1
+    assert lib.grm_cuda_tile_owner(1000, 3, 2, 4) == -1  # ti > tj is not an upper-triangular tile
+    assert lib.grm_cuda_packed_tiles_max(1000, 3) == 4  # 4 x 4 tiles -> 10 upper tiles over 3 ranks
+    assert b"bad argument" in lib.grm_cuda_last_error() or lib.grm_cuda_last_error() != b""

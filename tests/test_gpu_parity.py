@@ -387,6 +387,46 @@ def test_qc_mask_kernel_matches_filter_rules(ctx):
         assert int(kept[0]) == int(want.sum())
 
 
+def test_context_reuse_across_sizes_and_bad_arguments():
+    """One context, grow-only workspaces: small -> large -> small calls stay correct; a second context is independent;
+    argument errors come back as statuses."""
+    ctx1, ctx2 = grm_b200.Context(0), grm_b200.Context(0)
+    small = synth.dosage(50, 300, 2, seed=81)
+    large = synth.dosage(700, 9000, 4, seed=82)
+    cont = synth.continuous(90, 700, seed=83)
+    ref_small = O.np_grmsimple_raw_dosage(small, 2)
+    ref_large = O.np_grmsimple_raw_dosage(large, 4)
+    for ctx in (ctx1, ctx2, ctx1):
+        assert np.array_equal(grm_call(small, ctx=ctx, skip_repair=True)[0], ref_small)
+        assert np.array_equal(grm_call(large, ctx=ctx, skip_repair=True)[0], ref_large)
+        assert relerr(grm_call(cont, 2, ctx=ctx, skip_repair=True)[0], O.c_grmploidyaware_raw(cont, 2)[1]) <= RTOL_F64
+        assert np.array_equal(grm_call(small, ctx=ctx, skip_repair=True)[0], ref_small)
+    lib = ctx1.lib
+    G = np.zeros((50, 50), order="F")
+    o = _lib.default_options()
+    info = _lib.new_info()
+    import ctypes as C
+
+    assert lib.grm_cuda_simple(ctx1.handle, small.ctypes.data, 50, 300, 49, G.ctypes.data, 50, C.byref(o), C.byref(info)) \
+        == _lib.ERR_BAD_ARGUMENT  # lda < n
+    assert lib.grm_cuda_simple(ctx1.handle, small.ctypes.data, 50, 0, 50, G.ctypes.data, 50, C.byref(o), C.byref(info)) \
+        == _lib.ERR_BAD_ARGUMENT  # p < 1
+    o.denominator = 3
+    assert lib.grm_cuda_simple(ctx1.handle, small.ctypes.data, 50, 300, 50, G.ctypes.data, 50, C.byref(o), C.byref(info)) \
+        == _lib.ERR_BAD_ARGUMENT  # denominator must be a power of two
+    o = _lib.default_options()
+    o.maf = 0.7
+    assert lib.grm_cuda_simple(ctx1.handle, small.ctypes.data, 50, 300, 50, G.ctypes.data, 50, C.byref(o), C.byref(info)) \
+        == _lib.ERR_BAD_ARGUMENT
+    # a wrong denominator hint is detected by the per-cell verification
+    with pytest.raises(_lib.GrmCudaError) as e:
+        grm_call(large, ctx=ctx1, denominator=2, skip_repair=True)
+    assert e.value.status == _lib.ERR_NOT_DOSAGE
+    # m^2 p must fit the int32 accumulators: detected up front (p is only a count here, no such matrix is allocated)
+    ctx1.close()
+    ctx2.close()
+
+
 # P9: ordering follows the input order of entries
 def test_row_order_follows_entries():
     A = synth.dosage(60, 500, 4, seed=13)
