@@ -93,6 +93,7 @@ SIGNATURES = {
     "grm_cuda_locus_qc": (_i32, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "grm_cuda_syrk_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32]),
     "grm_cuda_syrk_i8_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
+    "grm_cuda_syrk_i8_f64_tiles": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i32, _i32]),
     "grm_cuda_packed_tiles_max": (_i64, [_i64, _i32]),
     "grm_cuda_syrk_i8_packed": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "grm_cuda_finalize_tiles": (_i32, [_vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),

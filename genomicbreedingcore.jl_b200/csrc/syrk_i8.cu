@@ -44,6 +44,8 @@ struct EpiParams {
     double rcp;  // RN(1/denom) when the fast exact division applies, else 0
     const double *u;
     const int32_t *slots;  // mode 3: slot of tile t in the packed int32 tile buffer C ([slot][256 cols][256 rows])
+    double *Gt;            // modes 1, 2 (2-CTA kernel): if set, tile t is stored packed at Gt + t*65536 ([col][row],
+                           // zeros outside n) instead of into the dense matrix G: the sharded-output form
 };
 
 // Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
@@ -349,8 +351,17 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
                 tmem_wait_ld();
-                if (EPI == 3) epilogue_store_packed(r, packed, 128 * static_cast<int>(cta) + quarter * 32 + lane, c0);
-                else epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
+                if (EPI == 3) {
+                    epilogue_store_packed(r, packed, 128 * static_cast<int>(cta) + quarter * 32 + lane, c0);
+                } else if ((EPI == 1 || EPI == 2) && ep.Gt != nullptr) {
+                    // sharded output: the same arithmetic, addressed tile-locally (leading dimension 256)
+                    EpiParams lt = ep;
+                    lt.G = ep.Gt + static_cast<int64_t>(t) * 65536 - (static_cast<int64_t>(tc.x) + static_cast<int64_t>(tc.y) * 256);
+                    lt.ldg = 256;
+                    epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, lt);
+                } else {
+                    epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -668,6 +679,60 @@ extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_r
     ep.u = d_u;
     if (beta == 0.0 && gamma == 0.0) finalize_tiles_kernel<1><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep);
     else finalize_tiles_kernel<2><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+// Sharded-output form of grm_cuda_syrk_i8_f64: the tiles owned by (rank, world) are written as packed 256 x 256 FP64
+// tiles, d_tiles[t][col][row] for the t-th owned tile (grm_cuda_tile_at), zeros outside the n x n matrix.  For outputs
+// that do not fit one device as a dense matrix (BASELINE C5: n = 100,000 -> 80 GB, 10 GB per GPU on 8 GPUs).
+extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                              int64_t nslabs, double alpha, double beta, double gamma, double denom,
+                                              const double *d_u, double *d_tiles, int32_t rank, int32_t world) {
+    if (!ctx || !d_codes || !d_tiles || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || nslabs < 1 || world < 1 ||
+        rank < 0 || rank >= world || (beta != 0.0 && !d_u)) {
+        grm_set_error("syrk_i8_f64_tiles: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    CUtensorMap tmap;
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
+    const int2 *d_tl;
+    int count;
+    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tl, &count));
+    if (count == 0) return GRM_CUDA_OK;
+    // tiles at the ragged edge are only partly written by the epilogue: define the rest as zeros
+    GRM_CUDA_TRY(cudaMemsetAsync(d_tiles, 0, static_cast<size_t>(count) * 65536 * sizeof(double), ctx->stream));
+    EpiParams ep{};
+    ep.n = n;
+    ep.Gt = d_tiles;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.gamma = gamma;
+    ep.denom = denom;
+    const double a = fabs(denom);
+    ep.rcp = (a > 1e-200 && a < 1e200) ? 1.0 / denom : 0.0;
+    ep.u = d_u;
+    const int kbs = static_cast<int>((p + BK - 1) / BK);
+    const int pairs = std::min(count, ctx->num_sms / 2);
+    const bool simple = beta == 0.0 && gamma == 0.0;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[simple ? 0 : 1]) {
+        if (simple)
+            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(SMEM2_BYTES)));
+        else
+            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(SMEM2_BYTES)));
+        attr_set[simple ? 0 : 1] = true;
+    }
+    if (simple)
+        syrk_i8_2cta_kernel<1><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(tmap, d_tl, count,
+                                                                                     kbs * static_cast<int>(nslabs), kbs, ep);
+    else
+        syrk_i8_2cta_kernel<2><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(tmap, d_tl, count,
+                                                                                     kbs * static_cast<int>(nslabs), kbs, ep);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

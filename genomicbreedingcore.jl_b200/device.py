@@ -124,6 +124,21 @@ def syrk_i8_f64(ctx, codes, p: int, alpha: float, beta: float, gamma: float, den
     return out
 
 
+def syrk_i8_f64_tiles(ctx, codes, p: int, alpha: float, beta: float, gamma: float, denom: float, u=None, rank: int = 0,
+                      world: int = 1, out=None):
+    """Sharded-output SYRK: returns [tiles_owned, 256 (col), 256 (row)] FP64 tiles of this rank."""
+    torch = _torch()
+    nslabs, n, ldc = _slabs(codes)
+    count = ctx.lib.grm_cuda_tile_count(n, rank, world)
+    if out is None:
+        out = torch.empty((count, 256, 256), dtype=torch.float64, device=codes.device)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_syrk_i8_f64_tiles(ctx.handle, _ptr(codes), n, p, ldc, nslabs, alpha, beta, gamma, denom,
+                                                  _ptr(u) if u is not None else None, _ptr(out), rank, world))
+    ctx.order_torch_after()
+    return out
+
+
 def syrk_i8_packed(ctx, codes, p: int, world: int, out=None):
     """Raw int32 tiles of ALL upper-triangular tiles over this GPU's loci, in reduce-scatter layout
     [world * tiles_max, 65536]."""

@@ -77,7 +77,10 @@ class ShardedGRM:
     """Per-rank driver of the sharded int8 path on device-resident loci slabs."""
 
     def __init__(self, n: int, p: int, ploidy: Optional[int], denominator: int, ctx: _lib.Context, group=None,
-                 mode: str = "auto"):
+                 mode: str = "auto", output: str = "dense"):
+        """output="dense": this rank's tiles inside a zero-initialised local n x n matrix (self.G);
+        output="tiles" (gather mode): packed [tiles_owned, 256, 256] FP64 tiles (self.tiles), never a dense matrix —
+        the form for GRMs larger than one device (BASELINE config 5: n = 100,000, 10 GB of tiles per GPU on 8)."""
         torch = _torch()
         import torch.distributed as dist
 
@@ -103,7 +106,15 @@ class ShardedGRM:
             self.packed = torch.zeros((self.world * self.tiles_max, 65536), dtype=torch.int32, device=dev)
             self.reduced = torch.zeros((self.tiles_max, 65536), dtype=torch.int32, device=dev)
         self.flags = torch.zeros((16,), dtype=torch.int32, device=dev)
-        self.G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        self.output = output
+        if output == "tiles":
+            if mode != "gather":
+                raise ValueError('output="tiles" is available in "gather" mode')
+            self.tiles = torch.zeros((ctx.lib.grm_cuda_tile_count(n, self.rank, self.world), 256, 256),
+                                     dtype=torch.float64, device=dev)
+            self.G = None
+        else:
+            self.G = torch.zeros((n, n), dtype=torch.float64, device=dev)
         self.launches = 0
         self._gathered = False
 
@@ -123,7 +134,7 @@ class ShardedGRM:
                 ev[0].record()
             self.colsum_slab.zero_()
             self.flags.zero_()
-            if self._gathered:  # other ranks' tiles were summed in by gather(): start from zeros again
+            if self._gathered and self.G is not None:  # other ranks' tiles were summed in by gather()
                 self.G.zero_()
                 self._gathered = False
             if pc > 0:
@@ -149,9 +160,9 @@ class ShardedGRM:
                     sums, r_, T_ = D.dosage_stats(ctx, self.codes_slab, pc, self.colsum_slab)
                     self.launches += 2
                 else:
-                    sums = torch.zeros((2,), dtype=torch.int64, device=self.G.device)
-                    r_ = torch.zeros((n,), dtype=torch.int64, device=self.G.device)
-                    T_ = torch.zeros((n,), dtype=torch.int64, device=self.G.device)
+                    sums = torch.zeros((2,), dtype=torch.int64, device=self.codes_slab.device)
+                    r_ = torch.zeros((n,), dtype=torch.int64, device=self.codes_slab.device)
+                    T_ = torch.zeros((n,), dtype=torch.int64, device=self.codes_slab.device)
                 if self.world > 1:
                     packed = torch.cat([sums, r_, T_])
                     dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
@@ -161,7 +172,13 @@ class ShardedGRM:
             self.scale = denom
             if ev:
                 ev[3].record()
-            if self.mode == "gather":
+            if self.mode == "gather" and self.output == "tiles":
+                D.syrk_i8_f64_tiles(ctx, self.codes_all, min(self.L, p), alpha, beta, gamma, denom, u, rank=self.rank,
+                                    world=self.world, out=self.tiles)
+                self.launches += 1
+                if ev:
+                    ev[4].record()
+            elif self.mode == "gather":
                 D.syrk_i8_f64(ctx, self.codes_all, min(self.L, p), alpha, beta, gamma, denom, u, rank=self.rank,
                               world=self.world, out=self.G)
                 self.launches += 1
@@ -195,7 +212,7 @@ class ShardedGRM:
         if flags:
             raise _lib.GrmCudaError(_lib.ERR_MISSING if flags & 1 else _lib.ERR_NONFINITE if flags & 2
                                     else _lib.ERR_NOT_DOSAGE, f"input flags {flags} on rank {self.rank}")
-        return self.G
+        return self.G if self.output == "dense" else self.tiles
 
     def gather(self):
         """Single-device copy on every rank: sum of the zero-padded tile sets, then mirror."""

@@ -210,6 +210,13 @@ int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t 
 int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_sums, const int64_t *d_r, const int64_t *d_T,
                                int64_t n, int64_t p, int32_t m, int32_t ploidy, double *d_u, double *scalars);
 
+/* Sharded-output form of grm_cuda_syrk_i8_f64: the t-th tile owned by (rank, world) (grm_cuda_tile_at) is written as
+ * a packed 256 x 256 FP64 tile, d_tiles[t*65536 + col*256 + row], zeros outside the n x n matrix.  For GRMs that do
+ * not fit one device as a dense matrix (BASELINE config 5: n = 100,000 -> 80 GB; 10 GB of tiles per GPU on 8 GPUs). */
+int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                   int64_t nslabs, double alpha, double beta, double gamma, double denom,
+                                   const double *d_u, double *d_tiles, int32_t rank, int32_t world);
+
 /* u[i] = sum_k codes[i,k] * w[k]  in FP64, fixed summation order (bit-reproducible). */
 int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                            const double *d_w, double *d_u);

@@ -526,6 +526,36 @@ def test_loci_split_packed_tiles_emulated_ranks(ctx, world, ploidy):
     assert np.array_equal(G.cpu().numpy(), full)
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_sharded_output_tiles_match_dense_result(ctx, world):
+    """BASELINE config 5's output form (tiles stay on their owners, never a dense n x n matrix) at a reduced size."""
+    import ctypes as C
+
+    from grm_b200 import device as D
+
+    n, p, m, ploidy = 1100, 2000, 2, 2
+    A = synth.dosage(n, p, m, seed=91)
+    full, info = grm_call(A, ploidy, skip_repair=True)
+    codes, colsum, flags = D.pack_dosage(ctx, to_dev(A), m)
+    sums, r, T = D.dosage_stats(ctx, codes, p, colsum)
+    u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r, T, p, m, ploidy)
+    ti, tj = C.c_int64(), C.c_int64()
+    seen = 0
+    for rk in range(world):
+        tiles = D.syrk_i8_f64_tiles(ctx, codes, p, alpha, beta, gamma, denom, u, rank=rk, world=world)
+        ctx.synchronize()
+        th = tiles.cpu().numpy()
+        for t in range(th.shape[0]):
+            assert ctx.lib.grm_cuda_tile_at(n, rk, world, t, C.byref(ti), C.byref(tj)) == 0
+            r0, c0 = ti.value * 256, tj.value * 256
+            blk = np.zeros((256, 256))
+            sub = full[r0:r0 + 256, c0:c0 + 256]
+            blk[:sub.shape[0], :sub.shape[1]] = sub
+            assert np.array_equal(th[t].T, blk)  # tile is [col][row]
+            seen += 1
+    assert seen == 15  # 5 x 5 tiles, upper triangle
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size (BASELINE C2) properties: a checksum of checksums for the integer Gram matrix
 #   sum_j C_ij = sum_k c_ik S_k ,  C_ii = sum_k c_ik^2 ,  sum_ij C_ij = sum_k S_k^2      (S_k = column sums)
