@@ -298,7 +298,18 @@ def run_b200(args, wl):
     e2e = None
     e2e_detail = {}
     A_host = None
+    e2e_skip = None
     if not args.no_e2e:
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        need = 8 * n * pc + (8 * n * n if rank == 0 else 0)
+        if avail is not None and avail < 1.15 * need * world + (2 << 30):  # every rank allocates its share of the host
+            e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available, {need / 2**30:.0f} GiB needed for the host buffers"
+    if not args.no_e2e and e2e_skip is None:
         try:
             A_host = torch.empty((pc, n), dtype=torch.float64, pin_memory=True)
             pinned = True
@@ -404,7 +415,8 @@ def run_b200(args, wl):
                    "l2": "inputs larger than L2 (FP64 input and int8 codes >> 126 MB)",
                    "parallelism": f"loci-split pack + tcgen05 SYRK over own loci + int32 reduce-scatter onto tile owners x{world} ({sharded.mode})" if world > 1
                    else "single GPU", "macs_per_step": macs(n, p)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack,
+        "clocks": clocks, "e2e": e2e if e2e is not None else ({"unavailable": e2e_skip} if e2e_skip else None),
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack,
         "cpu_baseline": cpu, "stage_ms": stage_ms,
     }
     if world > 1:
