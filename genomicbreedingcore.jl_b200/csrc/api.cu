@@ -18,6 +18,9 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_
                                      int32_t centred, double ploidy, const double *d_q, int32_t accumulate,
                                      int32_t fill_missing, const uint8_t *d_keep, double *d_G, int64_t ldg, int32_t rank,
                                      int32_t world);
+extern "C" int32_t grm_cuda_centre_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
+                                       int32_t centred, double ploidy, const double *d_q, int32_t fill_missing,
+                                       const uint8_t *d_keep, double *d_Z, int64_t ldz);
 extern "C" int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, double maf,
                                      double max_locus_sparsity, int32_t error_on_missing, double *d_q, uint8_t *d_keep,
                                      uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags);
@@ -538,10 +541,33 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                     GRM_TRY(grm_cuda_locus_stats_f64(ctx, dc, n, feed.len(c), feed.ld_dev(),
                                                      ctx->q.as<double>() + feed.k0(c), d_stats, d_flags, c > 0,
                                                      meanfill ? 1 : 0));
-                GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), centred ? 1 : 0,
-                                          static_cast<double>(ploidy), ctx->q.as<double>() + feed.k0(c), c > 0,
-                                          meanfill ? 1 : 0, masked ? d_keep + feed.k0(c) : nullptr, dG, ldG, o.rank,
-                                          o.world));
+                const double *qc = ctx->q.as<double>() + feed.k0(c);
+                const uint8_t *kc = masked ? d_keep + feed.k0(c) : nullptr;
+                if (!(centred || meanfill || masked)) {
+                    // grmsimple on clean data: the operands are the input itself
+                    GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), 0, 0.0, nullptr, c > 0, 0, nullptr,
+                                              dG, ldG, o.rank, o.world));
+                } else if (in_host) {
+                    // the staged chunk is ours: centre / fill / mask it in place, then a pure-DMMA SYRK
+                    double *z = const_cast<double *>(dc);
+                    GRM_TRY(grm_cuda_centre_f64(ctx, dc, n, feed.len(c), n, centred ? 1 : 0, static_cast<double>(ploidy),
+                                                qc, meanfill ? 1 : 0, kc, z, n));
+                    GRM_TRY(grm_cuda_syrk_f64(ctx, z, n, feed.len(c), n, 0, 0.0, nullptr, c > 0, 0, nullptr, dG, ldG,
+                                              o.rank, o.world));
+                } else {
+                    // device-resident caller buffer (read-only): transformed sub-chunks go through a scratch buffer
+                    const int64_t zc = std::max<int64_t>(32, std::min<int64_t>(feed.len(c), (512ll << 20) / (n * 8)));
+                    GRM_TRY(ctx->stage[0].reserve(static_cast<size_t>(n) * zc * sizeof(double)));
+                    double *z = ctx->stage[0].as<double>();
+                    for (int64_t s0 = 0; s0 < feed.len(c); s0 += zc) {
+                        const int64_t sl = std::min(zc, feed.len(c) - s0);
+                        GRM_TRY(grm_cuda_centre_f64(ctx, dc + s0 * feed.ld_dev(), n, sl, feed.ld_dev(), centred ? 1 : 0,
+                                                    static_cast<double>(ploidy), qc + s0, meanfill ? 1 : 0,
+                                                    kc ? kc + s0 : nullptr, z, n));
+                        GRM_TRY(grm_cuda_syrk_f64(ctx, z, n, sl, n, 0, 0.0, nullptr, (c > 0 || s0 > 0) ? 1 : 0, 0, nullptr,
+                                                  dG, ldG, o.rank, o.world));
+                    }
+                }
                 GRM_TRY(feed.release(c));
             }
             GRM_CUDA_TRY(cudaEventRecord(ev[1], st));

@@ -244,6 +244,13 @@ int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_
                           const uint8_t *d_keep /* optional QC mask */, double *d_G, int64_t ldg, int32_t rank,
                           int32_t world);
 
+/* Z (n x pc, leading dimension ldz) = the SYRK operand of a loci chunk, written once so that the contraction itself is
+ * pure DMMA: z = x (centred == 0) or fl(fl(ploidy*fl(x-0.5)) - q_k) (calc.jl:198,205); a NaN x is replaced by q_k first
+ * when fill_missing != 0; columns with keep == 0 become zeros.  In place (d_Z == dA, ldz == lda) is allowed. */
+int32_t grm_cuda_centre_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda, int32_t centred,
+                            double ploidy, const double *d_q, int32_t fill_missing, const uint8_t *d_keep,
+                            double *d_Z, int64_t ldz);
+
 /* G[i,j] = G[i,j]/denom for i <= j, then G[j,i] = G[i,j] for i < j (whole matrix; exact symmetry). */
 int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom);
 /* Copy the upper triangle onto the lower one (scale_mirror with denom = 1). */

@@ -271,6 +271,38 @@ def stage_pack_ab():
 STAGES = {"pack_ab": stage_pack_ab, "env": stage_env, "int_small": stage_int_small, "int_c2": stage_int_c2, "peaks": stage_peaks,
           "f64": stage_f64, "host": stage_host}
 
+def stage_f64_ab():
+    """FP64 SYRK: burst vs sustained, and the cost of centring / mean-fill on operand load."""
+    ctx = grm_b200.default_context(0)
+    n, p = 4096, 32768
+    At = synth.continuous_device(n, p, 5, dev)
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    t, _ = ev_time(lambda: D.syrk_f64(ctx, At, False, out=G), ctx)
+    print(f"[f64 burst n={n} p={p}] {t:.2f} ms -> {n*n*p/t/1e9:.1f} TFLOP/s")
+    with D.on_ctx_stream(ctx):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(150):
+            D.syrk_f64(ctx, At, False, out=G)
+        b.record()
+        b.synchronize()
+    t = a.elapsed_time(b) / 150
+    print(f"[f64 sustained 150 launches] {t:.2f} ms -> {n*n*p/t/1e9:.1f} TFLOP/s")
+    sh("nvidia-smi --query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap --format=csv,noheader")
+    del At, G
+    n, p = 10000, 100000
+    At = synth.continuous_device(n, p, 6, dev)
+    q, stats, flags = D.locus_stats_f64(ctx, At)
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for name, kw in (("simple", dict(centred=False)), ("centred", dict(centred=True, q=q)),
+                     ("centred+fill", dict(centred=True, q=q, fill_missing=True))):
+        t, ts = ev_time(lambda: D.syrk_f64(ctx, At, ploidy=2.0, out=G, **kw), ctx, reps=2)
+        print(f"[f64 n={n} p={p} {name}] {t:.1f} ms -> {n*n*p/t/1e9:.1f} TFLOP/s useful", ts)
+
+
+STAGES["f64_ab"] = stage_f64_ab
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:
@@ -280,3 +312,4 @@ if __name__ == "__main__":
         except Exception:
             traceback.print_exc()
         sys.stdout.flush()
+
