@@ -3,12 +3,12 @@
 
 The directory name contains a dot, so import it through the repo-root shim:  `import grm_b200`.
 """
-from . import _lib, synth
+from . import _lib, io, synth
 from ._lib import Context, GrmCudaError, default_context
 from .grm import grm_call, grmploidyaware, grmsimple, inflatediagonals
 from .structs import GRM, ArgumentError, ErrorException, Genomes, MissingDataError, checkdims, clone
 
 __all__ = [
     "Context", "GrmCudaError", "default_context", "grm_call", "grmsimple", "grmploidyaware", "inflatediagonals", "GRM", "Genomes",
-    "ArgumentError", "ErrorException", "MissingDataError", "checkdims", "clone", "synth",
+    "ArgumentError", "ErrorException", "MissingDataError", "checkdims", "clone", "synth", "io",
 ]
