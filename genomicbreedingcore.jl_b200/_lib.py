@@ -102,7 +102,7 @@ SIGNATURES = {
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "grm_cuda_locus_stats_i8": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "grm_cuda_locus_stats_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32]),
-    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _i32]),
+    "grm_cuda_syrk_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _i32, _i32]),
     "grm_cuda_centre_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _f64, _vp, _i32, _vp, _vp, _i64]),
     "grm_cuda_scale_mirror": (_i32, [_vp, _vp, _i64, _i64, _f64]),
     "grm_cuda_mirror": (_i32, [_vp, _vp, _i64, _i64]),

@@ -14,10 +14,8 @@ extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t
 extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
                                             double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate,
                                             int32_t skip_missing);
-extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                     int32_t centred, double ploidy, const double *d_q, int32_t accumulate,
-                                     int32_t fill_missing, const uint8_t *d_keep, double *d_G, int64_t ldg, int32_t rank,
-                                     int32_t world);
+extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_t n, int64_t p, int64_t ldz,
+                                     int32_t accumulate, double *d_G, int64_t ldg, int32_t rank, int32_t world);
 extern "C" int32_t grm_cuda_centre_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
                                        int32_t centred, double ploidy, const double *d_q, int32_t fill_missing,
                                        const uint8_t *d_keep, double *d_Z, int64_t ldz);
@@ -545,15 +543,13 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 const uint8_t *kc = masked ? d_keep + feed.k0(c) : nullptr;
                 if (!(centred || meanfill || masked)) {
                     // grmsimple on clean data: the operands are the input itself
-                    GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), 0, 0.0, nullptr, c > 0, 0, nullptr,
-                                              dG, ldG, o.rank, o.world));
+                    GRM_TRY(grm_cuda_syrk_f64(ctx, dc, n, feed.len(c), feed.ld_dev(), c > 0, dG, ldG, o.rank, o.world));
                 } else if (in_host) {
                     // the staged chunk is ours: centre / fill / mask it in place, then a pure-DMMA SYRK
                     double *z = const_cast<double *>(dc);
                     GRM_TRY(grm_cuda_centre_f64(ctx, dc, n, feed.len(c), n, centred ? 1 : 0, static_cast<double>(ploidy),
                                                 qc, meanfill ? 1 : 0, kc, z, n));
-                    GRM_TRY(grm_cuda_syrk_f64(ctx, z, n, feed.len(c), n, 0, 0.0, nullptr, c > 0, 0, nullptr, dG, ldG,
-                                              o.rank, o.world));
+                    GRM_TRY(grm_cuda_syrk_f64(ctx, z, n, feed.len(c), n, c > 0, dG, ldG, o.rank, o.world));
                 } else {
                     // device-resident caller buffer (read-only): transformed sub-chunks go through a scratch buffer
                     const int64_t zc = std::max<int64_t>(32, std::min<int64_t>(feed.len(c), (512ll << 20) / (n * 8)));
@@ -564,8 +560,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                         GRM_TRY(grm_cuda_centre_f64(ctx, dc + s0 * feed.ld_dev(), n, sl, feed.ld_dev(), centred ? 1 : 0,
                                                     static_cast<double>(ploidy), qc + s0, meanfill ? 1 : 0,
                                                     kc ? kc + s0 : nullptr, z, n));
-                        GRM_TRY(grm_cuda_syrk_f64(ctx, z, n, sl, n, 0, 0.0, nullptr, (c > 0 || s0 > 0) ? 1 : 0, 0, nullptr,
-                                                  dG, ldG, o.rank, o.world));
+                        GRM_TRY(grm_cuda_syrk_f64(ctx, z, n, sl, n, (c > 0 || s0 > 0) ? 1 : 0, dG, ldG, o.rank, o.world));
                     }
                 }
                 GRM_TRY(feed.release(c));

@@ -2,8 +2,8 @@
 // scale-and-mirror pass that makes the result exactly symmetric.
 //
 // Replaces the pair loop of src/grm/calc.jl:124-131 (grmsimple, z = x) and :202-209 (grmploidyaware,
-// z_ik = fl(fl(ploidy*fl(x_ik - 0.5)) - q_k), calc.jl:198,205 — the centring is applied while the operand is
-// staged into shared memory, with the reference's rounding sequence: no FMA contraction).
+// z_ik = fl(fl(ploidy*fl(x_ik - 0.5)) - q_k), calc.jl:198,205).  The operand Z is produced once per loci chunk by
+// centre_f64_kernel (reference rounding sequence, optional mean-fill and QC mask); the SYRK main loop is pure DMMA.
 //
 // tcgen05 has no FP64 kind, so the contraction runs on the FP64 tensor path that exists on sm_100:
 // mma.sync.m16n8k8.f64 (DMMA).  Block tile 128 x 128 entries, 8 warps (2 x 4), warp tile 64 x 32, K slab of 16
@@ -28,11 +28,9 @@ __device__ __forceinline__ void dmma_m16n8k8(double (&c)[4], const double (&a)[4
         : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
-template <bool CENTRED, bool FILL>
 __global__ void __launch_bounds__(256, 1)
-syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, double ploidy,
-                const double *__restrict__ q, const int2 *__restrict__ tiles, double *__restrict__ G, int64_t ldg,
-                int accumulate, const uint8_t *__restrict__ keep) {
+syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda, const int2 *__restrict__ tiles,
+                double *__restrict__ G, int64_t ldg, int accumulate) {
     extern __shared__ double sm[];
     double(*sA)[FK][FLD] = reinterpret_cast<double(*)[FK][FLD]>(sm);
     double(*sB)[FK][FLD] = reinterpret_cast<double(*)[FK][FLD]>(sm + 2 * FK * FLD);
@@ -61,20 +59,9 @@ syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int64_t k = k0 + h * FH + kh + j;
-            const bool vk = k < p && (keep == nullptr || keep[k] != 0);  // loci dropped by the QC mask contribute 0
-            double xa = (vk && va) ? __ldg(A + ra + k * lda) : 0.0;
-            double xb = (vk && vb) ? __ldg(A + rb + k * lda) : 0.0;
-            double qk = 0.0;
-            if (CENTRED || FILL) qk = vk ? __ldg(q + k) : 0.0;
-            if (FILL) {  // missing cell -> per-locus mean of the valid cells
-                xa = (xa != xa) ? qk : xa;
-                xb = (xb != xb) ? qk : xb;
-            }
-            if (CENTRED) {
-                // z = fl(fl(ploidy * fl(x - 0.5)) - q): explicit round-to-nearest ops, never contracted
-                xa = (vk && va) ? __dsub_rn(__dmul_rn(ploidy, __dsub_rn(xa, 0.5)), qk) : 0.0;
-                xb = (vk && vb) ? __dsub_rn(__dmul_rn(ploidy, __dsub_rn(xb, 0.5)), qk) : 0.0;
-            }
+            const bool vk = k < p;
+            const double xa = (vk && va) ? __ldg(A + ra + k * lda) : 0.0;
+            const double xb = (vk && vb) ? __ldg(A + rb + k * lda) : 0.0;
             pa[j] = xa;
             pb[j] = xb;
         }
@@ -241,14 +228,11 @@ int32_t get_tile_list_f64(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t wo
 
 }  // namespace
 
-extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                     int32_t centred, double ploidy, const double *d_q, int32_t accumulate,
-                                     int32_t fill_missing, const uint8_t *d_keep, double *d_G, int64_t ldg, int32_t rank,
-                                     int32_t world) {
-    if (!ctx || !dA || !d_G || n < 1 || p < 1 || lda < n || ldg < n || ((centred || fill_missing) && !d_q) || world < 1 ||
-        rank < 0 || rank >= world) {
-        grm_set_error("syrk_f64: bad argument (n=%lld p=%lld lda=%lld ldg=%lld)", (long long)n, (long long)p,
-                      (long long)lda, (long long)ldg);
+extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_t n, int64_t p, int64_t ldz,
+                                     int32_t accumulate, double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+    if (!ctx || !dZ || !d_G || n < 1 || p < 1 || ldz < n || ldg < n || world < 1 || rank < 0 || rank >= world) {
+        grm_set_error("syrk_f64: bad argument (n=%lld p=%lld ldz=%lld ldg=%lld)", (long long)n, (long long)p,
+                      (long long)ldz, (long long)ldg);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -256,18 +240,13 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_
     int count;
     GRM_TRY(get_tile_list_f64(ctx, n, rank, world, &d_tiles, &count));
     if (count == 0) return GRM_CUDA_OK;
-    typedef void (*KernelFn)(const double *, int64_t, int64_t, int64_t, double, const double *, const int2 *, double *,
-                             int64_t, int, const uint8_t *);
-    static const KernelFn kernels[4] = {syrk_f64_kernel<false, false>, syrk_f64_kernel<true, false>,
-                                        syrk_f64_kernel<false, true>, syrk_f64_kernel<true, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (KernelFn k : kernels)
-            GRM_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(F64_SMEM)));
+        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(F64_SMEM)));
         attr_set = true;
     }
-    const KernelFn kernel = kernels[(centred ? 1 : 0) + (fill_missing ? 2 : 0)];
-    kernel<<<count, 256, F64_SMEM, ctx->stream>>>(dA, n, p, lda, ploidy, d_q, d_tiles, d_G, ldg, accumulate, d_keep);
+    syrk_f64_kernel<<<count, 256, F64_SMEM, ctx->stream>>>(dZ, n, p, ldz, d_tiles, d_G, ldg, accumulate);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

@@ -230,17 +230,32 @@ def locus_stats_f64(ctx, A_pn, accumulate: bool = False, q=None, stats=None, fla
     return q, stats, flags
 
 
-def syrk_f64(ctx, A_pn, centred: bool, ploidy: float = 2.0, q=None, accumulate: bool = False, rank: int = 0,
+def centre_f64(ctx, A_pn, centred: bool, ploidy: float = 2.0, q=None, fill_missing: bool = False, keep=None, out=None):
+    """SYRK operand Z of a loci chunk: centred per calc.jl:198,205, optionally mean-filled and masked."""
+    torch = _torch()
+    p, n = A_pn.shape
+    if out is None:
+        out = torch.empty_like(A_pn)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_centre_f64(ctx.handle, _ptr(A_pn), n, p, n, 1 if centred else 0, float(ploidy),
+                                           _ptr(q) if q is not None else None, 1 if fill_missing else 0,
+                                           _ptr(keep) if keep is not None else None, _ptr(out), n))
+    ctx.order_torch_after()
+    return out
+
+
+def syrk_f64(ctx, A_pn, centred: bool = False, ploidy: float = 2.0, q=None, accumulate: bool = False, rank: int = 0,
              world: int = 1, out=None, fill_missing: bool = False, keep=None):
+    """G (+)= Z Z' over the owned upper-triangular tiles; Z = A, or centre_f64(A) when centring / filling / masking."""
     torch = _torch()
     p, n = A_pn.shape
     if out is None:
         out = torch.zeros((n, n), dtype=torch.float64, device=A_pn.device)
+    Z = A_pn
+    if centred or fill_missing or keep is not None:
+        Z = centre_f64(ctx, A_pn, centred, ploidy, q, fill_missing, keep)
     ctx.synchronize_with_torch()
-    _lib.check(ctx.lib.grm_cuda_syrk_f64(ctx.handle, _ptr(A_pn), n, p, n, 1 if centred else 0, float(ploidy),
-                                         _ptr(q) if q is not None else None, 1 if accumulate else 0,
-                                         1 if fill_missing else 0, _ptr(keep) if keep is not None else None, _ptr(out),
-                                         n, rank, world))
+    _lib.check(ctx.lib.grm_cuda_syrk_f64(ctx.handle, _ptr(Z), n, p, n, 1 if accumulate else 0, _ptr(out), n, rank, world))
     ctx.order_torch_after()
     return out
 

@@ -234,15 +234,11 @@ int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n,
                                  double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate,
                                  int32_t skip_missing);
 
-/* FP64 upper-triangular SYRK over owned tiles, raw sums (no division):
- *   centred == 0: G (+)= A*A'            (grmsimple, calc.jl:127)
- *   centred == 1: G (+)= Z*Z', z_ik = fl(fl(ploidy*fl(A_ik - 0.5)) - q_k) formed on operand load (calc.jl:198,205)
- * accumulate != 0 adds to G (loci streamed in chunks).  fill_missing != 0 replaces a NaN A_ik by q_k before anything
- * else (d_q required).  FP64 tensor path (DMMA). */
-int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int32_t centred,
-                          double ploidy, const double *d_q, int32_t accumulate, int32_t fill_missing,
-                          const uint8_t *d_keep /* optional QC mask */, double *d_G, int64_t ldg, int32_t rank,
-                          int32_t world);
+/* FP64 upper-triangular SYRK over owned tiles, raw sums (no division):  G (+)= Z*Z'  (pair loops of calc.jl:124-131,
+ * :202-209).  Z is the input itself for grmsimple on clean data, otherwise the output of grm_cuda_centre_f64.
+ * accumulate != 0 adds to G (loci streamed in chunks).  FP64 tensor path (DMMA), pure-DMMA main loop. */
+int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_t n, int64_t p, int64_t ldz, int32_t accumulate,
+                          double *d_G, int64_t ldg, int32_t rank, int32_t world);
 
 /* Z (n x pc, leading dimension ldz) = the SYRK operand of a loci chunk, written once so that the contraction itself is
  * pure DMMA: z = x (centred == 0) or fl(fl(ploidy*fl(x-0.5)) - q_k) (calc.jl:198,205); a NaN x is replaced by q_k first
