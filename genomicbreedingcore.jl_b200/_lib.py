@@ -97,7 +97,7 @@ SIGNATURES = {
     "grm_cuda_packed_tiles_max": (_i64, [_i64, _i32]),
     "grm_cuda_syrk_i8_packed": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "grm_cuda_finalize_tiles": (_i32, [_vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
-    "grm_cuda_dosage_stats": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32]),
+    "grm_cuda_dosage_stats": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _i32]),
     "grm_cuda_dosage_centre": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, C.POINTER(_f64)]),
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "grm_cuda_locus_stats_i8": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),

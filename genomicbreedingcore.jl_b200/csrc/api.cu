@@ -23,8 +23,8 @@ extern "C" int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_
                                      double max_locus_sparsity, int32_t error_on_missing, double *d_q, uint8_t *d_keep,
                                      uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags);
 extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                         const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
-                                         int32_t accumulate);
+                                         const int32_t *d_colsum, int32_t m, uint64_t *d_sums, int64_t *d_r,
+                                         int64_t *d_T, int32_t accumulate);
 extern "C" int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_sums, const int64_t *d_r,
                                           const int64_t *d_T, int64_t n, int64_t p, int32_t m, int32_t ploidy,
                                           double *d_u, double *scalars);
@@ -356,6 +356,11 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                       (long long)lda, (long long)ldg, o.rank, o.world);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
+    if (!o.skip_repair && o.world == 1 && n > 46000) {
+        grm_set_error("inflatediagonals! on n = %lld exceeds the single-GPU cuSOLVER range (n <= 46000); pass skip_repair "
+                      "to obtain the raw GRM", (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
     if (n > INT32_MAX - 512 || p > INT32_MAX - 512) {
         grm_set_error("n and p must fit TMA's 32-bit coordinates");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -513,7 +518,7 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
                 GRM_TRY(ctx->rT.reserve(static_cast<size_t>(2 * n + 2) * sizeof(int64_t)));
                 uint64_t *d_sums = ctx->rT.as<uint64_t>();
                 int64_t *d_r = ctx->rT.as<int64_t>() + 2, *d_T = d_r + n;
-                GRM_TRY(grm_cuda_dosage_stats(ctx, d_codes, n, p, ldc, d_colsum, d_sums, d_r, d_T, 0));
+                GRM_TRY(grm_cuda_dosage_stats(ctx, d_codes, n, p, ldc, d_colsum, m, d_sums, d_r, d_T, 0));
                 double sc[4];
                 GRM_TRY(grm_cuda_dosage_centre(ctx, d_sums, d_r, d_T, n, p_eff, m, ploidy, ctx->u.as<double>(), sc));
                 denom = sc[3];  // calc.jl:201

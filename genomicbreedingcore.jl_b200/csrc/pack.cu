@@ -735,15 +735,23 @@ extern "C" int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, 
 }
 
 extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                         const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
-                                         int32_t accumulate) {
-    if (!ctx || !d_codes || !d_colsum || !d_sums || !d_r || !d_T || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p) {
+                                         const int32_t *d_colsum, int32_t m, uint64_t *d_sums, int64_t *d_r,
+                                         int64_t *d_T, int32_t accumulate) {
+    if (!ctx || !d_codes || !d_colsum || !d_sums || !d_r || !d_T || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p ||
+        m < 1 || m > 64) {
         grm_set_error("dosage_stats: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     if (n >= (1ll << 18)) {  // S_k <= 64 n must fit the three byte planes
         grm_set_error("dosage_stats: n = %lld exceeds 2^18 entries", (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    // sum_k S_k^2 <= p (m n)^2 is accumulated in 64 bits: refuse shapes where even the bound could wrap
+    const double mnf = static_cast<double>(m) * static_cast<double>(n);
+    if (static_cast<double>(p) * mnf * mnf >= 9.0e18) {
+        grm_set_error("dosage_stats: p * (m n)^2 = %.3g may overflow the 64-bit sum of squared column sums",
+                      static_cast<double>(p) * mnf * mnf);
+        return GRM_CUDA_ERR_OVERFLOW;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     GRM_TRY(ctx->planes.reserve(static_cast<size_t>(3 * ldc)));

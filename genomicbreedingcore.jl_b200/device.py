@@ -174,7 +174,7 @@ def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
     return q, w, stats
 
 
-def dosage_stats(ctx, codes, p: int, colsum, sums=None, r=None, T=None, accumulate: bool = False):
+def dosage_stats(ctx, codes, p: int, colsum, sums=None, r=None, T=None, accumulate: bool = False, m: int = 64):
     """Exact integer r_i, T_i and {sum S, sum S^2} of one slab of codes (see grm_cuda_dosage_stats)."""
     torch = _torch()
     n, ldc = codes.shape
@@ -184,8 +184,8 @@ def dosage_stats(ctx, codes, p: int, colsum, sums=None, r=None, T=None, accumula
         r = torch.zeros((n,), dtype=torch.int64, device=dev)
         T = torch.zeros((n,), dtype=torch.int64, device=dev)
     ctx.synchronize_with_torch()
-    _lib.check(ctx.lib.grm_cuda_dosage_stats(ctx.handle, _ptr(codes), n, p, ldc, _ptr(colsum), _ptr(sums), _ptr(r),
-                                             _ptr(T), 1 if accumulate else 0))
+    _lib.check(ctx.lib.grm_cuda_dosage_stats(ctx.handle, _ptr(codes), n, p, ldc, _ptr(colsum), int(m), _ptr(sums),
+                                             _ptr(r), _ptr(T), 1 if accumulate else 0))
     ctx.order_torch_after()
     return sums, r, T
 

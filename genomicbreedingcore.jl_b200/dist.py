@@ -157,7 +157,7 @@ class ShardedGRM:
                 # integer statistics of the rank's OWN loci, then an exact integer all-reduce (r, T and the two sums
                 # are additive over loci): no rank re-reads the other slabs, and any rank count gives the same bits
                 if pc > 0:
-                    sums, r_, T_ = D.dosage_stats(ctx, self.codes_slab, pc, self.colsum_slab)
+                    sums, r_, T_ = D.dosage_stats(ctx, self.codes_slab, pc, self.colsum_slab, m=m)
                     self.launches += 2
                 else:
                     sums = torch.zeros((2,), dtype=torch.int64, device=self.codes_slab.device)

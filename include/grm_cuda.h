@@ -198,9 +198,10 @@ int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int
 /* Exact integer statistics of the codes for the rank-1 centring of grmploidyaware:
  *   r[i] = sum_k codes[i,k]      T[i] = sum_k codes[i,k]*colsum[k]      sums = { sum_k colsum[k], sum_k colsum[k]^2 }
  * (dp4a against the byte planes of colsum; order-independent, hence bit-identical for any chunking / GPU count).
- * accumulate != 0 adds to r, T and sums (loci held as several slabs).  Requires n < 2^18. */
+ * accumulate != 0 adds to r, T and sums (loci held as several slabs).  Requires n < 2^18 and p*(m*n)^2 < 9e18
+ * (m = dosage denominator: the codes are in [0, m]). */
 int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                              const int32_t *d_colsum, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
+                              const int32_t *d_colsum, int32_t m, uint64_t *d_sums, int64_t *d_r, int64_t *d_T,
                               int32_t accumulate);
 
 /* From those integers (q_k = colsum_k/(m n), w_k = ploidy/2 + q_k; calc.jl:197-201,205), with p the total loci count:
