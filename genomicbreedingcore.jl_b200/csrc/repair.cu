@@ -8,6 +8,7 @@
 #include <cusolverDn.h>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -85,6 +86,18 @@ struct Repair {
     double *d_diag;
     std::vector<double> h_diag;
     std::vector<int> h_ipiv;
+    // 64-bit cuSOLVER API (GRM_CUDA_GETRF=x0|x1): same LAPACK-style partial-pivoting LU, int64 pivots, selectable
+    // algorithm; measured against the legacy Dgetrf in profiles/
+    int xalg = -1;  // -1 = legacy cusolverDnDgetrf
+    cusolverDnParams_t params = nullptr;
+    ~Repair() {
+        if (params) cusolverDnDestroyParams(params);
+    }
+    int64_t *ipiv64 = nullptr;
+    void *xwork_d = nullptr;
+    size_t xwork_d_bytes = 0, xwork_h_bytes = 0;
+    std::vector<char> xwork_h;
+    std::vector<int64_t> h_ipiv64;
 
     int32_t copy_in() {
         const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
@@ -98,14 +111,21 @@ struct Repair {
     // sequential product of diag(U) times (-1)^(number of row interchanges).
     int32_t det(double *out) {
         GRM_TRY(copy_in());
-        GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), work_mat, static_cast<int>(n),
-                                        lwork, ipiv, info));
+        if (xalg >= 0)
+            GRM_SOLVER_TRY(cusolverDnXgetrf(h, params, n, n, CUDA_R_64F, work_mat, n, ipiv64, CUDA_R_64F, xwork_d,
+                                            xwork_d_bytes, xwork_h.data(), xwork_h_bytes, info));
+        else
+            GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), work_mat, static_cast<int>(n),
+                                            lwork, ipiv, info));
         diag_extract_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(work_mat, n, d_diag);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         int h_info = 0;
         GRM_CUDA_TRY(cudaMemcpyAsync(h_diag.data(), d_diag, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (xalg >= 0)
+            GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv64.data(), ipiv64, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (h_info < 0) {
@@ -120,7 +140,8 @@ struct Repair {
         int swaps = 0;
         for (int64_t i = 0; i < n; ++i) {
             P = P * h_diag[i];
-            if (h_ipiv[i] != static_cast<int>(i + 1)) ++swaps;
+            const int64_t pv = xalg >= 0 ? h_ipiv64[i] : static_cast<int64_t>(h_ipiv[i]);
+            if (pv != i + 1) ++swaps;
         }
         *out = (swaps & 1) ? -P : P;
         return GRM_CUDA_OK;
@@ -155,7 +176,7 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
                           double *eps_total) {
     *iters = 0;
     *eps_total = 0.0;
-    if (n > 46000) {  // legacy 32-bit cuSOLVER indexing: n*n must stay below 2^31
+    if (n > 46000) {  // 32-bit indexing of the legacy potrf/getrf entry points: n*n must stay below 2^31
         grm_set_error("inflate_diagonals: n=%lld exceeds the single-GPU cuSOLVER range (n <= 46000)", (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
@@ -209,6 +230,22 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
     r.d_diag = reinterpret_cast<double *>(r.ipiv + int_slots);
     r.h_diag.resize(n);
     r.h_ipiv.resize(n);
+    {
+        const char *e = getenv("GRM_CUDA_GETRF");
+        if (e && e[0] == 'x') r.xalg = (e[1] == '1') ? 1 : 0;
+    }
+    if (r.xalg >= 0) {
+        GRM_SOLVER_TRY(cusolverDnCreateParams(&r.params));
+        GRM_SOLVER_TRY(cusolverDnSetAdvOptions(r.params, CUSOLVERDN_GETRF, r.xalg == 1 ? CUSOLVER_ALG_1 : CUSOLVER_ALG_0));
+        GRM_SOLVER_TRY(cusolverDnXgetrf_bufferSize(h, r.params, n, n, CUDA_R_64F, r.work_mat, n, CUDA_R_64F,
+                                                   &r.xwork_d_bytes, &r.xwork_h_bytes));
+        const size_t off = (r.xwork_d_bytes + 255) & ~size_t(255);
+        GRM_TRY(ctx->misc2.reserve(off + static_cast<size_t>(n) * sizeof(int64_t)));
+        r.xwork_d = ctx->misc2.ptr;
+        r.ipiv64 = reinterpret_cast<int64_t *>(static_cast<char *>(ctx->misc2.ptr) + off);
+        r.xwork_h.resize(r.xwork_h_bytes + 1);
+        r.h_ipiv64.resize(n);
+    }
 
     const double eps = DBL_EPSILON;
     // calc.jl:49-51 — early return; isposdef is evaluated only if det > eps (&& short-circuit)

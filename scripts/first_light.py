@@ -303,6 +303,36 @@ def stage_f64_ab():
 STAGES["f64_ab"] = stage_f64_ab
 
 
+def stage_repair_ab():
+    """inflatediagonals!: legacy cusolverDnDgetrf vs the 64-bit cusolverDnXgetrf (ALG_0 / ALG_1)."""
+    import ctypes as C
+    ctx = grm_b200.default_context(0)
+    for (n, p, m, ploidy) in [(5000, 20000, 2, None), (20000, 20000, 4, 4)]:
+        At = synth.dosage_device(n, p, m, 3, dev)
+        G0, info = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)
+        ctx.synchronize()
+        base = None
+        for var in ("legacy", "x0", "x1", "legacy"):
+            os.environ["GRM_CUDA_GETRF"] = var
+            G = G0.clone()
+            torch.cuda.synchronize()
+            it, tot = C.c_int32(0), C.c_double(0.0)
+            t0 = time.perf_counter()
+            _lib.check(ctx.lib.grm_cuda_inflate_diagonals(ctx.handle, G.data_ptr(), n, n, 1000, _lib.LOC_DEVICE,
+                                                          C.byref(it), C.byref(tot)))
+            ctx.synchronize()
+            dt = time.perf_counter() - t0
+            res = (it.value, tot.value)
+            same = base is None or (res == base[0] and torch.equal(G, base[1]))
+            if base is None:
+                base = (res, G)
+            print(f"[repair n={n}] {var}: {dt*1e3:.1f} ms iters={it.value} eps_total={tot.value:.6g} identical_to_legacy={same}")
+    os.environ.pop("GRM_CUDA_GETRF", None)
+
+
+STAGES["repair_ab"] = stage_repair_ab
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:
