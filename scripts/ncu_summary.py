@@ -71,9 +71,10 @@ def main():
                 f = float(v.replace(",", ""))
                 return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
             short = "syrk_i8" if "syrk_i8" in name else "pack" if "pack_dosage" in name else name.split("(")[0]
-            summary[f"{short}_dram_bytes_per_launch"] = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
-            summary[f"{short}_tensor_pipe_pct"] = vals.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("", ""))[0]
-            summary[f"{short}_dram_pct"] = vals.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", ("", ""))[0]
+            wl = tag.split("_")[-1]  # r1_c2 -> c2
+            summary[f"{short}_dram_bytes_per_launch_{wl}"] = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
+            summary[f"{short}_tensor_pipe_pct_{wl}"] = vals.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("", ""))[0]
+            summary[f"{short}_dram_pct_{wl}"] = vals.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", ("", ""))[0]
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     open(os.path.join(ROOT, "profiles", f"ncu_{tag}.md"), "w").write("\n".join(lines) + "\n")
     sp = os.path.join(ROOT, "profiles", "ncu_summary.json")
