@@ -55,7 +55,7 @@ struct grm_cuda_ctx {
     cudaEvent_t copy_done[2] = {}, stage_free[2] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
-    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt, keep;
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt, keep, progress;
     TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed;
     int32_t launches = 0;  // kernels launched since last reset
 };

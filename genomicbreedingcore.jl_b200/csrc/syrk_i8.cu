@@ -232,13 +232,34 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict_
 // Only the leader CTA (rank 0) issues MMAs; its tcgen05.commit multicasts to the barriers of both CTAs.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int STAGES2 = 6;
+constexpr int NUM_THREADS2 = 224;  // warps 0..5 as in the single-CTA kernel + warp 6: K-window watcher
 constexpr uint32_t STAGE2_BYTES = 2 * A_BYTES;  // A (16 KiB) + this CTA's half of B (16 KiB)
 constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 
+// K-window synchronisation of the persistent CTA pairs.  All pairs stream the loci (K) of their current tile at the same
+// nominal pace, and tiles that are in flight together share operand panels — but only while they read the SAME part of
+// K: left alone, the pairs drift apart over the ~40 tiles each of them processes and the L2 working set grows from
+// (panels in flight) x (a few K blocks) to (panels in flight) x (all of K): ncu measured 383 GB of DRAM reads for the
+// 10 GB operand of C3 (L2 hit rate 51 %, HBM at 69 % of peak while the tensor pipe waits for power).  The leader's
+// producer publishes its global K step every SYNC_PUBLISH blocks; a watcher warp (warp 6 of the leader) keeps
+// min(progress of all pairs) + SYNC_WINDOW in shared memory, and the producer does not issue a load beyond it.  The
+// slowest pair never waits (no deadlock; all CTAs of the grid are co-resident: one per SM), and with a static tile
+// assignment the fast pairs would only have idled at the end anyway.  Measured on C3: 102 ms -> 66 ms.
+constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW = 64;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
-                    int kb_per_slab, EpiParams ep) {
+                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
@@ -246,6 +267,8 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
     uint64_t *tmem_full = empty_bar + STAGES2;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    volatile uint32_t *sync_allowed = tmem_slot + 1;  // highest K step the producer may issue
+    volatile uint32_t *sync_done = tmem_slot + 2;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -266,6 +289,10 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    if (threadIdx.x == 0) {
+        *sync_allowed = SYNC_WINDOW;
+        *sync_done = 0;
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -275,11 +302,19 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, step = 0;
+            const bool throttle = progress != nullptr && leader;
             for (int t = pair; t < num_tiles; t += num_pairs) {
                 const int2 tc = tiles[t];
                 int slab = 0, kin = 0;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = 0; kb < num_kb; ++kb, ++step) {
+                    if (throttle) {
+                        if ((step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
+                        uint32_t spins = 0;
+                        while (step > *sync_allowed) {  // more than SYNC_WINDOW ahead of the slowest pair
+                            if (++spins > (1u << 28)) __trap();  // a pair that never starts: fail, do not hang
+                        }
+                    }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *sA = smem + stage * STAGE2_BYTES;
                     uint8_t *sB = sA + A_BYTES;
@@ -297,6 +332,21 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                         phase ^= 1;
                     }
                 }
+            }
+            if (throttle) {
+                st_relaxed_u32(&progress[pair], 0xffffffffu);  // done: nobody waits for this pair
+                *sync_done = 1;
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== K-window watcher (leader CTA) =====================
+        if (progress != nullptr && leader) {
+            while (*sync_done == 0) {
+                uint32_t mn = 0xffffffffu;
+                for (int i = lane; i < num_pairs; i += 32) mn = min(mn, ld_relaxed_u32(&progress[i]));
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                if (lane == 0) *sync_allowed = (mn > 0xffffffffu - SYNC_WINDOW) ? 0xffffffffu : mn + SYNC_WINDOW;
+                __nanosleep(2000);  // ~8 K blocks: coarse on purpose, 74 watchers poll the same three cache lines
             }
         }
     } else if (warp == 1) {
@@ -451,6 +501,22 @@ int32_t get_tile_list_2cta(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t w
     return GRM_CUDA_OK;
 }
 
+// zeroed progress words for the K-window synchronisation (GRM_CUDA_SYRK_SYNC=0 switches it off, =1 forces it).
+// Drift needs many tiles per pair to build up; for short launches (fewer than 6 tiles per pair) the bookkeeping costs
+// more than it saves (measured on C2: +10 %), so it is left off there.
+int32_t sync_buffer(grm_cuda_ctx *ctx, int pairs, int tiles, uint32_t **out) {
+    const char *e = getenv("GRM_CUDA_SYRK_SYNC");
+    const bool forced = e && e[0] == '1';
+    if ((e && e[0] == '0') || (!forced && tiles < 6 * pairs)) {
+        *out = nullptr;
+        return GRM_CUDA_OK;
+    }
+    GRM_TRY(ctx->progress.reserve(static_cast<size_t>(pairs) * sizeof(uint32_t) + 64));
+    GRM_CUDA_TRY(cudaMemsetAsync(ctx->progress.ptr, 0, static_cast<size_t>(pairs) * sizeof(uint32_t), ctx->stream));
+    *out = ctx->progress.as<uint32_t>();
+    return GRM_CUDA_OK;
+}
+
 bool use_2cta() {
     const char *e = getenv("GRM_CUDA_SYRK_I8");  // read per call so that both variants can be timed in one process
     return !(e && (!strcmp(e, "1cta") || !strcmp(e, "1")));  // default: CTA pairs (measured +18 % on C3)
@@ -481,8 +547,10 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
             attr2_set[EPI] = true;
         }
         const int pairs = std::min(count, ctx->num_sms / 2);
-        syrk_i8_2cta_kernel<EPI><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep);
+        uint32_t *prog = nullptr;
+        GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
+        syrk_i8_2cta_kernel<EPI><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
+            tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         return GRM_CUDA_OK;
@@ -646,8 +714,10 @@ extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_co
                                      ctx->stream));
     const int kbs = static_cast<int>((p + BK - 1) / BK);
     const int pairs = std::min(count, ctx->num_sms / 2);
-    syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), count, kbs, kbs,
-                                                                                 ep);
+    uint32_t *prog = nullptr;
+    GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
+    syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), count, kbs, kbs,
+                                                                                 ep, prog);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
@@ -727,12 +797,14 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
                                               static_cast<int>(SMEM2_BYTES)));
         attr_set[simple ? 0 : 1] = true;
     }
+    uint32_t *prog = nullptr;
+    GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
     if (simple)
-        syrk_i8_2cta_kernel<1><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(tmap, d_tl, count,
-                                                                                     kbs * static_cast<int>(nslabs), kbs, ep);
+        syrk_i8_2cta_kernel<1><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
+            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog);
     else
-        syrk_i8_2cta_kernel<2><<<2 * pairs, NUM_THREADS, SMEM2_BYTES, ctx->stream>>>(tmap, d_tl, count,
-                                                                                     kbs * static_cast<int>(nslabs), kbs, ep);
+        syrk_i8_2cta_kernel<2><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
+            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

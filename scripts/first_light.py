@@ -333,6 +333,40 @@ def stage_repair_ab():
 STAGES["repair_ab"] = stage_repair_ab
 
 
+def stage_syrk_ab():
+    """2-CTA SYRK at C3 scale with and without the K-window synchronisation, alternating in one process."""
+    ctx = grm_b200.default_context(0)
+    n, p = 20000, 500000
+    ldc = D.padded_loci(p)
+    codes = torch.randint(0, 5, (n, ldc), dtype=torch.int8, device=dev)
+    codes[:, p:] = 0
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    ref = None
+    macs = n * n * p / 2
+    for rep in range(3):
+        for var in ("1", "0"):
+            os.environ["GRM_CUDA_SYRK_SYNC"] = var
+            t, ts = ev_time(lambda: D.syrk_i8_f64(ctx, codes, p, 1.0 / 16, 0.0, 0.0, float(p), out=G), ctx, reps=2)
+            ctx.synchronize()
+            chk = float(G.sum())
+            if ref is None:
+                ref = chk
+            print(f"[syrk C3 sync={var}] {t:.2f} ms -> {2*macs/t/1e9:.0f} TOP/s  {['%.2f' % x for x in ts]} same={chk == ref}", flush=True)
+    os.environ.pop("GRM_CUDA_SYRK_SYNC", None)
+    n, p = 5000, 100000
+    codes = torch.randint(0, 3, (n, D.padded_loci(p)), dtype=torch.int8, device=dev)
+    codes[:, p:] = 0
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for var in ("1", "0", "1", "0"):
+        os.environ["GRM_CUDA_SYRK_SYNC"] = var
+        t, ts = ev_time(lambda: D.syrk_i8_f64(ctx, codes, p, 0.25, 0.0, 0.0, float(p), out=G), ctx, reps=3)
+        print(f"[syrk C2 sync={var}] {t:.3f} ms -> {n*n*p/t/1e9:.0f} TOP/s", flush=True)
+    os.environ.pop("GRM_CUDA_SYRK_SYNC", None)
+
+
+STAGES["syrk_ab"] = stage_syrk_ab
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:
