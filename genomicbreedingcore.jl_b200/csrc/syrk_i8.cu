@@ -245,7 +245,7 @@ constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 // min(progress of all pairs) + SYNC_WINDOW in shared memory, and the producer does not issue a load beyond it.  The
 // slowest pair never waits (no deadlock; all CTAs of the grid are co-resident: one per SM), and with a static tile
 // assignment the fast pairs would only have idled at the end anyway.  Measured on C3: 102 ms -> 66 ms.
-constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW = 64;
+constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW_DEFAULT = 64;
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
     uint32_t v;
@@ -259,7 +259,7 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
-                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress) {
+                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_window) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
@@ -290,7 +290,7 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
     }
     if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
     if (threadIdx.x == 0) {
-        *sync_allowed = SYNC_WINDOW;
+        *sync_allowed = sync_window;
         *sync_done = 0;
     }
     tc_fence_before();
@@ -311,7 +311,7 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                     if (throttle) {
                         if ((step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
                         uint32_t spins = 0;
-                        while (step > *sync_allowed) {  // more than SYNC_WINDOW ahead of the slowest pair
+                        while (step > *sync_allowed) {  // more than the window ahead of the slowest pair
                             if (++spins > (1u << 28)) __trap();  // a pair that never starts: fail, do not hang
                         }
                     }
@@ -345,7 +345,7 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                 uint32_t mn = 0xffffffffu;
                 for (int i = lane; i < num_pairs; i += 32) mn = min(mn, ld_relaxed_u32(&progress[i]));
                 mn = __reduce_min_sync(0xffffffffu, mn);
-                if (lane == 0) *sync_allowed = (mn > 0xffffffffu - SYNC_WINDOW) ? 0xffffffffu : mn + SYNC_WINDOW;
+                if (lane == 0) *sync_allowed = (mn > 0xffffffffu - sync_window) ? 0xffffffffu : mn + sync_window;
                 __nanosleep(2000);  // ~8 K blocks: coarse on purpose, 74 watchers poll the same three cache lines
             }
         }
@@ -517,6 +517,12 @@ int32_t sync_buffer(grm_cuda_ctx *ctx, int pairs, int tiles, uint32_t **out) {
     return GRM_CUDA_OK;
 }
 
+uint32_t sync_window() {
+    const char *e = getenv("GRM_CUDA_SYRK_WINDOW");
+    const long v = e ? atol(e) : 0;
+    return v > 0 ? static_cast<uint32_t>(v) : SYNC_WINDOW_DEFAULT;
+}
+
 bool use_2cta() {
     const char *e = getenv("GRM_CUDA_SYRK_I8");  // read per call so that both variants can be timed in one process
     return !(e && (!strcmp(e, "1cta") || !strcmp(e, "1")));  // default: CTA pairs (measured +18 % on C3)
@@ -550,7 +556,7 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
         uint32_t *prog = nullptr;
         GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
         syrk_i8_2cta_kernel<EPI><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog);
+            tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         return GRM_CUDA_OK;
@@ -717,7 +723,7 @@ extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_co
     uint32_t *prog = nullptr;
     GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
     syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), count, kbs, kbs,
-                                                                                 ep, prog);
+                                                                                  ep, prog, sync_window());
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
@@ -801,10 +807,10 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
     GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
     if (simple)
         syrk_i8_2cta_kernel<1><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog);
+            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
     else
         syrk_i8_2cta_kernel<2><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog);
+            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

@@ -367,6 +367,24 @@ def stage_syrk_ab():
 STAGES["syrk_ab"] = stage_syrk_ab
 
 
+def stage_syrk_window():
+    """Sweep of the K-window of the pair synchronisation at C3 scale."""
+    ctx = grm_b200.default_context(0)
+    n, p = 20000, 500000
+    codes = torch.randint(0, 5, (n, D.padded_loci(p)), dtype=torch.int8, device=dev)
+    codes[:, p:] = 0
+    G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for rep in range(2):
+        for w in ("16", "32", "64", "128", "256", "512"):
+            os.environ["GRM_CUDA_SYRK_WINDOW"] = w
+            t, ts = ev_time(lambda: D.syrk_i8_f64(ctx, codes, p, 1.0 / 16, 0.0, 0.0, float(p), out=G), ctx, reps=2)
+            print(f"[syrk C3 window={w}] {t:.2f} ms {['%.2f' % x for x in ts]}", flush=True)
+    os.environ.pop("GRM_CUDA_SYRK_WINDOW", None)
+
+
+STAGES["syrk_window"] = stage_syrk_window
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:
