@@ -88,6 +88,9 @@ SIGNATURES = {
     "grm_cuda_simple": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
     "grm_cuda_ploidyaware": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
     "grm_cuda_inflate_diagonals": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
+    "grm_cuda_repair_probe": (_i32, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(C.c_uint32),
+                                     C.POINTER(_f64)]),
+    "grm_cuda_repair_apply": (_i32, [_vp, _vp, _i64, _i64, _i32, _f64, C.POINTER(_f64)]),
     "grm_cuda_detect_denominator": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
     "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "grm_cuda_locus_qc": (_i32, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),

@@ -74,6 +74,20 @@ __global__ void diag_add_kernel(double *__restrict__ X, int64_t n, int64_t ldx, 
     if (i < n) X[i + i * ldx] = X[i + i * ldx] + eps;
 }
 
+// X[i,i] after `rounds` rounds of the reference's loop: ((x + e_0) + e_1) + ... with e_0 = eps0, e_{t+1} = fl(e_t (1+eps))
+// — the same sequence of roundings as `rounds` calls of diag_add_kernel (calc.jl:63-65)
+__global__ void diag_add_rounds_kernel(double *__restrict__ X, int64_t n, int64_t ldx, double eps0, int rounds) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double d = X[i + i * ldx], e = eps0;
+        for (int t = 0; t < rounds; ++t) {
+            d = __dadd_rn(d, e);
+            e = __dmul_rn(e, 1.0 + DBL_EPSILON);
+        }
+        X[i + i * ldx] = d;
+    }
+}
+
 struct Repair {
     grm_cuda_ctx *ctx;
     cusolverDnHandle_t h;
@@ -84,6 +98,8 @@ struct Repair {
     int lwork_len;
     int *ipiv, *info;
     double *d_diag;
+    int shift_rounds = 0;  // probe mode: factorise X after this many rounds of inflation (X itself untouched)
+    double shift_eps0 = 0.0;
     std::vector<double> h_diag;
     std::vector<int> h_ipiv;
     // 64-bit cuSOLVER API (GRM_CUDA_GETRF=x0|x1): same LAPACK-style partial-pivoting LU, int64 pivots, selectable
@@ -104,6 +120,12 @@ struct Repair {
         copy_matrix_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(X, n, ldx, work_mat);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
+        if (shift_rounds > 0) {
+            diag_add_rounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(work_mat, n, n, shift_eps0,
+                                                                                                shift_rounds);
+            GRM_CUDA_TRY(cudaGetLastError());
+            ctx->launches++;
+        }
         return GRM_CUDA_OK;
     }
 
@@ -171,11 +193,9 @@ int32_t grm_cusolver_destroy(void *h) {
     return GRM_CUDA_OK;
 }
 
-// device-resident implementation; X is a device pointer
-int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
-                          double *eps_total) {
-    *iters = 0;
-    *eps_total = 0.0;
+// cuSOLVER handle, workspaces and the symmetry / NaN / Inf / max|X| scan (h_scan[0] = flags, h_scan[1] = bits of max|X|)
+static int32_t repair_setup(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, Repair &r,
+                            unsigned long long *h_scan) {
     if (n > 46000) {  // 32-bit indexing of the legacy potrf/getrf entry points: n*n must stay below 2^31
         grm_set_error("inflate_diagonals: n=%lld exceeds the single-GPU cuSOLVER range (n <= 46000)", (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -198,15 +218,9 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
     }
-    unsigned long long h_scan[2];
-    GRM_CUDA_TRY(cudaMemcpyAsync(h_scan, d_scan, sizeof(h_scan), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaMemcpyAsync(h_scan, d_scan, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (h_scan[0] & 1ull) {
-        grm_set_error("The input matrix is not symmetric.");
-        return GRM_CUDA_ERR_NOT_SYMMETRIC;
-    }
 
-    Repair r;
     r.ctx = ctx;
     r.h = h;
     r.X = X;
@@ -245,6 +259,22 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
         r.ipiv64 = reinterpret_cast<int64_t *>(static_cast<char *>(ctx->misc2.ptr) + off);
         r.xwork_h.resize(r.xwork_h_bytes + 1);
         r.h_ipiv64.resize(n);
+    }
+
+    return GRM_CUDA_OK;
+}
+
+// device-resident implementation; X is a device pointer
+int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
+                          double *eps_total) {
+    *iters = 0;
+    *eps_total = 0.0;
+    Repair r;
+    unsigned long long h_scan[2];
+    GRM_TRY(repair_setup(ctx, X, n, ldx, r, h_scan));
+    if (h_scan[0] & 1ull) {
+        grm_set_error("The input matrix is not symmetric.");
+        return GRM_CUDA_ERR_NOT_SYMMETRIC;
     }
 
     const double eps = DBL_EPSILON;
@@ -293,5 +323,65 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
     }
     *iters = iter;
     *eps_total = total;
+    return GRM_CUDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU inflatediagonals!: the loop tests of different rounds are independent given max|X| (round t looks at X
+// with its diagonal inflated t times), so with the matrix replicated on every GPU, rank r evaluates round r: the
+// wall time of the repair becomes one LU (+ one Cholesky) instead of rounds + 1 of them.  The arithmetic of each probe
+// is the arithmetic of the sequential loop, so the outcome is identical.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds,
+                                         double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs) {
+    if (!ctx || !dX || n < 1 || ldx < n || rounds < 0 || !det_out || !posdef_out || !scan_flags || !maxabs) {
+        grm_set_error("repair_probe: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    Repair r;
+    unsigned long long h_scan[2];
+    GRM_TRY(repair_setup(ctx, const_cast<double *>(dX), n, ldx, r, h_scan));
+    *scan_flags = static_cast<uint32_t>(h_scan[0]);
+    double mx = 0.0;
+    {
+        const long long bits = static_cast<long long>(h_scan[1]);
+        memcpy(&mx, &bits, sizeof(double));
+    }
+    *maxabs = mx;
+    *det_out = 0.0;
+    *posdef_out = -1;
+    if (h_scan[0] & 1ull) return GRM_CUDA_OK;  // not symmetric: the caller raises before any factorisation (calc.jl:43)
+    r.shift_rounds = rounds;
+    r.shift_eps0 = mx;
+    GRM_TRY(r.det(det_out));
+    if (!(*det_out < DBL_EPSILON)) {  // the reference evaluates isposdef only when det passes (&& / || short-circuit)
+        bool pd = false;
+        GRM_TRY(r.posdef(&pd));
+        *posdef_out = pd ? 1 : 0;
+    }
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t n, int64_t ldx, int32_t rounds,
+                                         double maxabs, double *eps_total) {
+    if (!ctx || !dX || n < 1 || ldx < n || rounds < 0) {
+        grm_set_error("repair_apply: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (rounds > 0) {
+        diag_add_rounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(dX, n, ldx, maxabs, rounds);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (eps_total) {  // calc.jl:64-65 on the host: the same sequence of roundings
+        volatile double e = maxabs, total = 0.0;
+        for (int t = 0; t < rounds; ++t) {
+            total = total + e;
+            e = e * (1.0 + DBL_EPSILON);
+        }
+        *eps_total = total;
+    }
     return GRM_CUDA_OK;
 }

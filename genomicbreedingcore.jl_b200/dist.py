@@ -224,3 +224,77 @@ class ShardedGRM:
             D.scale_mirror(self.ctx, self.G, 1.0)
         self._gathered = True
         return self.G
+
+
+def repair_probe(ctx, G, rounds: int):
+    """(det, posdef, scan_flags, maxabs) of G after `rounds` rounds of inflation; G (device, n x n) is not modified."""
+    import ctypes as C
+
+    from . import device as _D  # noqa: F401  (installs Context.synchronize_with_torch)
+
+    n = G.shape[0]
+    det, pd, fl, mx = C.c_double(0.0), C.c_int32(-1), C.c_uint32(0), C.c_double(0.0)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_repair_probe(ctx.handle, C.c_void_p(G.data_ptr()), n, n, int(rounds), C.byref(det),
+                                             C.byref(pd), C.byref(fl), C.byref(mx)))
+    return det.value, pd.value, fl.value, mx.value
+
+
+def inflatediagonals_parallel(ctx, G, max_iter: int = 1000, group=None, world: Optional[int] = None,
+                              rank: Optional[int] = None, exchange=None):
+    """inflatediagonals!(G) (src/grm/calc.jl:41-70) with the rounds evaluated in parallel: every rank holds the same G
+    and probes round base + rank; the first round whose test passes is applied on every rank.  Identical outcome to
+    the sequential loop (same arithmetic per probe).  Returns (iters, eps_total).  `exchange(list) -> list of lists`
+    replaces the all-gather in single-process tests."""
+    import ctypes as C
+    import math
+
+    torch = _torch()
+    eps = 2.220446049250313e-16
+    if world is None:
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = G.shape[0]
+    base, iters, maxabs = 0, None, 0.0
+    while iters is None:
+        r = base + rank
+        mine = [float("nan"), -1.0, 0.0, 0.0]
+        if r <= max_iter:
+            det, pd, fl, mx = repair_probe(ctx, G, r)
+            mine = [det, float(pd), float(fl), mx]
+        if exchange is not None:
+            allr = exchange(mine)
+        else:
+            import torch.distributed as dist
+
+            t = torch.tensor(mine, dtype=torch.float64, device=G.device)
+            out = torch.empty((world, 4), dtype=torch.float64, device=G.device)
+            dist.all_gather_into_tensor(out.view(-1), t, group=group)
+            allr = out.cpu().tolist()
+        if base == 0:
+            det0, pd0, fl0, maxabs = allr[0]
+            flags = int(fl0)
+            if flags & 1:
+                raise _lib.GrmCudaError(_lib.ERR_NOT_SYMMETRIC, "The input matrix is not symmetric.")  # calc.jl:43-45
+            if det0 > eps and pd0 == 1.0:
+                return 0, 0.0  # calc.jl:49-51
+            if flags & 2:
+                raise _lib.GrmCudaError(_lib.ERR_NAN_MATRIX, "The input matrix contains NaN values.")
+            if flags & 4:
+                raise _lib.GrmCudaError(_lib.ERR_INF_MATRIX, "The input matrix contains Inf values.")
+        for k, (det, pd, _fl, _mx) in enumerate(allr):
+            t_round = base + k
+            need = (det < eps) or (pd != 1.0)  # calc.jl:61 (NaN det compares false, then isposdef decides)
+            if (not need) or t_round >= max_iter:
+                iters = t_round
+                break
+        base += world
+    tot = C.c_double(0.0)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_repair_apply(ctx.handle, C.c_void_p(G.data_ptr()), n, n, int(iters), float(maxabs),
+                                             C.byref(tot)))
+    from . import device as _D  # noqa: F401  (installs Context.order_torch_after)
+
+    ctx.order_torch_after()
+    return iters, tot.value

@@ -139,6 +139,19 @@ int32_t grm_cuda_ploidyaware(grm_cuda_ctx *ctx, const double *A, int64_t n, int6
 int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
                                    int32_t location, int32_t *iters, double *eps_total);
 
+/* Multi-GPU inflatediagonals! (calc.jl:41-70).  Given max|X|, the loop test of round t only looks at X with its
+ * diagonal inflated t times, so with X replicated on every GPU rank r can evaluate round r while the others evaluate
+ * theirs: one LU (+ Cholesky) of wall time instead of rounds + 1.  Each probe performs the arithmetic of the sequential
+ * loop, hence the same outcome.
+ *   grm_cuda_repair_probe: X untouched.  scan_flags: bit0 not symmetric, bit1 NaN, bit2 Inf; maxabs = max|X| (the
+ *     first epsilon); det_out = det(X after `rounds` rounds); posdef_out = isposdef of the same matrix, evaluated only
+ *     when !(det < eps) as in the reference's short-circuit (-1 = not evaluated).
+ *   grm_cuda_repair_apply: performs `rounds` rounds of X[diag] .+= eps_t on X and returns their total. */
+int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds,
+                              double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs);
+int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t n, int64_t ldx, int32_t rounds, double maxabs,
+                              double *eps_total);
+
 /* ---- staged device-side API (all pointers are DEVICE pointers; work is enqueued on the context stream) ------
  * These are the pieces the three entry points are assembled from.  They exist so that parity tests can look at
  * intermediate results (integer Gram matrix, q, d) and so that a multi-GPU host (one process per GPU) can put its

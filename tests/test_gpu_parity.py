@@ -556,6 +556,39 @@ def test_sharded_output_tiles_match_dense_result(ctx, world):
     assert seen == 15  # 5 x 5 tiles, upper triangle
 
 
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_parallel_repair_equals_sequential_loop(ctx, world):
+    """Multi-GPU inflatediagonals!: rounds probed in parallel (ranks emulated one after another on one GPU) must give
+    the sequential loop's rounds, total and matrix, bit for bit — including the det-underflow / early-return cases."""
+    import torch
+
+    from grm_b200 import device as D, dist as GD  # noqa: F401
+
+    cases = []
+    for gen, n, p, ploidy in (("dosage", 300, 2000, None), ("continuous", 300, 2000, 2), ("dosage", 600, 3000, 2)):
+        A = synth.dosage(n, p, 2, seed=7) if gen == "dosage" else synth.continuous(n, p, seed=7)
+        cases.append(grm_call(A, ploidy, skip_repair=True)[0])
+    cases.append(np.asfortranarray(np.eye(400) * 0.5))   # SPD but det underflows: one round
+    cases.append(np.asfortranarray(np.eye(400) * 1e3))   # det overflows to Inf: untouched
+    cases.append(np.asfortranarray(-np.eye(4)))
+    for X in cases:
+        st, Xs, it, tot = O.np_inflatediagonals(X)
+        Xd0 = torch.from_numpy(np.ascontiguousarray(X)).to(dev())  # stays untouched: what every rank holds
+        calls = {"base": 0}
+
+        def exchange(mine):
+            # the emulated all-gather: the probes of all ranks of this batch, evaluated one after another
+            out = [list(map(float, GD.repair_probe(ctx, Xd0, calls["base"] + rk))) for rk in range(world)]
+            calls["base"] += world
+            return out
+
+        Xw = Xd0.clone()
+        it2, tot2 = GD.inflatediagonals_parallel(ctx, Xw, 1000, world=world, rank=0, exchange=exchange)
+        ctx.synchronize()
+        assert (it2, tot2) == (it, tot)
+        assert np.array_equal(Xw.cpu().numpy(), Xs)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size (BASELINE C2) properties: a checksum of checksums for the integer Gram matrix
 #   sum_j C_ij = sum_k c_ik S_k ,  C_ii = sum_k c_ik^2 ,  sum_ij C_ij = sum_k S_k^2      (S_k = column sums)
