@@ -502,12 +502,13 @@ int32_t get_tile_list_2cta(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t w
 }
 
 // zeroed progress words for the K-window synchronisation (GRM_CUDA_SYRK_SYNC=0 switches it off, =1 forces it).
-// Drift needs many tiles per pair to build up; for short launches (fewer than 6 tiles per pair) the bookkeeping costs
-// more than it saves (measured on C2: +10 %), so it is left off there.
-int32_t sync_buffer(grm_cuda_ctx *ctx, int pairs, int tiles, uint32_t **out) {
+// It pays when drift can build up AND the operand is far larger than L2: many tiles per pair and a multi-GB operand
+// (C3 on one GPU: 10 GB, 43 tiles per pair: 73 -> 54 ms).  Measured neutral at 5 GB (C3 on 2 GPUs) and a loss for
+// short launches (C2: +5 %; C3 on 4 / 8 GPUs, 2.5 / 1.25 GB per GPU: +11 %), so it is enabled from 6 GB up.
+int32_t sync_buffer(grm_cuda_ctx *ctx, int pairs, int tiles, int64_t operand_bytes, uint32_t **out) {
     const char *e = getenv("GRM_CUDA_SYRK_SYNC");
     const bool forced = e && e[0] == '1';
-    if ((e && e[0] == '0') || (!forced && tiles < 6 * pairs)) {
+    if ((e && e[0] == '0') || (!forced && (tiles < 6 * pairs || operand_bytes < (6ll << 30)))) {
         *out = nullptr;
         return GRM_CUDA_OK;
     }
@@ -554,7 +555,7 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
         }
         const int pairs = std::min(count, ctx->num_sms / 2);
         uint32_t *prog = nullptr;
-        GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
+        GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc * nslabs, &prog));
         syrk_i8_2cta_kernel<EPI><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
             tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
         GRM_CUDA_TRY(cudaGetLastError());
@@ -721,7 +722,7 @@ extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_co
     const int kbs = static_cast<int>((p + BK - 1) / BK);
     const int pairs = std::min(count, ctx->num_sms / 2);
     uint32_t *prog = nullptr;
-    GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
+    GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc, &prog));
     syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), count, kbs, kbs,
                                                                                   ep, prog, sync_window());
     GRM_CUDA_TRY(cudaGetLastError());
@@ -804,7 +805,7 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
         attr_set[simple ? 0 : 1] = true;
     }
     uint32_t *prog = nullptr;
-    GRM_TRY(sync_buffer(ctx, pairs, count, &prog));
+    GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc * nslabs, &prog));
     if (simple)
         syrk_i8_2cta_kernel<1><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
             tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
