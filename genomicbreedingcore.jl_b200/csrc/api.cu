@@ -138,9 +138,17 @@ extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) {
     if (!ctx) return GRM_CUDA_ERR_OOM;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    GRM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // the compute stream outranks the auxiliary one: when a persistent SYRK and a pack kernel are both runnable
+    // (pipelined flow, run_grm) the SYRK CTAs are placed first and the pack fills what is left of each SM
+    int prio_least = 0, prio_greatest = 0;
+    GRM_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    GRM_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
     GRM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    GRM_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_least));
     for (auto &ev : ctx->ev) GRM_CUDA_TRY(cudaEventCreate(&ev));
+    for (int i = 0; i < 40; ++i)
+        GRM_CUDA_TRY(i < 16 ? cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming)
+                            : cudaEventCreate(&ctx->pipe_ev[i]));
     for (int i = 0; i < 2; ++i) {
         GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
         GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming));
@@ -159,15 +167,17 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
                       &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->lu, &ctx->lu_work, &ctx->ipiv, &ctx->misc,
                       &ctx->tiles_i8.buf, &ctx->tiles_i8_2cta.buf, &ctx->tiles_f64.buf, &ctx->tiles_packed.buf, &ctx->planes,
-                      &ctx->rT, &ctx->cnt, &ctx->keep, &ctx->misc2, &ctx->progress};
+                      &ctx->rT, &ctx->cnt, &ctx->keep, &ctx->misc2, &ctx->progress, &ctx->acc};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->pipe_ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(ctx->copy_done[i]);
         cudaEventDestroy(ctx->stage_free[i]);
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return GRM_CUDA_OK;
 }
@@ -178,6 +188,7 @@ extern "C" int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx) {
     if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->aux_stream));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return GRM_CUDA_OK;
 }
@@ -344,6 +355,22 @@ int32_t flags_to_status(uint32_t f) {
     return GRM_CUDA_OK;
 }
 
+// launches of the staged entry points go to ctx->stream; the pipelined flow redirects some of them to the auxiliary
+// stream for the lifetime of this guard
+struct StreamSwap {
+    grm_cuda_ctx *ctx;
+    cudaStream_t saved;
+    bool saved_small;
+    StreamSwap(grm_cuda_ctx *c, cudaStream_t s, bool small_pack) : ctx(c), saved(c->stream), saved_small(c->pack_small_footprint) {
+        ctx->stream = s;
+        ctx->pack_small_footprint = small_pack;
+    }
+    ~StreamSwap() {
+        ctx->stream = saved;
+        ctx->pack_small_footprint = saved_small;
+    }
+};
+
 int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda, bool centred, int32_t ploidy,
                 double *G, int64_t ldg, const grm_cuda_options *uopts, grm_cuda_info *info) {
     Timer wall;
@@ -439,6 +466,17 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
         }
     }
 
+    // pipelined int8 flow, opt-in (GRM_CUDA_PIPELINE = number of loci chunks, 2..8) for device-resident, unmasked,
+    // single-GPU calls.  Off by default: measured on C3 it is bit-identical and 2.7 % faster in short bursts (71.1 vs
+    // 73.1 ms) but 3 % slower in a sustained, power-capped loop (76.1 vs 73.8 ms) — a pack CTA sharing an SM with a
+    // persistent SYRK CTA runs at 1/3 of its stand-alone rate (the MMA operand reads own the shared-memory / L1 data
+    // path), so 3/4 of the pack ends up on the critical path anyway (profiles/README.md).
+    int pipe_chunks = 1, pipelined_done = 0;
+    if (!in_host && !masked && !meanfill && !sharded && grm_syrk_i8_pairs() && p >= 8 * 128) {
+        const char *e = getenv("GRM_CUDA_PIPELINE");
+        pipe_chunks = e ? std::max(1, std::min(atoi(e), 8)) : 1;
+    }
+
     double denom = 0.0;
     bool done = false;
     while (!done) {
@@ -454,6 +492,90 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
             int32_t *d_colsum = ctx->colsum.as<int32_t>();
             GRM_CUDA_TRY(cudaMemsetAsync(d_colsum, 0, static_cast<size_t>(ldc) * sizeof(int32_t), st));
             if (masked) GRM_CUDA_TRY(cudaMemsetAsync(d_kept, 0, sizeof(uint64_t), st));
+            if (pipe_chunks > 1) {
+                // ---- pipelined flow (device-resident input): the loci are cut into chunks; the pack of chunk c + 1
+                // (and, at the end, the integer statistics) runs on the low-priority auxiliary stream while the
+                // tensor cores contract chunk c.  Partial sums live as packed int32 tiles; the last chunk's launch adds
+                // them in its fused FP64 epilogue, so G is still written once.  Same integers, same epilogue
+                // arithmetic: bit-identical to the serial flow.
+                const int nk = pipe_chunks;
+                cudaStream_t aux = ctx->aux_stream;
+                cudaEvent_t *pe = ctx->pipe_ev;
+                GRM_TRY(ctx->acc.reserve(static_cast<size_t>(grm_syrk_i8_partial_bytes(n))));
+                int32_t *d_acc = ctx->acc.as<int32_t>();
+                GRM_CUDA_TRY(cudaEventRecord(pe[15], st));
+                GRM_CUDA_TRY(cudaStreamWaitEvent(aux, pe[15], 0));
+                auto cut = [&](int c) { return c >= nk ? p : (p * c / nk) / 128 * 128; };
+                int32_t rc = GRM_CUDA_OK;
+                for (int c = 0; c < nk && rc == GRM_CUDA_OK; ++c) {
+                    const int64_t k0 = cut(c), len = cut(c + 1) - k0;
+                    {
+                        StreamSwap on_aux(ctx, aux, /*small footprint pack*/ c > 0);
+                        if (c == 0) GRM_CUDA_TRY(cudaEventRecord(pe[32], aux));
+                        rc = grm_cuda_pack_dosage(ctx, A + k0 * lda, n, len, lda, m, d_codes + k0, ldc, d_colsum + k0,
+                                                  d_flags, nullptr);
+                        if (rc != GRM_CUDA_OK) break;
+                        GRM_CUDA_TRY(cudaEventRecord(pe[c], aux));
+                        if (c == nk - 1) GRM_CUDA_TRY(cudaEventRecord(pe[33], aux));
+                    }
+                    if (c < nk - 1) {
+                        GRM_CUDA_TRY(cudaStreamWaitEvent(st, pe[c], 0));
+                        GRM_CUDA_TRY(cudaEventRecord(pe[16 + 2 * c], st));
+                        rc = grm_syrk_i8_partial(ctx, d_codes + k0, n, len, ldc, d_acc, c > 0);
+                        GRM_CUDA_TRY(cudaEventRecord(pe[17 + 2 * c], st));
+                    }
+                }
+                uint32_t h_flags = 0;
+                double sc[4] = {1.0 / (static_cast<double>(m) * m), 0.0, 0.0, static_cast<double>(p)};
+                if (rc == GRM_CUDA_OK) {
+                    StreamSwap on_aux(ctx, aux, false);
+                    GRM_CUDA_TRY(cudaMemcpyAsync(&h_flags, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, aux));
+                    GRM_CUDA_TRY(cudaEventRecord(pe[34], aux));
+                    if (centred) {
+                        // exact integer statistics -> u, W2, d, hidden under the SYRK of chunk nk - 2
+                        rc = ctx->u.reserve(static_cast<size_t>(n) * sizeof(double));
+                        if (rc == GRM_CUDA_OK) rc = ctx->rT.reserve(static_cast<size_t>(2 * n + 2) * sizeof(int64_t));
+                        uint64_t *d_sums = ctx->rT.as<uint64_t>();
+                        int64_t *d_r = ctx->rT.as<int64_t>() + 2, *d_T = d_r + n;
+                        if (rc == GRM_CUDA_OK)
+                            rc = grm_cuda_dosage_stats(ctx, d_codes, n, p, ldc, d_colsum, m, d_sums, d_r, d_T, 0);
+                        if (rc == GRM_CUDA_OK)
+                            rc = grm_cuda_dosage_centre(ctx, d_sums, d_r, d_T, n, p, m, ploidy, ctx->u.as<double>(), sc);
+                    }
+                    GRM_CUDA_TRY(cudaEventRecord(pe[35], aux));
+                    GRM_CUDA_TRY(cudaStreamSynchronize(aux));
+                }
+                if (rc == GRM_CUDA_OK) rc = flags_to_status(h_flags);
+                if (rc != GRM_CUDA_OK) {
+                    cudaStreamSynchronize(aux);
+                    cudaStreamSynchronize(st);
+                    return rc;
+                }
+                if (h_flags & 4u) {
+                    // a later locus broke the denominator guessed from the sample: same policy as the serial flow
+                    if (o.path == GRM_CUDA_PATH_I8 || o.denominator != 0) {
+                        cudaStreamSynchronize(st);
+                        grm_set_error("allele frequencies are not all multiples of 1/%d", m);
+                        return GRM_CUDA_ERR_NOT_DOSAGE;
+                    }
+                    if (m < 64) m = 64; else path = GRM_CUDA_PATH_F64;
+                    GRM_CUDA_TRY(cudaMemsetAsync(d_flags, 0, 16 * sizeof(uint32_t), st));
+                    continue;
+                }
+                denom = sc[3];  // calc.jl:127 / :201
+                const int64_t k0 = cut(nk - 1), len = p - k0;
+                GRM_CUDA_TRY(cudaEventRecord(ev[1], st));
+                GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
+                GRM_CUDA_TRY(cudaEventRecord(pe[16 + 2 * (nk - 1)], st));
+                GRM_TRY(grm_syrk_i8_f64_prev(ctx, d_codes + k0, n, len, ldc, 1, sc[0], sc[1], sc[2], denom,
+                                             centred ? ctx->u.as<double>() : nullptr, dG, ldG, 0, 1, d_acc));
+                GRM_CUDA_TRY(cudaEventRecord(pe[17 + 2 * (nk - 1)], st));
+                GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
+                GRM_TRY(grm_cuda_scale_mirror(ctx, dG, n, ldG, 1.0));
+                pipelined_done = nk;
+                done = true;
+                continue;
+            }
             for (int64_t c = 0; c < feed.nchunks; ++c) {
                 const double *dc;
                 GRM_TRY(feed.acquire(c, &dc));
@@ -649,6 +771,18 @@ int32_t run_grm(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_
     cudaEventElapsedTime(&inf.ms_pack, ev[0], ev[1]);
     cudaEventElapsedTime(&inf.ms_rowdot, ev[1], ev[2]);
     cudaEventElapsedTime(&inf.ms_syrk, ev[2], ev[3]);
+    if (pipelined_done > 0) {
+        // overlapping stages: each is timed on its own stream (pack and statistics on the auxiliary stream, the SYRK
+        // launches on the compute stream), so the stage times sum to more than the call
+        cudaEventElapsedTime(&inf.ms_pack, ctx->pipe_ev[32], ctx->pipe_ev[33]);
+        cudaEventElapsedTime(&inf.ms_rowdot, ctx->pipe_ev[34], ctx->pipe_ev[35]);
+        inf.ms_syrk = 0.f;
+        for (int c = 0; c < pipelined_done; ++c) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ctx->pipe_ev[16 + 2 * c], ctx->pipe_ev[17 + 2 * c]);
+            inf.ms_syrk += t;
+        }
+    }
     cudaEventElapsedTime(&inf.ms_finalize, ev[3], ev[4]);
     cudaEventElapsedTime(&inf.ms_repair, ev[4], ev[5]);
     if (out_host) cudaEventElapsedTime(&inf.ms_d2h, ev[7], ev[8]);

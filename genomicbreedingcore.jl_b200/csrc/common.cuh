@@ -51,11 +51,14 @@ struct grm_cuda_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // lower priority than `stream`: the pack / statistics side of the pipelined flow
+    bool pack_small_footprint = false;  // pack with the register-staged variant (co-resides with a persistent SYRK CTA)
     cudaEvent_t ev[16] = {};
+    cudaEvent_t pipe_ev[40] = {};       // pipelined flow: [0..15] chunk packed, [16..39] SYRK launch begin / end
     cudaEvent_t copy_done[2] = {}, stage_free[2] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
-    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt, keep, progress;
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt, keep, progress, acc;
     TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed;
     int32_t launches = 0;  // kernels launched since last reset
 };
@@ -70,6 +73,15 @@ typedef CUresult (*GrmEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint3
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int32_t grm_tmap_encoder(GrmEncodeTiledFn *fn);
+
+// pipelined single-GPU int8 flow (syrk_i8.cu): partial sums per loci chunk, then the fused FP64 epilogue on the last one
+int64_t grm_syrk_i8_partial_bytes(int64_t n);
+int32_t grm_syrk_i8_partial(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t *d_acc,
+                            int accumulate);
+int32_t grm_syrk_i8_f64_prev(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs,
+                             double alpha, double beta, double gamma, double denom, const double *d_u, double *d_G,
+                             int64_t ldg, int32_t rank, int32_t world, const int32_t *d_prev);
+bool grm_syrk_i8_pairs();  // CTA-pair kernel selected (the default)
 
 // kernels' host launchers (implemented across the .cu files)
 int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,

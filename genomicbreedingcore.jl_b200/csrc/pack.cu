@@ -630,7 +630,7 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     const char *pack_env = getenv("GRM_CUDA_PACK");  // "ldg" forces the non-TMA variant (read per call: A/B timing)
-    const bool use_tma = !(pack_env && !strcmp(pack_env, "ldg"));
+    const bool use_tma = !(pack_env && !strcmp(pack_env, "ldg")) && !ctx->pack_small_footprint;
     if (use_tma && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(dA) % 16) == 0 && n < (1ll << 31) && pc < (1ll << 31)) {
         // TMA-staged variant: needs 16-byte aligned rows of A (global strides are multiples of 16 bytes)
         GrmEncodeTiledFn encode = nullptr;
@@ -671,12 +671,18 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
     constexpr int EITERS = 4;
     dim3 grid(static_cast<unsigned>((pc + PK_LOCI - 1) / PK_LOCI),
               static_cast<unsigned>((n + PK_SLAB * EITERS - 1) / (PK_SLAB * EITERS)));
+    // experiment knob: unused dynamic shared memory (KB) to cap the CTAs resident per SM
+    const char *pad_env = getenv("GRM_CUDA_PACK_PAD");
+    const size_t pad = pad_env ? static_cast<size_t>(atol(pad_env)) << 10 : 0;
+    if (pad > 0)
+        GRM_CUDA_TRY(cudaFuncSetAttribute(pack_dosage_kernel<EITERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(pad)));
     if (d_keep)
         pack_dosage_kernel<EITERS, true><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
                                                                         d_flags, d_keep);
     else
-        pack_dosage_kernel<EITERS, false><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
-                                                                         d_flags, nullptr);
+        pack_dosage_kernel<EITERS, false><<<grid, 256, pad, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
+                                                                           d_flags, nullptr);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

@@ -46,6 +46,8 @@ struct EpiParams {
     const int32_t *slots;  // mode 3: slot of tile t in the packed int32 tile buffer C ([slot][256 cols][256 rows])
     double *Gt;            // modes 1, 2 (2-CTA kernel): if set, tile t is stored packed at Gt + t*65536 ([col][row],
                            // zeros outside n) instead of into the dense matrix G: the sharded-output form
+    const int32_t *prev;   // 2-CTA kernel, modes 1-3: if set, packed int32 tiles ([slot][col][row]) holding the partial
+                           // sums of earlier loci chunks; added to the accumulator before the mode's own epilogue
 };
 
 // Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
@@ -394,15 +396,29 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             const bool row_ok = row < ep.n;
             double ui = 0.0;
             if (EPI == 2 && row_ok) ui = ep.u[row];
+            const int64_t slot = ep.slots ? static_cast<int64_t>(ep.slots[t]) : static_cast<int64_t>(t);
             int32_t *packed = nullptr;
-            if (EPI == 3) packed = ep.C + static_cast<int64_t>(ep.slots[t]) * 65536;
+            if (EPI == 3) packed = ep.C + slot * 65536;
+            const int row_local = 128 * static_cast<int>(cta) + quarter * 32 + lane;
+            const int32_t *prev = (EPI != 0 && ep.prev) ? ep.prev + slot * 65536 + row_local : nullptr;
 #pragma unroll 1
             for (int c0 = 0; c0 < 256; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
-                tmem_wait_ld();
+                if (prev) {
+                    // partial sums of the earlier loci chunks: issue the (coalesced) loads before waiting on TMEM
+                    int32_t pv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pv[j] = prev[(c0 + j) * 256];
+                    tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] += static_cast<uint32_t>(pv[j]);
+                } else {
+                    tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+                    tmem_wait_ld();
+                }
                 if (EPI == 3) {
-                    epilogue_store_packed(r, packed, 128 * static_cast<int>(cta) + quarter * 32 + lane, c0);
+                    epilogue_store_packed(r, packed, row_local, c0);
                 } else if ((EPI == 1 || EPI == 2) && ep.Gt != nullptr) {
                     // sharded output: the same arithmetic, addressed tile-locally (leading dimension 256)
                     EpiParams lt = ep;
@@ -596,10 +612,13 @@ extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, in
     return launch<0>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
 }
 
-extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                        int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
-                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) {
-    if (!d_G || ldg < n || (beta != 0.0 && !d_u)) {
+bool grm_syrk_i8_pairs() { return use_2cta(); }
+
+// d_prev: packed int32 tiles of earlier loci chunks (grm_syrk_i8_partial), added before the FP64 epilogue; or null
+int32_t grm_syrk_i8_f64_prev(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs,
+                             double alpha, double beta, double gamma, double denom, const double *d_u, double *d_G,
+                             int64_t ldg, int32_t rank, int32_t world, const int32_t *d_prev) {
+    if (!d_G || ldg < n || (beta != 0.0 && !d_u) || (d_prev && !(use_2cta() && world == 1))) {
         grm_set_error("syrk_i8_f64: bad output or missing u (ldg=%lld n=%lld)", (long long)ldg, (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
@@ -619,8 +638,56 @@ extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes
         ep.rcp = (a > 1e-200 && a < 1e200 && !(no_fast && no_fast[0] == '1')) ? 1.0 / denom : 0.0;
     }
     ep.u = d_u;
+    ep.prev = d_prev;
     if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
     return launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
+}
+
+extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                        int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
+                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+    return grm_syrk_i8_f64_prev(ctx, d_codes, n, p, ldc, nslabs, alpha, beta, gamma, denom, d_u, d_G, ldg, rank, world,
+                                nullptr);
+}
+
+// One loci chunk of the pipelined single-GPU flow (api.cu): raw int32 partial sums of ALL upper-triangular tiles, packed
+// [tile t of the (rank 0, world 1) tile list][col][row]; `accumulate` adds to what d_acc already holds.
+int64_t grm_syrk_i8_partial_bytes(int64_t n) {
+    const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
+    return T * (T + 1) / 2 * 65536 * static_cast<int64_t>(sizeof(int32_t));
+}
+
+int32_t grm_syrk_i8_partial(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t *d_acc,
+                            int accumulate) {
+    if (!ctx || !d_codes || !d_acc || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0) {
+        grm_set_error("syrk_i8_partial: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    CUtensorMap tmap;
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, 1, &tmap));
+    const int2 *d_tiles;
+    int count;
+    GRM_TRY(get_tile_list_2cta(ctx, n, 0, 1, &d_tiles, &count));
+    EpiParams ep{};
+    ep.n = n;
+    ep.C = d_acc;
+    ep.prev = accumulate ? d_acc : nullptr;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(SMEM2_BYTES)));
+        attr_set = true;
+    }
+    const int kbs = static_cast<int>((p + BK - 1) / BK);
+    const int pairs = std::min(count, ctx->num_sms / 2);
+    uint32_t *prog = nullptr;
+    GRM_TRY(sync_buffer(ctx, pairs, count, n * p, &prog));
+    syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(tmap, d_tiles, count, kbs, kbs, ep, prog,
+                                                                                  sync_window());
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

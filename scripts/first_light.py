@@ -385,6 +385,55 @@ def stage_syrk_window():
 STAGES["syrk_window"] = stage_syrk_window
 
 
+def stage_pipeline_ab():
+    """C3 step (device-resident input) with the serial flow and the pipelined flow at several chunk counts."""
+    from grm_b200 import synth
+    ctx = grm_b200.default_context(0)
+    n, p, ploidy = 20000, 500000, 4
+    A = torch.empty((p, n), dtype=torch.float64, device=dev)
+    for c0 in range(0, p, 2500):
+        A[c0:c0 + 2500] = synth.dosage_device(n, 2500, ploidy, 1000 + c0 // 2500, dev, chunk=2500)
+    G = torch.empty((n, n), dtype=torch.float64, device=dev)
+    ref = None
+    for rep in range(2):
+        for ch in ("1", "2", "3", "4", "6", "8"):
+            os.environ["GRM_CUDA_PIPELINE"] = ch
+            infos = []
+            t, ts = ev_time(lambda: infos.append(D.grm_device(ctx, A, ploidy, denominator=ploidy, skip_repair=True, out=G)[1]),
+                            ctx, reps=3)
+            i = infos[-1]
+            if ref is None:
+                ref = G.clone()
+            same = bool(torch.equal(ref, G))
+            print(f"[C3 pipeline chunks={ch}] {t:.2f} ms {['%.2f' % x for x in ts]} pack {i['ms_pack']:.2f} stats "
+                  f"{i['ms_rowdot']:.2f} syrk {i['ms_syrk']:.2f} launches {i['kernel_launches']} identical={same}", flush=True)
+    os.environ.pop("GRM_CUDA_PIPELINE", None)
+
+
+STAGES["pipeline_ab"] = stage_pipeline_ab
+
+
+def stage_pack_occ():
+    """LDG pack kernel at 2 CTAs/SM (default) and capped to 1 CTA/SM by padding shared memory: is the co-resident
+    pack of the pipelined flow limited by occupancy or by contention with the SYRK?"""
+    ctx = grm_b200.default_context(0)
+    n, p, m = 20000, 200000, 4
+    At = synth.dosage_device(n, p, m, 9, dev)
+    torch.cuda.synchronize()
+    codes, colsum, flags = D.pack_dosage(ctx, At, m)
+    os.environ["GRM_CUDA_PACK"] = "ldg"
+    for rep in range(2):
+        for pad in ("0", "120"):
+            os.environ["GRM_CUDA_PACK_PAD"] = pad
+            t, ts = ev_time(lambda: D.pack_dosage(ctx, At, m, codes=codes, colsum=colsum, flags=flags), ctx, reps=3)
+            print(f"[pack ldg pad={pad} KB] {t:.3f} ms -> {9*n*p/t/1e6:.0f} GB/s r+w {['%.3f' % x for x in ts]}", flush=True)
+    os.environ.pop("GRM_CUDA_PACK", None)
+    os.environ.pop("GRM_CUDA_PACK_PAD", None)
+
+
+STAGES["pack_occ"] = stage_pack_occ
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:

@@ -626,3 +626,44 @@ def test_full_size_c2_integer_properties(ctx):
     assert torch.equal(G, G.T)
     sub = Cfull[:64, :64].cpu().numpy().astype(np.float64)
     assert np.array_equal(G[:64, :64].cpu().numpy(), (sub / (m * m)) / p)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pipelined flow (pack of chunk c+1 and the integer statistics overlap the SYRK of chunk c): bit-identical to the
+# serial flow for any number of chunks, ragged sizes included
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p,m,ploidy", [(300, 4000, 2, None), (257, 3001, 4, 4), (1000, 20_000, 2, 2),
+                                          (513, 1024, 4, None)])
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+def test_pipelined_flow_is_bit_identical_to_serial(ctx, monkeypatch, n, p, m, ploidy, chunks):
+    import torch
+
+    from grm_b200 import device as D
+
+    At = synth.dosage_device(n, p, m, 11 + chunks, dev())
+    torch.cuda.synchronize()
+    monkeypatch.setenv("GRM_CUDA_PIPELINE", "1")
+    G0, i0 = D.grm_device(ctx, At, ploidy, skip_repair=True)
+    G0 = G0.clone()
+    monkeypatch.setenv("GRM_CUDA_PIPELINE", str(chunks))
+    G1, i1 = D.grm_device(ctx, At, ploidy, skip_repair=True)
+    ctx.synchronize()
+    assert i0["path"] == _lib.PATH_I8 and i1["path"] == _lib.PATH_I8
+    assert i1["kernel_launches"] > i0["kernel_launches"]  # the chunked SYRK launches really ran
+    assert torch.equal(G0, G1)
+    assert i0["scale"] == i1["scale"]
+    # errors surface the same way: a NaN in the last chunk
+    Ab = At.clone()
+    Ab[p - 1, n - 1] = float("nan")
+    with pytest.raises(_lib.GrmCudaError) as ei:
+        D.grm_device(ctx, Ab, ploidy, skip_repair=True)
+    assert ei.value.status == _lib.ERR_MISSING
+    # a non-dosage value in a late chunk: the sample-based guess is retried / falls back exactly as in the serial flow
+    Ac = At.clone()
+    Ac[p - 1, 0] = 0.3
+    G2, i2 = D.grm_device(ctx, Ac, ploidy, skip_repair=True)
+    G2 = G2.clone()
+    monkeypatch.setenv("GRM_CUDA_PIPELINE", "1")
+    G3, i3 = D.grm_device(ctx, Ac, ploidy, skip_repair=True)
+    assert i2["path"] == i3["path"] == _lib.PATH_F64
+    assert torch.equal(G2, G3)
