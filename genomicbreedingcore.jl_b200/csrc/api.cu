@@ -58,6 +58,7 @@ extern "C" const char *grm_cuda_status_string(int32_t s) {
         case GRM_CUDA_ERR_NOT_DOSAGE: return "input is not dosage-quantised";
         case GRM_CUDA_ERR_OVERFLOW: return "int32 accumulator overflow";
         case GRM_CUDA_ERR_ALL_FILTERED: return "All loci filtered out";
+        case GRM_CUDA_ERR_NOT_POSDEF: return "matrix is not positive definite";
         default: return "unknown status";
     }
 }

@@ -207,6 +207,7 @@ static int32_t repair_setup(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx
     }
     cusolverDnHandle_t h = static_cast<cusolverDnHandle_t>(ctx->cusolver);
     GRM_SOLVER_TRY(cusolverDnSetStream(h, ctx->stream));
+    ctx->factor_n = -1;  // the work matrix is about to be overwritten
 
     // calc.jl:43-48 — symmetry (squareness is implied by the C signature), plus the NaN/Inf/max|X| scan
     GRM_TRY(ctx->misc.reserve(64));
@@ -284,7 +285,10 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
     if (det0 > eps) {
         bool pd = false;
         GRM_TRY(r.posdef(&pd));
-        if (pd) return GRM_CUDA_OK;
+        if (pd) {
+            ctx->factor_n = n;  // the work matrix now holds chol(X).U (grm_cuda_last_factor)
+            return GRM_CUDA_OK;
+        }
     }
     // calc.jl:52-57
     if (h_scan[0] & 2ull) {
@@ -311,6 +315,7 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
             bool pd = false;
             GRM_TRY(r.posdef(&pd));
             need = !pd;
+            if (pd) ctx->factor_n = n;  // last factorisation = Cholesky of the matrix being returned
         }
         if (!need || iter >= max_iter) break;
         ++iter;
@@ -384,4 +389,106 @@ extern "C" int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t 
         *eps_total = total;
     }
     return GRM_CUDA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Consumer side of the GRM: simulateeffects builds MvNormal(mu, Sigma) from
+// simulatecovariancekinship's matrix (src/simulations/simulate_effects.jl:344-351, :479-481), i.e. PDMat(Sigma) ->
+// cholesky(Sigma) = LAPACK potrf!('U', copy(Sigma)).  The repair above ends with exactly that factorisation of the
+// matrix it returns, so the factor can be handed out instead of being recomputed (1/3 n^3 flop saved).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+// U[i,j] = F[i,j] for i <= j, 0 below the diagonal (potrf leaves the other triangle of its input untouched)
+__global__ void triu_copy_kernel(const double *__restrict__ F, int64_t n, double *__restrict__ U, int64_t ldu) {
+    const int64_t j = blockIdx.y;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        U[i + j * ldu] = (i <= j) ? F[i + j * n] : 0.0;
+}
+
+int32_t emit_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_t location) {
+    const double *F = ctx->lu.as<double>();
+    double *dU = U;
+    int64_t ld = ldu;
+    if (location == GRM_CUDA_LOC_HOST) {
+        GRM_TRY(ctx->misc2.reserve(static_cast<size_t>(n) * n * sizeof(double)));
+        dU = ctx->misc2.as<double>();
+        ld = n;
+    }
+    const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
+    triu_copy_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(F, n, dU, ld);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    if (location == GRM_CUDA_LOC_HOST)
+        GRM_CUDA_TRY(cudaMemcpy2DAsync(U, ldu * sizeof(double), dU, n * sizeof(double), n * sizeof(double),
+                                       static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GRM_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t grm_cuda_last_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_t location) {
+    if (!ctx || !U || n < 1 || ldu < n || (location != GRM_CUDA_LOC_HOST && location != GRM_CUDA_LOC_DEVICE)) {
+        grm_set_error("last_factor: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    if (ctx->factor_n != n) {
+        grm_set_error("last_factor: no Cholesky factor of a %lld x %lld matrix is cached on this context (the last repair "
+                      "must have run, on this context, and ended positive definite)", (long long)n, (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    return emit_factor(ctx, n, U, ldu, location);
+}
+
+extern "C" int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t n, int64_t ldx, int32_t x_location,
+                                     double *U, int64_t ldu, int32_t u_location) {
+    if (!ctx || !X || !U || n < 1 || ldx < n || ldu < n ||
+        (x_location != GRM_CUDA_LOC_HOST && x_location != GRM_CUDA_LOC_DEVICE) ||
+        (u_location != GRM_CUDA_LOC_HOST && u_location != GRM_CUDA_LOC_DEVICE)) {
+        grm_set_error("cholesky: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    if (n > 46000) {
+        grm_set_error("cholesky: n=%lld exceeds the single-GPU cuSOLVER range (n <= 46000)", (long long)n);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->cusolver) {
+        cusolverDnHandle_t h;
+        GRM_SOLVER_TRY(cusolverDnCreate(&h));
+        ctx->cusolver = h;
+    }
+    cusolverDnHandle_t h = static_cast<cusolverDnHandle_t>(ctx->cusolver);
+    GRM_SOLVER_TRY(cusolverDnSetStream(h, ctx->stream));
+    ctx->factor_n = -1;
+    GRM_TRY(ctx->lu.reserve(static_cast<size_t>(n) * n * sizeof(double)));
+    double *F = ctx->lu.as<double>();
+    GRM_CUDA_TRY(cudaMemcpy2DAsync(F, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), static_cast<size_t>(n),
+                                   x_location == GRM_CUDA_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+    int lw = 0;
+    GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), F, static_cast<int>(n), &lw));
+    GRM_TRY(ctx->lu_work.reserve(std::max<size_t>(static_cast<size_t>(lw), 1) * sizeof(double)));
+    GRM_TRY(ctx->misc.reserve(64));
+    int *info = ctx->misc.as<int>();
+    // like Julia's cholesky(Symmetric(X)), only the upper triangle of X is read
+    GRM_SOLVER_TRY(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), F, static_cast<int>(n),
+                                    ctx->lu_work.as<double>(), lw, info));
+    int h_info = 0;
+    GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_info < 0) {
+        grm_set_error("cusolverDnDpotrf: illegal argument %d", -h_info);
+        return GRM_CUDA_ERR_CUDA;
+    }
+    if (h_info > 0) {
+        // Julia: PosDefException(info) — "matrix is not positive definite; Factorization failed."
+        grm_set_error("matrix is not positive definite; Cholesky factorization failed (leading minor of order %d).", h_info);
+        return GRM_CUDA_ERR_NOT_POSDEF;
+    }
+    ctx->factor_n = n;
+    return emit_factor(ctx, n, U, ldu, u_location);
 }

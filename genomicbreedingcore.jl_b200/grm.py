@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from .structs import GRM, ArgumentError, ErrorException, Genomes, MissingDataError, checkdims
+from .structs import GRM, ArgumentError, ErrorException, Genomes, MissingDataError, PosDefException, checkdims
 
 
 def _raise_for(err: _lib.GrmCudaError):
@@ -23,6 +23,8 @@ def _raise_for(err: _lib.GrmCudaError):
         raise MissingDataError(err.message) from None
     if s == _lib.ERR_ALL_FILTERED:
         raise ErrorException(err.message) from None  # filter.jl:363-365, :644-646 throw ErrorException
+    if s == _lib.ERR_NOT_POSDEF:
+        raise PosDefException(err.message) from None
     if s in (_lib.ERR_BAD_ARGUMENT, _lib.ERR_NOT_SYMMETRIC, _lib.ERR_NAN_MATRIX, _lib.ERR_INF_MATRIX,
              _lib.ERR_NONFINITE, _lib.ERR_NOT_DOSAGE, _lib.ERR_OVERFLOW):
         raise ArgumentError(err.message) from None
@@ -125,3 +127,102 @@ def inflatediagonals(X: np.ndarray, max_iter: int = 1_000, verbose: bool = False
         print(f"Performed {iters.value} iterations of diagonal inflation to ensure matrix invertibility "
               f"(ϵ_total = {tot.value}).")
     return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# consumer side of the GRM
+# ---------------------------------------------------------------------------------------------------------------
+def cholesky(X: np.ndarray, *, ctx: Optional[_lib.Context] = None) -> np.ndarray:
+    """cholesky(X).U as MvNormal(mu, X) computes it (src/simulations/simulate_effects.jl:479-481 -> PDMat ->
+    LAPACK potrf!('U', copy(X))): upper-triangular U with U'U = X; only the upper triangle of X is read.
+    Raises PosDefException where Julia does."""
+    if not isinstance(X, np.ndarray) or X.dtype != np.float64 or X.ndim != 2 or X.shape[0] != X.shape[1]:
+        raise TypeError("cholesky expects a square 2-D float64 numpy array (Matrix{Float64})")
+    ctx = ctx or _lib.default_context()
+    Xf = np.asfortranarray(X)
+    n = Xf.shape[0]
+    U = np.empty((n, n), dtype=np.float64, order="F")
+    try:
+        _lib.check(ctx.lib.grm_cuda_cholesky(ctx.handle, Xf.ctypes.data, n, n, _lib.LOC_HOST, U.ctypes.data, n,
+                                             _lib.LOC_HOST))
+    except _lib.GrmCudaError as e:
+        _raise_for(e)
+    return U
+
+
+def isposdef(X: np.ndarray, *, ctx: Optional[_lib.Context] = None) -> bool:
+    """isposdef(X) = ishermitian(X) && the Cholesky factorisation succeeds (LinearAlgebra; used at
+    src/grm/calc.jl:49,61 and src/tebv/bayes.jl:1334,1340)."""
+    X = np.asarray(X)
+    if X.ndim != 2 or X.shape[0] != X.shape[1] or not np.array_equal(X, X.T):
+        return False
+    try:
+        cholesky(np.ascontiguousarray(X, dtype=np.float64), ctx=ctx)
+    except PosDefException:
+        return False
+    return True
+
+
+def last_factor(n: int, *, ctx: Optional[_lib.Context] = None) -> np.ndarray:
+    """The Cholesky factor U (U'U = G) of the n x n matrix that the last grmsimple / grmploidyaware /
+    inflatediagonals call on `ctx` returned: the repair ends with this factorisation (calc.jl:49,61), so the consumer
+    (MvNormal) does not have to redo it.  Raises ArgumentError if no such factor is cached."""
+    ctx = ctx or _lib.default_context()
+    U = np.empty((n, n), dtype=np.float64, order="F")
+    try:
+        _lib.check(ctx.lib.grm_cuda_last_factor(ctx.handle, n, U.ctypes.data, n, _lib.LOC_HOST))
+    except _lib.GrmCudaError as e:
+        _raise_for(e)
+    return U
+
+
+def simulatecovariancekinship(p: int, genomes: Genomes, *, ctx: Optional[_lib.Context] = None) -> np.ndarray:
+    """simulatecovariancekinship(p, genomes)::Matrix{Float64} (src/simulations/simulate_effects.jl:344-351):
+    the grmsimple matrix of `genomes`, after checking that p is its number of entries."""
+    if p != len(genomes.entries):
+        raise ArgumentError("simulatecovariancekinship: p must match the number of entries in genomes.")
+    return grmsimple(genomes, ctx=ctx).genomic_relationship_matrix
+
+
+def covariance_from_grm(grm: GRM, coefficient_names, *, verbose: bool = False,
+                        ctx: Optional[_lib.Context] = None) -> np.ndarray:
+    """The entries-by-name lookup analyseviaBLR applies to a GRM (src/tebv/bayes.jl:1314-1349): Sigma[i, j] =
+    G[k, l] for the entries named in coefficient names i and j (the LAST space-separated token starting "entry_";
+    the LAST matching row of grm.entries), left at zero when the two names differ in more than one token; then up to
+    11 rounds of `inflatediagonals!` while the matrix is not positive definite, ErrorException if it still is not."""
+    names = [str(x) for x in coefficient_names]
+    n = len(names)
+    last = {}
+    for idx, e in enumerate(grm.entries):
+        last[e] = idx  # findall(grm.entries .== entry)[end]
+    G = grm.genomic_relationship_matrix
+    toks = [nm.split(" ") for nm in names]
+    ent = []
+    for t in toks:
+        hits = [w for w in t if "entry_" in w]
+        if not hits:
+            raise ArgumentError(f"coefficient name {' '.join(t)!r} names no entry")
+        if hits[-1] not in last:
+            raise ArgumentError(f"entry {hits[-1]!r} is not in the GRM")
+        ent.append(last[hits[-1]])
+    S = np.zeros((n, n), dtype=np.float64, order="F")
+    for i in range(n):
+        for j in range(n):
+            a, b = toks[i], toks[j]
+            if len(a) == len(b):
+                same = sum(1 for x, y in zip(a, b) if x == y)
+            else:
+                raise ArgumentError("coefficient names of one factor must have the same number of tokens")
+            if same < len(a) - 1:
+                continue
+            S[i, j] = G[ent[i], ent[j]]
+    counter = 0
+    while not isposdef(S, ctx=ctx):
+        if counter > 10:
+            break
+        inflatediagonals(S, verbose=verbose, ctx=ctx)
+        counter += 1
+    if not isposdef(S, ctx=ctx):
+        raise ErrorException("The variance-covariance matrix for the entries remains non-positive definite after 10 "
+                             "inflation attempts.")
+    return S

@@ -24,6 +24,10 @@ class ErrorException(RuntimeError):
     """Julia's ErrorException."""
 
 
+class PosDefException(ArithmeticError):
+    """Julia's PosDefException (what cholesky / MvNormal throw for a matrix that is not positive definite)."""
+
+
 class MissingDataError(TypeError):
     """What the reference raises (a MethodError inside a TaskFailedException) when `missing` reaches `dot`."""
 

@@ -49,7 +49,9 @@ typedef enum grm_cuda_status {
     GRM_CUDA_ERR_OOM = 8,            /* device or pinned-host allocation failed                                      */
     GRM_CUDA_ERR_NOT_DOSAGE = 9,     /* int8 path forced but the frequencies are not k/m with m a power of two <= 64 */
     GRM_CUDA_ERR_OVERFLOW = 10,      /* m*m*p would overflow the int32 accumulators                                  */
-    GRM_CUDA_ERR_ALL_FILTERED = 11   /* QC mask: "All loci filtered out ..." (src/genomes/filter.jl:363-365, :644-646) */
+    GRM_CUDA_ERR_ALL_FILTERED = 11,  /* QC mask: "All loci filtered out ..." (src/genomes/filter.jl:363-365, :644-646) */
+    GRM_CUDA_ERR_NOT_POSDEF = 12     /* grm_cuda_cholesky: Julia's PosDefException (what MvNormal(mu, Sigma) throws,
+                                        src/simulations/simulate_effects.jl:480) */
 } grm_cuda_status;
 
 /* Which contraction ran (grm_cuda_info.path) / may run (grm_cuda_options.path). */
@@ -151,6 +153,21 @@ int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, in
                               double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs);
 int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t n, int64_t ldx, int32_t rounds, double maxabs,
                               double *eps_total);
+
+/* ---- consumer side of the GRM ---------------------------------------------------------------
+ * simulateeffects turns simulatecovariancekinship's matrix (= grmsimple(genomes).genomic_relationship_matrix,
+ * src/simulations/simulate_effects.jl:344-351) into MvNormal(mu, Sigma) (:479-481), whose constructor factorises
+ * Sigma: cholesky(Sigma) = LAPACK potrf!('U', copy(Sigma)).
+ *   grm_cuda_cholesky: U (n x n, upper triangular, zeros below the diagonal, U'U = X) as Julia's cholesky(X).U; only
+ *     the upper triangle of X is read; GRM_CUDA_ERR_NOT_POSDEF where Julia throws PosDefException.
+ *   grm_cuda_last_factor: the same factor of the matrix the last grm_cuda_simple / _ploidyaware /
+ *     _inflate_diagonals call ON THIS CONTEXT returned — the repair ends with exactly this factorisation, so handing it
+ *     out saves the consumer's n^3/3 flop.  GRM_CUDA_ERR_BAD_ARGUMENT if no factor of that size is cached (repair
+ *     skipped, exhausted max_iter, or another factorisation ran since).
+ * `*_location`: GRM_CUDA_LOC_HOST / GRM_CUDA_LOC_DEVICE.  Both synchronise the stream. */
+int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t n, int64_t ldx, int32_t x_location, double *U,
+                          int64_t ldu, int32_t u_location);
+int32_t grm_cuda_last_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_t u_location);
 
 /* ---- staged device-side API (all pointers are DEVICE pointers; work is enqueued on the context stream) ------
  * These are the pieces the three entry points are assembled from.  They exist so that parity tests can look at

@@ -11,6 +11,7 @@
 module GRMCuda
 
 using GenomicBreedingCore: Genomes, GRM, checkdims
+import LinearAlgebra
 
 const LIB = get(ENV, "GRM_CUDA_LIB", joinpath(@__DIR__, "..", "genomicbreedingcore.jl_b200", "libgrm_cuda.so"))
 
@@ -72,6 +73,8 @@ function throwstatus(st::Int32)
         throw(MethodError(convert, (Float64, missing)))
     elseif st in (1, 3, 4, 5, 6, 9, 10)
         throw(ArgumentError(msg))
+    elseif st == 12
+        throw(LinearAlgebra.PosDefException(1))                                  # what cholesky / MvNormal throw
     else
         throw(ErrorException("libgrm_cuda status $st: $msg"))
     end
@@ -135,6 +138,27 @@ function inflatediagonals!(X::Matrix{Float64}; max_iter::Int64 = 1_000, verbose:
         println("Performed $(iters[]) iterations of diagonal inflation to ensure matrix invertibility (ϵ_total = $(total[])).")
     end
     nothing
+end
+
+# ---- consumer side (SURVEY.md §8 f3): MvNormal(μ, Σ) factorises Σ (simulate_effects.jl:479-481) -------------------
+# cholesky(Σ).U computed on the GPU; `lastfactor(n)` hands out the factor the repair of the last GRM call ended with, so
+# `MvNormal(μ, PDMat(Σ, Cholesky(lastfactor(n), 'U', 0)))` skips the second O(n³) factorisation.
+function cholesky_upper(X::Matrix{Float64})::Matrix{Float64}
+    n = size(X, 1)
+    size(X, 2) == n || throw(DimensionMismatch("matrix is not square"))
+    U = Matrix{Float64}(undef, n, n)
+    st = GC.@preserve X U ccall((:grm_cuda_cholesky, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int32, Ptr{Float64}, Int64, Int32), context(), X, n, n, 0, U, n, 0)
+    st == 0 || throwstatus(st)
+    U
+end
+
+function lastfactor(n::Integer)::Matrix{Float64}
+    U = Matrix{Float64}(undef, n, n)
+    st = GC.@preserve U ccall((:grm_cuda_last_factor, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Int32),
+        context(), n, U, n, 0)
+    st == 0 || throwstatus(st)
+    U
 end
 
 end # module

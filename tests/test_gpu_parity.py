@@ -667,3 +667,70 @@ def test_pipelined_flow_is_bit_identical_to_serial(ctx, monkeypatch, n, p, m, pl
     G3, i3 = D.grm_device(ctx, Ac, ploidy, skip_repair=True)
     assert i2["path"] == i3["path"] == _lib.PATH_F64
     assert torch.equal(G2, G3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# consumer side: the Cholesky factor MvNormal(mu, Sigma) computes, and the by-name lookup
+# ---------------------------------------------------------------------------------------------------------------
+RTOL_CHOL = 1e-10  # FP64 library factorisation (cuSOLVER potrf vs LAPACK potrf): same algorithm class, other blocking
+
+
+@pytest.mark.parametrize("n,p,kind", [(100, 10_000, "dosage"), (257, 2000, "continuous"), (1, 10, "dosage")])
+def test_cholesky_factor_matches_lapack_and_is_reused_from_the_repair(n, p, kind):
+    from scipy.linalg import cholesky as sp_chol
+
+    A = synth.dosage(n, p, 2, seed=21) if kind == "dosage" else synth.continuous(n, p, seed=22)
+    ctx = grm_b200.default_context()
+    grm = grmsimple(Genomes.from_matrix(A), ctx=ctx)
+    G = grm.genomic_relationship_matrix
+    U_cached = grm_b200.last_factor(n, ctx=ctx)        # left behind by the repair's final isposdef
+    U = grm_b200.cholesky(G, ctx=ctx)                  # computed afresh
+    assert np.array_equal(U, U_cached)                  # same routine on the same matrix
+    ref = sp_chol(G, lower=False)                       # LAPACK dpotrf('U'), what Julia calls
+    assert np.array_equal(np.tril(U, -1), np.zeros_like(U))
+    assert relerr(U, ref) < RTOL_CHOL
+    assert relerr(U.T @ U, G) < 1e-13
+    assert grm_b200.isposdef(G, ctx=ctx)
+    # only the upper triangle is read, as with Julia's cholesky(Symmetric(X)) inside PDMat
+    G2 = np.array(G, order="F", copy=True)
+    G2[np.tril_indices(n, -1)] = 123.0
+    assert np.array_equal(grm_b200.cholesky(G2, ctx=ctx), U)
+    # not positive definite -> PosDefException; and the cached factor is gone after a failed factorisation
+    bad = -np.eye(max(n, 2))
+    with pytest.raises(grm_b200.PosDefException):
+        grm_b200.cholesky(bad, ctx=ctx)
+    assert not grm_b200.isposdef(bad, ctx=ctx)
+    with pytest.raises(ArgumentError):
+        grm_b200.last_factor(max(n, 2), ctx=ctx)
+    # repair skipped -> nothing cached
+    grmsimple(Genomes.from_matrix(A), ctx=ctx, skip_repair=True)
+    with pytest.raises(ArgumentError):
+        grm_b200.last_factor(n, ctx=ctx)
+
+
+def test_simulatecovariancekinship_and_lookup_by_entry_name():
+    n, p = 60, 3000
+    g = Genomes.from_matrix(synth.continuous(n, p, seed=5))
+    S = grm_b200.simulatecovariancekinship(n, g)
+    st, ref, _, _ = O.c_grmsimple(g.allele_frequencies)
+    assert st == O.OK and relerr(S, ref) < RTOL_F64
+    assert S.shape == (n, n) and np.var(S) > 0.0 and abs(np.linalg.det(S)) > 0.0  # simulate_effects.jl:334-342
+    with pytest.raises(ArgumentError):
+        grm_b200.simulatecovariancekinship(n + 1, g)
+    # analyseviaBLR's lookup (bayes.jl:1314-1349): coefficient names "entries entry_XX" in another order, a subset
+    grm = grmsimple(g)
+    pick = [7, 3, 59, 0, 21]
+    names = [f"entries {g.entries[i]}" for i in pick]
+    Sig = grm_b200.covariance_from_grm(grm, names)
+    sub = np.array(grm.genomic_relationship_matrix[np.ix_(pick, pick)], order="F")
+    ref_sub = sub.copy()
+    k = 0
+    while not O.np_isposdef(ref_sub) and k <= 10:
+        _, ref_sub, _, _ = O.np_inflatediagonals(ref_sub)
+        k += 1
+    assert np.allclose(Sig, ref_sub, rtol=1e-12, atol=0)
+    assert grm_b200.isposdef(Sig)
+    # interaction names that differ in more than one token stay zero
+    names2 = [f"site_1 {g.entries[0]}", f"site_2 {g.entries[1]}", f"site_1 {g.entries[1]}"]
+    Sig2 = grm_b200.covariance_from_grm(grm, names2)
+    assert Sig2[0, 1] == 0.0 and Sig2[0, 2] != 0.0 and Sig2[1, 2] != 0.0
