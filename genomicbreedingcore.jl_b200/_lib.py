@@ -103,6 +103,12 @@ SIGNATURES = {
     "grm_cuda_packed_tiles_max": (_i64, [_i64, _i32]),
     "grm_cuda_syrk_i8_packed": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "grm_cuda_finalize_tiles": (_i32, [_vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
+    "grm_cuda_syrk_i8_scatter": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
+    "grm_cuda_finalize_tiles_parts": (_i32, [_vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
+    "grm_cuda_ipc_alloc": (_i32, [_vp, _i64, C.POINTER(_vp), _vp]),
+    "grm_cuda_ipc_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    "grm_cuda_ipc_close": (_i32, [_vp, _vp]),
+    "grm_cuda_ipc_free": (_i32, [_vp, _vp]),
     "grm_cuda_dosage_stats": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _i32]),
     "grm_cuda_dosage_centre": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, C.POINTER(_f64)]),
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),

@@ -185,6 +185,63 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
 
 extern "C" void *grm_cuda_ctx_stream(grm_cuda_ctx *ctx) { return ctx ? ctx->stream : nullptr; }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-visible device buffers for the one-process-per-GPU exchange (grm_cuda_syrk_i8_scatter): plain cudaMalloc
+// allocations exported / opened through CUDA IPC handles (64 opaque bytes the host processes exchange themselves).
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int32_t grm_cuda_ipc_alloc(grm_cuda_ctx *ctx, int64_t bytes, void **dptr, uint8_t *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ctx || bytes < 1 || !dptr || !handle64) {
+        grm_set_error("ipc_alloc: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        grm_set_error("ipc_alloc: cudaMalloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return GRM_CUDA_ERR_OOM;
+    }
+    cudaIpcMemHandle_t h;
+    const cudaError_t e2 = cudaIpcGetMemHandle(&h, p);
+    if (e2 != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+        grm_set_error("ipc_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e2));
+        return GRM_CUDA_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    *dptr = p;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_ipc_open(grm_cuda_ctx *ctx, const uint8_t *handle64, void **dptr) {
+    if (!ctx || !handle64 || !dptr) {
+        grm_set_error("ipc_open: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    GRM_CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_ipc_close(grm_cuda_ctx *ctx, void *dptr) {
+    if (!ctx || !dptr) return GRM_CUDA_ERR_BAD_ARGUMENT;
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_ipc_free(grm_cuda_ctx *ctx, void *dptr) {
+    if (!ctx || !dptr) return GRM_CUDA_ERR_BAD_ARGUMENT;
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    GRM_CUDA_TRY(cudaFree(dptr));
+    return GRM_CUDA_OK;
+}
+
 extern "C" int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx) {
     if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));

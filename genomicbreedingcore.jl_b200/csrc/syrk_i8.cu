@@ -34,6 +34,8 @@ constexpr int NUM_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 2 * BN;              // two accumulator stages of 256 int32 columns
 constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
+constexpr int GRM_MAX_PEERS = 8;
+
 struct EpiParams {
     int64_t n;
     int32_t *C;      // mode 0
@@ -48,6 +50,11 @@ struct EpiParams {
                            // zeros outside n) instead of into the dense matrix G: the sharded-output form
     const int32_t *prev;   // 2-CTA kernel, modes 1-3: if set, packed int32 tiles ([slot][col][row]) holding the partial
                            // sums of earlier loci chunks; added to the accumulator before the mode's own epilogue
+    // mode 3, peer-store form (tiles_max > 0): the tile in slot (o, s) = (slot / tiles_max, slot % tiles_max) is stored
+    // straight into GPU o's receive buffer over NVLink, at part `src_rank`: peers[o] + (src_rank*tiles_max + s)*65536
+    int32_t *peers[GRM_MAX_PEERS];
+    int32_t tiles_max;
+    int32_t src_rank;
 };
 
 // Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
@@ -398,7 +405,14 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             if (EPI == 2 && row_ok) ui = ep.u[row];
             const int64_t slot = ep.slots ? static_cast<int64_t>(ep.slots[t]) : static_cast<int64_t>(t);
             int32_t *packed = nullptr;
-            if (EPI == 3) packed = ep.C + slot * 65536;
+            if (EPI == 3) {
+                if (ep.tiles_max > 0) {
+                    const int64_t o = slot / ep.tiles_max, sl = slot - o * ep.tiles_max;
+                    packed = ep.peers[o] + (static_cast<int64_t>(ep.src_rank) * ep.tiles_max + sl) * 65536;
+                } else {
+                    packed = ep.C + slot * 65536;
+                }
+            }
             const int row_local = 128 * static_cast<int>(cta) + quarter * 32 + lane;
             const int32_t *prev = (EPI != 0 && ep.prev) ? ep.prev + slot * 65536 + row_local : nullptr;
 #pragma unroll 1
@@ -724,14 +738,17 @@ void make_packed_plan(int64_t n, int32_t world, PackedPlan &pl) {
 // G tile <- formula(reduced int32 tile): block = one owned tile, same arithmetic as the fused SYRK epilogue
 template <int EPI>
 __global__ void __launch_bounds__(256)
-finalize_tiles_kernel(const int32_t *__restrict__ packed, const int2 *__restrict__ tiles, EpiParams ep) {
+finalize_tiles_kernel(const int32_t *__restrict__ packed, const int2 *__restrict__ tiles, EpiParams ep, int nparts,
+                      int64_t part_stride) {
     const int2 tc = tiles[blockIdx.x];
     const int32_t *tile = packed + static_cast<int64_t>(blockIdx.x) * 65536;
     for (int idx = threadIdx.x; idx < 65536; idx += 256) {
         const int cl = idx >> 8, rl = idx & 255;
         const int64_t row = tc.x + rl, col = tc.y + cl;
         if (row < ep.n && col < ep.n) {
-            double v = static_cast<double>(tile[idx]) * ep.alpha;
+            int32_t c = tile[idx];
+            for (int q = 1; q < nparts; ++q) c += tile[q * part_stride + idx];  // peer-store form: one part per GPU
+            double v = static_cast<double>(c) * ep.alpha;
             if (EPI == 2) v = (v - ep.beta * (__ldg(ep.u + row) + __ldg(ep.u + col))) + ep.gamma;
             ep.G[row + col * ep.ldg] = (ep.rcp != 0.0) ? div_const(v, ep.denom, ep.rcp) : v / ep.denom;
         }
@@ -746,9 +763,10 @@ extern "C" int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world) {
     return (T * (T + 1) / 2 + world - 1) / world;
 }
 
-extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                           int32_t world, int32_t *d_packed) {
-    if (!ctx || !d_codes || !d_packed || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1) {
+static int32_t syrk_i8_packed_impl(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                   int32_t world, int32_t *d_packed, int32_t src_rank, void *const *peer_recv) {
+    if (!ctx || !d_codes || (!d_packed && !peer_recv) || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1 ||
+        (peer_recv && (world > GRM_MAX_PEERS || src_rank < 0 || src_rank >= world))) {
         grm_set_error("syrk_i8_packed: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
@@ -781,11 +799,22 @@ extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_co
                                           static_cast<int>(SMEM2_BYTES)));
         attr_set = true;
     }
-    // unused slots of the reduce-scatter layout must be defined (they are summed too)
     const int64_t tiles_max = grm_cuda_packed_tiles_max(n, world);
-    if (static_cast<int64_t>(count) != tiles_max * world)
+    if (peer_recv) {
+        for (int r = 0; r < world; ++r) {
+            if (!peer_recv[r]) {
+                grm_set_error("syrk_i8_scatter: receive buffer of rank %d is null", r);
+                return GRM_CUDA_ERR_BAD_ARGUMENT;
+            }
+            ep.peers[r] = static_cast<int32_t *>(peer_recv[r]);
+        }
+        ep.tiles_max = static_cast<int32_t>(tiles_max);
+        ep.src_rank = src_rank;
+    } else if (static_cast<int64_t>(count) != tiles_max * world) {
+        // unused slots of the reduce-scatter layout must be defined (they are summed too)
         GRM_CUDA_TRY(cudaMemsetAsync(d_packed, 0, static_cast<size_t>(tiles_max) * world * 65536 * sizeof(int32_t),
                                      ctx->stream));
+    }
     const int kbs = static_cast<int>((p + BK - 1) / BK);
     const int pairs = std::min(count, ctx->num_sms / 2);
     uint32_t *prog = nullptr;
@@ -797,14 +826,29 @@ extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_co
     return GRM_CUDA_OK;
 }
 
-extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha,
-                                           double beta, double gamma, double denom, const double *d_u, double *d_G,
-                                           int64_t ldg, int32_t rank, int32_t world) {
-    if (!ctx || !d_reduced || !d_G || n < 1 || ldg < n || world < 1 || rank < 0 || rank >= world ||
+extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                           int32_t world, int32_t *d_packed) {
+    return syrk_i8_packed_impl(ctx, d_codes, n, p, ldc, world, d_packed, 0, nullptr);
+}
+
+extern "C" int32_t grm_cuda_syrk_i8_scatter(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                            int32_t rank, int32_t world, void *const *peer_recv) {
+    if (!peer_recv) {
+        grm_set_error("syrk_i8_scatter: peer_recv is null");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    return syrk_i8_packed_impl(ctx, d_codes, n, p, ldc, world, nullptr, rank, peer_recv);
+}
+
+static int32_t finalize_tiles_impl(grm_cuda_ctx *ctx, const int32_t *d_reduced, int nparts, int64_t n, double alpha,
+                                   double beta, double gamma, double denom, const double *d_u, double *d_G,
+                                   int64_t ldg, int32_t rank, int32_t world) {
+    if (!ctx || !d_reduced || !d_G || n < 1 || ldg < n || world < 1 || rank < 0 || rank >= world || nparts < 1 ||
         (beta != 0.0 && !d_u)) {
         grm_set_error("finalize_tiles: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
+    const int64_t part_stride = grm_cuda_packed_tiles_max(n, world) * 65536;
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     const int2 *d_tiles;
     int count;
@@ -821,11 +865,25 @@ extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_r
     const double a = fabs(denom);
     ep.rcp = (a > 1e-200 && a < 1e200) ? 1.0 / denom : 0.0;
     ep.u = d_u;
-    if (beta == 0.0 && gamma == 0.0) finalize_tiles_kernel<1><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep);
-    else finalize_tiles_kernel<2><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep);
+    if (beta == 0.0 && gamma == 0.0)
+        finalize_tiles_kernel<1><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep, nparts, part_stride);
+    else
+        finalize_tiles_kernel<2><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep, nparts, part_stride);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha,
+                                           double beta, double gamma, double denom, const double *d_u, double *d_G,
+                                           int64_t ldg, int32_t rank, int32_t world) {
+    return finalize_tiles_impl(ctx, d_reduced, 1, n, alpha, beta, gamma, denom, d_u, d_G, ldg, rank, world);
+}
+
+extern "C" int32_t grm_cuda_finalize_tiles_parts(grm_cuda_ctx *ctx, const int32_t *d_recv, int64_t n, double alpha,
+                                                 double beta, double gamma, double denom, const double *d_u,
+                                                 double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+    return finalize_tiles_impl(ctx, d_recv, world, n, alpha, beta, gamma, denom, d_u, d_G, ldg, rank, world);
 }
 
 // Sharded-output form of grm_cuda_syrk_i8_f64: the tiles owned by (rank, world) are written as packed 256 x 256 FP64

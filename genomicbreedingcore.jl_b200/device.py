@@ -162,6 +162,63 @@ def finalize_tiles(ctx, reduced, n: int, alpha: float, beta: float, gamma: float
     return G
 
 
+def syrk_i8_scatter(ctx, codes, p: int, rank: int, world: int, peer_ptrs):
+    """K-split contraction with the exchange fused into the epilogue: every finished int32 tile is stored straight into
+    its owner's receive buffer (peer memory), part `rank`.  peer_ptrs: `world` raw device pointers (ints)."""
+    n, ldc = codes.shape
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in peer_ptrs])
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_syrk_i8_scatter(ctx.handle, _ptr(codes), n, p, ldc, rank, world, arr))
+    ctx.order_torch_after()
+
+
+def finalize_tiles_parts(ctx, recv_ptr: int, n: int, alpha: float, beta: float, gamma: float, denom: float, u, G,
+                         rank: int, world: int):
+    """Sum the `world` parts of each owned tile in the receive buffer and apply the epilogue formula."""
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_finalize_tiles_parts(ctx.handle, C.c_void_p(int(recv_ptr)), n, alpha, beta, gamma, denom,
+                                                     _ptr(u) if u is not None else None, _ptr(G), n, rank, world))
+    ctx.order_torch_after()
+    return G
+
+
+class PeerBuffer:
+    """A cudaMalloc'ed buffer of this rank plus the mappings of the same buffer of every peer (CUDA IPC)."""
+
+    def __init__(self, ctx, nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _lib.check(ctx.lib.grm_cuda_ipc_alloc(ctx.handle, self.nbytes, C.byref(ptr), handle))
+        self.ptr = int(ptr.value)
+        self.handle = bytes(handle)
+        self.peers = None     # raw pointers, index = rank
+        self._opened = []
+
+    def open_peers(self, handles, rank: int):
+        """handles: list of 64-byte handles, index = rank (own entry ignored)."""
+        self.peers = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                self.peers.append(self.ptr)
+                continue
+            buf = (C.c_uint8 * 64).from_buffer_copy(bytes(h))
+            p = C.c_void_p()
+            _lib.check(self.ctx.lib.grm_cuda_ipc_open(self.ctx.handle, buf, C.byref(p)))
+            self.peers.append(int(p.value))
+            self._opened.append(int(p.value))
+        return self.peers
+
+    def close(self):
+        for p in self._opened:
+            self.ctx.lib.grm_cuda_ipc_close(self.ctx.handle, C.c_void_p(p))
+        self._opened = []
+        if self.ptr:
+            self.ctx.lib.grm_cuda_ipc_free(self.ctx.handle, C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
 def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
     torch = _torch()
     dev = colsum.device

@@ -28,6 +28,8 @@ The exchange helpers take plain tensors and a process group, so they run under `
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Tuple
 
 from . import _lib
@@ -77,7 +79,7 @@ class ShardedGRM:
     """Per-rank driver of the sharded int8 path on device-resident loci slabs."""
 
     def __init__(self, n: int, p: int, ploidy: Optional[int], denominator: int, ctx: _lib.Context, group=None,
-                 mode: str = "auto", output: str = "dense"):
+                 mode: str = "auto", output: str = "dense", exchange: str = "auto"):
         """output="dense": this rank's tiles inside a zero-initialised local n x n matrix (self.G);
         output="tiles" (gather mode): packed [tiles_owned, 256, 256] FP64 tiles (self.tiles), never a dense matrix —
         the form for GRMs larger than one device (BASELINE config 5: n = 100,000, 10 GB of tiles per GPU on 8)."""
@@ -102,9 +104,31 @@ class ShardedGRM:
             self.codes_all = torch.zeros((self.world, n, self.lds), dtype=torch.int8, device=dev)
             self.colsum_all = torch.zeros((self.world, self.lds), dtype=torch.int32, device=dev)
         else:
+            # exchange of the K-split partial tiles: "nccl" = packed buffer + reduce-scatter + finalize;
+            # "p2p" = the SYRK epilogue stores every tile into its owner's receive buffer over NVLink peer memory
+            # (CUDA IPC mappings), then a one-element all-reduce as barrier and a finalize that sums the parts
+            if exchange == "auto":
+                exchange = os.environ.get("GRM_CUDA_EXCHANGE", "nccl")
+            if exchange not in ("nccl", "p2p"):
+                raise ValueError(f"exchange must be 'nccl' or 'p2p', got {exchange!r}")
+            if exchange == "p2p" and not (1 < self.world <= 8):
+                exchange = "nccl"
+            self.exchange = exchange
+            if denominator * denominator * p >= 2 ** 31:
+                raise _lib.GrmCudaError(_lib.ERR_OVERFLOW, f"m^2 * p = {denominator}^2 * {p} overflows int32")
             self.tiles_max = ctx.lib.grm_cuda_packed_tiles_max(n, self.world)
-            self.packed = torch.zeros((self.world * self.tiles_max, 65536), dtype=torch.int32, device=dev)
-            self.reduced = torch.zeros((self.tiles_max, 65536), dtype=torch.int32, device=dev)
+            if exchange == "p2p":
+                from . import device as D
+
+                self.recv = D.PeerBuffer(ctx, self.world * self.tiles_max * 65536 * 4)
+                mine = torch.tensor(list(self.recv.handle), dtype=torch.uint8, device=dev)
+                allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+                self.recv.open_peers([bytes(row.tolist()) for row in allh.cpu()], self.rank)
+                self._token = torch.zeros((1,), dtype=torch.int32, device=dev)
+            else:
+                self.packed = torch.zeros((self.world * self.tiles_max, 65536), dtype=torch.int32, device=dev)
+                self.reduced = torch.zeros((self.tiles_max, 65536), dtype=torch.int32, device=dev)
         self.flags = torch.zeros((16,), dtype=torch.int32, device=dev)
         self.output = output
         if output == "tiles":
@@ -184,6 +208,24 @@ class ShardedGRM:
                 self.launches += 1
                 if ev:
                     ev[4].record()
+            elif self.exchange == "p2p":
+                if self.ploidy is None:
+                    # no statistics all-reduce in this step: a one-element all-reduce keeps any rank from storing into
+                    # a peer that is still finalising the previous step
+                    dist.all_reduce(self._token, group=self.group)
+                D.syrk_i8_scatter(ctx, self.codes_slab, max(pc, 1), self.rank, self.world, self.recv.peers)
+                self.launches += 1
+                if ev:
+                    ev[4].record()
+                    ev5, ev6 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.all_reduce(self._token, group=self.group)  # barrier: every peer's stores have landed
+                if ev:
+                    ev5.record()
+                D.finalize_tiles_parts(ctx, self.recv.ptr, n, alpha, beta, gamma, denom, u, self.G, self.rank,
+                                       self.world)
+                self.launches += 1
+                if ev:
+                    ev6.record()
             else:
                 D.syrk_i8_packed(ctx, self.codes_slab, max(pc, 1), self.world, out=self.packed)
                 self.launches += 1
@@ -213,6 +255,18 @@ class ShardedGRM:
             raise _lib.GrmCudaError(_lib.ERR_MISSING if flags & 1 else _lib.ERR_NONFINITE if flags & 2
                                     else _lib.ERR_NOT_DOSAGE, f"input flags {flags} on rank {self.rank}")
         return self.G if self.output == "dense" else self.tiles
+
+    def close(self):
+        """Release the peer mappings and the receive buffer of the "p2p" exchange (collective: call on every rank)."""
+        recv = getattr(self, "recv", None)
+        if recv is not None:
+            import torch.distributed as dist
+
+            self.ctx.synchronize()
+            if dist.is_initialized() and self.world > 1:
+                dist.barrier(group=self.group)  # no peer may still be storing into a buffer that is about to go
+            recv.close()
+            self.recv = None
 
     def gather(self):
         """Single-device copy on every rank: sum of the zero-padded tile sets, then mirror."""

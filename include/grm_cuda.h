@@ -225,6 +225,26 @@ int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int
                                 double gamma, double denom, const double *d_u, double *d_G, int64_t ldg,
                                 int32_t rank, int32_t world);
 
+/* The same exchange WITHOUT a collective, fused into the SYRK epilogue (one process per GPU, NVLink / NVSwitch peer
+ * memory): every GPU owns a receive buffer of [world parts][tiles_max][256][256] int32 that its peers can address
+ * (grm_cuda_ipc_alloc / _open).  grm_cuda_syrk_i8_scatter stores each finished int32 tile straight into its OWNER's
+ * receive buffer, at part `rank`, while the tensor cores work on the next tile (plain coalesced stores to peer memory,
+ * no atomics, every part written by exactly one GPU); after a barrier across the GPUs,
+ * grm_cuda_finalize_tiles_parts sums the `world` parts of each owned tile (int32, exact, fixed order) and applies the
+ * epilogue formula.  peer_recv: host array of `world` device pointers (entry r = rank r's receive buffer as mapped
+ * in THIS process; entry `rank` = the own buffer).  The caller orders the steps: a peer may only be written after it
+ * has finalised the previous step (dist.py uses the statistics all-reduce / a one-element all-reduce as barriers). */
+int32_t grm_cuda_syrk_i8_scatter(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                 int32_t rank, int32_t world, void *const *peer_recv);
+int32_t grm_cuda_finalize_tiles_parts(grm_cuda_ctx *ctx, const int32_t *d_recv, int64_t n, double alpha, double beta,
+                                      double gamma, double denom, const double *d_u, double *d_G, int64_t ldg,
+                                      int32_t rank, int32_t world);
+/* cudaMalloc'ed buffer + its 64-byte CUDA IPC handle; open / close a peer's handle; free an own buffer. */
+int32_t grm_cuda_ipc_alloc(grm_cuda_ctx *ctx, int64_t bytes, void **dptr, uint8_t *handle64);
+int32_t grm_cuda_ipc_open(grm_cuda_ctx *ctx, const uint8_t *handle64, void **dptr);
+int32_t grm_cuda_ipc_close(grm_cuda_ctx *ctx, void *dptr);
+int32_t grm_cuda_ipc_free(grm_cuda_ctx *ctx, void *dptr);
+
 /* Exact integer statistics of the codes for the rank-1 centring of grmploidyaware:
  *   r[i] = sum_k codes[i,k]      T[i] = sum_k codes[i,k]*colsum[k]      sums = { sum_k colsum[k], sum_k colsum[k]^2 }
  * (dp4a against the byte planes of colsum; order-independent, hence bit-identical for any chunking / GPU count).

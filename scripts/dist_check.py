@@ -24,16 +24,21 @@ for (n, p, m, ploidy) in [(3000, 20000, 4, 4), (1100, 777, 2, None), (2049, 5001
     sh.step(A[k0:k1].contiguous())
     G = sh.gather().clone()
     sh.step(A[k0:k1].contiguous())  # second step after a gather must start from zeros again
-    G2 = sh.gather()
+    G2 = sh.gather().clone()
+    for _ in range(4):  # back-to-back steps: a rank may not overwrite a peer that still finalises the previous step
+        sh.step(A[k0:k1].contiguous())
+    G3 = sh.gather()
     ref, info = D.grm_device(ctx, A, ploidy, denominator=m, skip_repair=True)
     ctx.synchronize()
     same = torch.equal(G, ref)
     rel = float((G - ref).abs().max() / ref.abs().max())
-    again = torch.equal(G, G2)
+    again = torch.equal(G, G2) and torch.equal(G, G3)
     sym = torch.equal(G, G.T)
-    print(f"[rank {rank}/{world}] n={n} p={p} ploidy={ploidy}: bit-identical={same} rel={rel:.2e} repeat={again} symmetric={sym}",
+    print(f"[rank {rank}/{world}] n={n} p={p} ploidy={ploidy}: bit-identical={same} rel={rel:.2e} repeat={again} symmetric={sym} mode={sh.mode} exchange={getattr(sh, 'exchange', '-')}",
           flush=True)
     ok = ok and same and again and sym  # integer statistics: bit-identical for any number of ranks
+    exch = getattr(sh, "exchange", "-")
+    sh.close()
 t = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

@@ -526,6 +526,49 @@ def test_loci_split_packed_tiles_emulated_ranks(ctx, world, ploidy):
     assert np.array_equal(G.cpu().numpy(), full)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("ploidy", [None, 4])
+def test_loci_split_peer_store_exchange_emulated_ranks(ctx, world, ploidy):
+    """The collective-free exchange of the "ksplit" decomposition with the ranks emulated on one GPU: every rank's SYRK
+    epilogue stores its int32 tiles straight into the owner's receive buffer (part = source rank), every owner sums
+    its `world` parts and finalises; the union must be bit-identical to one call.  (Across processes the receive
+    buffers are CUDA IPC mappings; here they are `world` buffers of one process.)"""
+    import torch
+
+    from grm_b200 import device as D, dist as GD
+
+    n, p, m = 1100, 3001, 4
+    A = synth.dosage(n, p, m, seed=62)
+    full, info = grm_call(A, ploidy, skip_repair=True)
+    At = to_dev(A)
+    tmax = ctx.lib.grm_cuda_packed_tiles_max(n, world)
+    bufs = [D.PeerBuffer(ctx, world * tmax * 65536 * 4) for _ in range(world)]
+    try:
+        assert all(len(b.handle) == 64 for b in bufs)
+        ptrs = [b.ptr for b in bufs]
+        sums = r = T = None
+        for rk in range(world):
+            k0, k1 = GD.loci_range(p, rk, world)
+            codes, colsum, flags = D.pack_dosage(ctx, At[k0:k1].contiguous(), m)
+            D.syrk_i8_scatter(ctx, codes, k1 - k0, rk, world, ptrs)
+            sums, r, T = D.dosage_stats(ctx, codes, k1 - k0, colsum, sums, r, T, accumulate=sums is not None)
+            ctx.synchronize()
+        if ploidy is None:
+            u, (alpha, beta, gamma, denom) = None, (1.0 / (m * m), 0.0, 0.0, float(p))
+        else:
+            u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r, T, p, m, ploidy)
+        G = torch.zeros((n, n), dtype=torch.float64, device=dev())
+        for rk in range(world):
+            D.finalize_tiles_parts(ctx, ptrs[rk], n, alpha, beta, gamma, denom, u, G, rk, world)
+        D.scale_mirror(ctx, G, 1.0)
+        ctx.synchronize()
+        assert np.array_equal(G.cpu().numpy(), full)
+    finally:
+        ctx.synchronize()
+        for b in bufs:
+            b.close()
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_sharded_output_tiles_match_dense_result(ctx, world):
     """BASELINE config 5's output form (tiles stay on their owners, never a dense n x n matrix) at a reduced size."""
