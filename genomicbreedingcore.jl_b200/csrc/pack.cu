@@ -505,7 +505,7 @@ colsum_planes_kernel(const int32_t *__restrict__ colsum, int64_t p, int64_t ldc,
 }
 
 // block = 256 threads x 8 entry rows; thread t owns 16-locus groups t, t+256, ...; 16 dp4a per row and group
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 rowstats_i8_kernel(const int8_t *__restrict__ codes, int64_t n, int64_t p, int64_t ldc,
                    const uint8_t *__restrict__ planes, long long *__restrict__ r_out, long long *__restrict__ T_out,
                    int accumulate) {
@@ -520,17 +520,22 @@ rowstats_i8_kernel(const int8_t *__restrict__ codes, int64_t n, int64_t p, int64
         const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(planes + k));
         const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(planes + ldc + k));
         const uint4 b2 = __ldg(reinterpret_cast<const uint4 *>(planes + 2 * ldc + k));
+        // all row loads of the group first (unconditional: rows beyond n are clamped onto the last row and their
+        // sums discarded below), then the arithmetic — a conditional load per row left one load in flight per thread
+        // (ncu: long-scoreboard stalls on the first dp4a of every row, HBM at 37 %)
+        uint4 c[RD_ROWS];
 #pragma unroll
         for (int r = 0; r < RD_ROWS; ++r) {
-            const int64_t row = r0 + r;
-            if (row < n) {
-                const uint4 c = __ldg(reinterpret_cast<const uint4 *>(codes + row * ldc + k));
-                t0[r] = __dp4a(c.x, b0.x, __dp4a(c.y, b0.y, __dp4a(c.z, b0.z, __dp4a(c.w, b0.w, t0[r]))));
-                t1[r] = __dp4a(c.x, b1.x, __dp4a(c.y, b1.y, __dp4a(c.z, b1.z, __dp4a(c.w, b1.w, t1[r]))));
-                t2[r] = __dp4a(c.x, b2.x, __dp4a(c.y, b2.y, __dp4a(c.z, b2.z, __dp4a(c.w, b2.w, t2[r]))));
-                rs[r] = __dp4a(c.x, 0x01010101u, __dp4a(c.y, 0x01010101u, __dp4a(c.z, 0x01010101u,
-                                                                                __dp4a(c.w, 0x01010101u, rs[r]))));
-            }
+            const int64_t row = (r0 + r < n) ? r0 + r : n - 1;
+            c[r] = __ldg(reinterpret_cast<const uint4 *>(codes + row * ldc + k));
+        }
+#pragma unroll
+        for (int r = 0; r < RD_ROWS; ++r) {
+            t0[r] = __dp4a(c[r].x, b0.x, __dp4a(c[r].y, b0.y, __dp4a(c[r].z, b0.z, __dp4a(c[r].w, b0.w, t0[r]))));
+            t1[r] = __dp4a(c[r].x, b1.x, __dp4a(c[r].y, b1.y, __dp4a(c[r].z, b1.z, __dp4a(c[r].w, b1.w, t1[r]))));
+            t2[r] = __dp4a(c[r].x, b2.x, __dp4a(c[r].y, b2.y, __dp4a(c[r].z, b2.z, __dp4a(c[r].w, b2.w, t2[r]))));
+            rs[r] = __dp4a(c[r].x, 0x01010101u, __dp4a(c[r].y, 0x01010101u, __dp4a(c[r].z, 0x01010101u,
+                                                                                      __dp4a(c[r].w, 0x01010101u, rs[r]))));
         }
     }
     __shared__ unsigned long long shT[RD_ROWS][8], shR[RD_ROWS][8];
