@@ -25,6 +25,7 @@ ERR_NOT_DOSAGE = 9
 ERR_OVERFLOW = 10
 ERR_ALL_FILTERED = 11
 ERR_NOT_POSDEF = 12
+DIM_LOCI, DIM_ENTRIES = 0, 1
 
 PATH_AUTO, PATH_I8, PATH_F64 = 0, 1, 2
 MISSING_ERROR, MISSING_MEANFILL = 0, 1
@@ -94,6 +95,8 @@ SIGNATURES = {
     "grm_cuda_repair_apply": (_i32, [_vp, _vp, _i64, _i64, _i32, _f64, C.POINTER(_f64)]),
     "grm_cuda_cholesky": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _i64, _i32]),
     "grm_cuda_last_factor": (_i32, [_vp, _i64, _vp, _i64, _i32]),
+    "grm_cuda_distances": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                  _i32]),
     "grm_cuda_detect_denominator": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
     "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
     "grm_cuda_locus_qc": (_i32, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),

@@ -226,3 +226,75 @@ def covariance_from_grm(grm: GRM, coefficient_names, *, verbose: bool = False,
         raise ErrorException("The variance-covariance matrix for the entries remains non-positive definite after 10 "
                              "inflation attempts.")
     return S
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# distances(genomes)
+# ---------------------------------------------------------------------------------------------------------------
+RECOGNISED_DISTANCE_METRICS = ["euclidean", "correlation", "mad", "rmsd", "χ²"]  # genomes.jl:470
+
+
+def distances(genomes: Genomes, distance_metrics=None, idx_loci_alleles=None, include_loci_alleles: bool = True,
+              include_entries: bool = True, include_counts: bool = True, verbose: bool = False, *, seed: int = 42,
+              ctx: Optional[_lib.Context] = None):
+    """distances(genomes; distance_metrics, idx_loci_alleles, include_loci_alleles, include_entries, include_counts)
+    (src/genomes/genomes.jl:454-654).  Returns (loci_alleles_names, entries, Dict "dimension|metric" -> matrix) with the
+    reference's keys ("loci_alleles|euclidean", "entries|counts", ...).
+
+    `idx_loci_alleles` is 1-based like the Julia argument.  Differences that cannot be avoided: the reference's default
+    metric list contains "covariance", which its own validation rejects (:455 vs :470), so the default here is the list
+    of recognised metrics; and `idx_loci_alleles = nothing` samples 100 loci with Julia's global RNG — here with
+    NumPy's `default_rng(seed)`."""
+    if not checkdims(genomes):
+        raise ArgumentError("The genomes struct is corrupted ☹.")
+    metrics = list(dict.fromkeys(RECOGNISED_DISTANCE_METRICS if distance_metrics is None else distance_metrics))
+    if len(metrics) < 1:
+        raise ArgumentError("Please supply at least 1 distance metric. Choose from:\n\t‣ " +
+                            "\n\t‣ ".join(RECOGNISED_DISTANCE_METRICS))
+    bad = [m for m in metrics if m not in RECOGNISED_DISTANCE_METRICS]
+    if bad:
+        raise ArgumentError("Unrecognised metric/s:\n\t‣ " + "\n\t‣ ".join(bad) + "\nPlease choose from:\n\t‣ " +
+                            "\n\t‣ ".join(RECOGNISED_DISTANCE_METRICS))
+    A = genomes.allele_frequencies
+    n, p = A.shape
+    if idx_loci_alleles is None:
+        if verbose:
+            print("Warning: Randomly sampling 100 loci-alleles")
+        if p < 100:
+            raise ArgumentError("Cannot take a sample of 100 loci-alleles without replacement from fewer than 100.")
+        idx = np.sort(np.random.default_rng(seed).choice(p, 100, replace=False)) + 1
+    else:
+        idx = np.asarray(idx_loci_alleles, dtype=np.int64)
+        if idx.size == 0 or idx.min() < 1 or idx.max() > p:
+            raise ArgumentError("We accept `idx_loci_alleles` from 1 to `n_loci_alleles` of `genomes`.")
+        idx = np.unique(idx)  # unique(sort(...)), genomes.jl:500
+    t = int(idx.size)
+    idx0 = np.ascontiguousarray(idx - 1, dtype=np.int64)
+    ctx = ctx or _lib.default_context()
+    if A.dtype != np.float64 or A.strides[0] != 8 or (p > 1 and (A.strides[1] % 8 or A.strides[1] < 8 * n)):
+        A = np.asfortranarray(A, dtype=np.float64)
+    lda = A.strides[1] // 8 if p > 1 else n
+    slot = {"euclidean": 0, "correlation": 1, "mad": 2, "rmsd": 3, "χ²": 4}
+    out = {}
+    for dim_name, dim, r, on in (("loci_alleles", _lib.DIM_LOCI, t, include_loci_alleles and t > 1),
+                                 ("entries", _lib.DIM_ENTRIES, n, include_entries and n > 1)):
+        if not on:
+            continue
+        mats = [None] * 6
+        for m in metrics:
+            mats[slot[m]] = np.empty((r, r), dtype=np.float64, order="F")
+        if include_counts:
+            mats[5] = np.empty((r, r), dtype=np.float64, order="F")
+        ptrs = [x.ctypes.data if x is not None else None for x in mats]
+        try:
+            _lib.check(ctx.lib.grm_cuda_distances(ctx.handle, A.ctypes.data, n, p, lda, _lib.LOC_HOST, idx0.ctypes.data, t,
+                                                  dim, *ptrs, r, _lib.LOC_HOST))
+        except _lib.GrmCudaError as e:
+            _raise_for(e)
+        for m in metrics:
+            out[f"{dim_name}|{m}"] = mats[slot[m]]
+        if include_counts:
+            out[f"{dim_name}|counts"] = mats[5]
+    if not out:
+        raise ErrorException("Genomes struct is too sparse. No distance matrix was calculated.")
+    return [genomes.loci_alleles[k] for k in idx0], list(genomes.entries), out

@@ -169,6 +169,25 @@ int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t n, int64_t
                           int64_t ldu, int32_t u_location);
 int32_t grm_cuda_last_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_t u_location);
 
+/* ---- distances(genomes) ------------------------------------------------------------------------
+ * Replaces the pair loops of distances (src/genomes/genomes.jl:454-654): for the sorted, unique loci-alleles
+ * idx_loci[0..t) (0-based HOST array) one matrix per requested metric, over pairs of loci (dimension =
+ * GRM_CUDA_DIM_LOCI: t x t, vectors of length n) or pairs of entries (GRM_CUDA_DIM_ENTRIES: n x n, vectors of length t).
+ * A pair uses the positions where both vectors are non-NaN (= non-missing) and finite; with fewer than 2 of them the
+ * element keeps the reference's fill value (+Inf; -Inf for correlation; 0 in counts).  Metrics as in genomes.jl:556-569
+ * and :617-631: euclidean, correlation (cor; -Inf when either variance < 1e-7), mad, rmsd, chi2 = sum((y1-y2)^2 /
+ * (y2 + eps)).  Loci pairs follow the reference's i <= j loop: D[j,i] = D[i,j] (chi2 takes the lower-indexed locus as
+ * y1) and counts fill the upper triangle only; entry pairs are evaluated for every ordered (i, j).
+ * Output pointers that are NULL are skipped; the others are r x r column-major with leading dimension ldo (r = t or n).
+ * "covariance" is in the reference's default metric list but not in its list of recognised metrics (:470), so it can
+ * never be computed there and is not offered here.  Synchronises the stream. */
+#define GRM_CUDA_DIM_LOCI    0
+#define GRM_CUDA_DIM_ENTRIES 1
+int32_t grm_cuda_distances(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda, int32_t a_location,
+                           const int64_t *idx_loci, int64_t t, int32_t dimension, double *euclidean,
+                           double *correlation, double *mad, double *rmsd, double *chi2, double *counts, int64_t ldo,
+                           int32_t out_location);
+
 /* ---- staged device-side API (all pointers are DEVICE pointers; work is enqueued on the context stream) ------
  * These are the pieces the three entry points are assembled from.  They exist so that parity tests can look at
  * intermediate results (integer Gram matrix, q, d) and so that a multi-GPU host (one process per GPU) can put its

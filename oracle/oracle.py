@@ -261,3 +261,70 @@ def np_inflatediagonals(X, max_iter=1000):
         tot += e
         e *= 1.0 + EPS
     return OK, X, it, tot
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# distances(genomes) (src/genomes/genomes.jl:454-654), restated pair by pair
+# ---------------------------------------------------------------------------------------------------------------
+def _pair_metric(metric, y1, y2):
+    """genomes.jl:556-569 / :617-631 for one pair restricted to its jointly usable positions; None = `continue`."""
+    if metric == "euclidean":
+        return float(np.sqrt(np.sum((y1 - y2) ** 2)))
+    if metric == "correlation":
+        if np.var(y1, ddof=1) < 1e-7 or np.var(y2, ddof=1) < 1e-7:
+            return None
+        u, v = y1 - np.mean(y1), y2 - np.mean(y2)
+        xx, yy, xy = float(np.sum(u * u)), float(np.sum(v * v)), float(np.sum(u * v))
+        hi, lo = max(xx, yy), min(xx, yy)
+        return float(min(1.0, max(-1.0, xy / hi / np.sqrt(lo / hi))))  # Statistics.corm + clampcor
+    if metric == "mad":
+        return float(np.mean(np.abs(y1 - y2)))
+    if metric == "rmsd":
+        return float(np.sqrt(np.mean((y1 - y2) ** 2)))
+    if metric == "χ²":
+        return float(np.sum((y1 - y2) ** 2 / (y2 + EPS)))
+    raise ValueError(metric)
+
+
+def np_distances(A, idx_loci0, metrics, include_counts=True):
+    """Dict "dimension|metric" -> matrix for the loci idx_loci0 (0-based, sorted, unique) of A (n x p, NaN = missing),
+    following the reference's loops: loci pairs i <= j mirrored (counts upper triangle only), entry pairs all (i, j);
+    fill +Inf (-Inf for correlation); pairs with fewer than 2 jointly usable positions keep the fill."""
+    A = np.asarray(A, dtype=np.float64)
+    S = A[:, idx_loci0]
+    n, t = S.shape
+    ok = np.isfinite(S)
+    out = {}
+    if t > 1:
+        for m in metrics:
+            D = np.full((t, t), -np.inf if m == "correlation" else np.inf)
+            cnt = np.zeros((t, t))
+            for i in range(t):
+                for j in range(i, t):
+                    use = ok[:, i] & ok[:, j]
+                    if use.sum() < 2:
+                        continue
+                    cnt[i, j] = use.sum()
+                    v = _pair_metric(m, S[use, i], S[use, j])
+                    if v is not None:
+                        D[i, j] = D[j, i] = v
+            out[f"loci_alleles|{m}"] = D
+            if include_counts:
+                out["loci_alleles|counts"] = cnt
+    if n > 1:
+        for m in metrics:
+            D = np.full((n, n), -np.inf if m == "correlation" else np.inf)
+            cnt = np.zeros((n, n))
+            for i in range(n):
+                for j in range(n):
+                    use = ok[i] & ok[j]
+                    if use.sum() < 2:
+                        continue
+                    cnt[i, j] = use.sum()
+                    v = _pair_metric(m, S[i, use], S[j, use])
+                    if v is not None:
+                        D[i, j] = v
+            out[f"entries|{m}"] = D
+            if include_counts:
+                out["entries|counts"] = cnt
+    return out

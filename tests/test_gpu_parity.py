@@ -777,3 +777,88 @@ def test_simulatecovariancekinship_and_lookup_by_entry_name():
     names2 = [f"site_1 {g.entries[0]}", f"site_2 {g.entries[1]}", f"site_1 {g.entries[1]}"]
     Sig2 = grm_b200.covariance_from_grm(grm, names2)
     assert Sig2[0, 1] == 0.0 and Sig2[0, 2] != 0.0 and Sig2[1, 2] != 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# distances(genomes): every metric, both dimensions, against the pair-by-pair restatement
+# ---------------------------------------------------------------------------------------------------------------
+RTOL_DIST = 1e-12  # FP64 sums of <= a few thousand terms in a different order than Julia's SIMD sum
+
+
+def _assert_dist_equal(got, ref, key):
+    assert got.shape == ref.shape, key
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin), f"{key}: fill pattern differs"
+    assert np.array_equal(got[~fin], ref[~fin]), f"{key}: fill values differ"  # +Inf / -Inf placed identically
+    if "counts" in key:
+        assert np.array_equal(got, ref), key
+    elif fin.any():
+        scale = max(np.abs(ref[fin]).max(), 1e-300)
+        assert np.abs(got[fin] - ref[fin]).max() <= RTOL_DIST * scale, (key, np.abs(got[fin] - ref[fin]).max(), scale)
+
+
+@pytest.mark.parametrize("n,p,t,missing", [(40, 300, 25, 0.0), (70, 500, 100, 0.15), (33, 64, 64, 0.5), (5, 200, 3, 0.0)])
+def test_distances_match_the_pairwise_restatement(n, p, t, missing):
+    rng = np.random.default_rng(100 + n)
+    A = synth.continuous(n, p, seed=n)
+    if missing > 0:
+        A[rng.random(A.shape) < missing] = np.nan
+        A[0, :] = np.nan                      # an entry with no data at all: every pair with it keeps the fill
+        A[1, 2:] = np.nan                     # an entry with at most 2 usable loci
+        A[:, 5] = 0.25                        # a constant locus: var < 1e-7 -> correlation stays -Inf
+        A[3, 7] = np.inf                      # non-finite cells are excluded like missing ones
+    idx1 = np.sort(rng.choice(p, t, replace=False)) + 1          # 1-based, like the Julia argument
+    if missing > 0:
+        idx1 = np.unique(np.concatenate([idx1, [6, 8]]))          # make sure the special loci are in
+    g = Genomes.from_matrix(A)
+    metrics = ["euclidean", "correlation", "mad", "rmsd", "χ²"]
+    names, entries, got = grm_b200.distances(g, metrics, idx1.tolist())
+    ref = O.np_distances(A, idx1 - 1, metrics)
+    assert sorted(got) == sorted(ref)
+    assert names == [g.loci_alleles[k - 1] for k in idx1] and entries == g.entries
+    for key in ref:
+        _assert_dist_equal(got[key], ref[key], key)
+    # the reference's doctest properties (genomes.jl:440-452)
+    if missing == 0.0:
+        C = got["entries|correlation"]
+        assert np.array_equal(np.diag(C), np.ones(n))
+        X = got["loci_alleles|χ²"]
+        assert np.array_equal(np.diag(X), np.zeros(len(idx1)))
+    # entries|χ² is not symmetric, loci_alleles|χ² is (mirrored upper triangle); loci counts are upper-triangular
+    assert np.array_equal(got["loci_alleles|χ²"], got["loci_alleles|χ²"].T)
+    assert np.array_equal(np.tril(got["loci_alleles|counts"], -1), np.zeros_like(got["loci_alleles|counts"]))
+
+
+def test_distances_argument_handling_and_device_buffers(ctx):
+    import ctypes as C
+
+    import torch
+
+    g = Genomes.from_matrix(synth.continuous(20, 150, seed=2))
+    with pytest.raises(ArgumentError):
+        grm_b200.distances(g, ["euclidean", "covariance"], [1, 2, 3])   # not a recognised metric (genomes.jl:470)
+    with pytest.raises(ArgumentError):
+        grm_b200.distances(g, [], [1, 2, 3])
+    with pytest.raises(ArgumentError):
+        grm_b200.distances(g, ["mad"], [0, 1])                           # 1-based range check (genomes.jl:497-499)
+    with pytest.raises(grm_b200.ErrorException):
+        grm_b200.distances(g, ["mad"], [1, 2], include_loci_alleles=False, include_entries=False)
+    # duplicates and order are normalised like unique(sort(idx)); subsets of the outputs
+    _, _, d = grm_b200.distances(g, ["mad"], [9, 3, 3, 7], include_entries=False, include_counts=False)
+    assert sorted(d) == ["loci_alleles|mad"] and d["loci_alleles|mad"].shape == (3, 3)
+    _, _, d100 = grm_b200.distances(g, ["rmsd"])                         # default: 100 sampled loci
+    assert d100["loci_alleles|rmsd"].shape == (100, 100) and d100["entries|counts"].max() == 100
+    # device-resident input and output through the C ABI, leading dimension larger than the matrix
+    A = g.allele_frequencies
+    n, p = A.shape
+    At = to_dev(A)
+    idx0 = np.array([2, 5, 11, 40, 41, 149], dtype=np.int64)
+    out = torch.full((n, n + 3), -7.0, dtype=torch.float64, device=dev())  # column-major n x n with ld = n + 3
+    torch.cuda.synchronize()
+    _lib.check(ctx.lib.grm_cuda_distances(ctx.handle, C.c_void_p(At.data_ptr()), n, p, n, _lib.LOC_DEVICE,
+                                          idx0.ctypes.data, len(idx0), _lib.DIM_ENTRIES, C.c_void_p(out.data_ptr()),
+                                          None, None, None, None, None, n + 3, _lib.LOC_DEVICE))
+    got = out.cpu().numpy()  # (n, ld) row-major == column-major ld x n: got[j, i] is element (i, j)
+    ref = O.np_distances(A, idx0, ["euclidean"])["entries|euclidean"]
+    assert np.abs(got[:, :n].T - ref).max() <= RTOL_DIST * ref.max()
+    assert np.all(got[:, n:] == -7.0)                                    # padding rows untouched

@@ -147,3 +147,26 @@ def test_qc_keep_and_meanfill_follow_the_filter_rules():
     assert not np.isnan(F).any()
     assert F[0, 2] == (0.5 + 0.5 + 1.0) / 3 and F[3, 3] == 1.0
     assert np.array_equal(F[~np.isnan(A[:, :4])], A[:, :4][~np.isnan(A[:, :4])])
+
+
+def test_distances_restatement_reproduces_the_reference_doctest():
+    """src/genomes/genomes.jl:440-452: keys of the returned Dict, correlation diagonal == 1, χ² diagonal == 0."""
+    from grm_b200 import synth
+
+    A = synth.continuous(100, 1000, seed=42)
+    idx = np.sort(np.random.default_rng(1).choice(1000, 100, replace=False))
+    d = O.np_distances(A, idx, ["correlation", "χ²"])
+    assert sorted(d) == ["entries|correlation", "entries|counts", "entries|χ²", "loci_alleles|correlation",
+                         "loci_alleles|counts", "loci_alleles|χ²"]
+    assert np.array_equal(np.diag(d["entries|correlation"]), np.ones(100))
+    assert np.array_equal(np.diag(d["loci_alleles|χ²"]), np.zeros(100))
+    # pairs with fewer than 2 jointly usable positions keep the fill; a constant vector has no correlation
+    B = A[:6, :8].copy()
+    B[:, 3] = 0.5
+    B[0, :] = np.nan
+    B[1, 1:] = np.nan
+    e = O.np_distances(B, np.arange(8), ["correlation", "euclidean"])
+    assert np.all(np.isneginf(e["entries|correlation"][0])) and np.all(np.isposinf(e["entries|euclidean"][0]))
+    assert np.isposinf(e["entries|euclidean"][1, 2]) and e["entries|counts"][1, 2] == 0
+    assert np.all(np.isneginf(e["loci_alleles|correlation"][3]))  # the constant locus
+    assert np.isfinite(e["loci_alleles|euclidean"][3, 4])
