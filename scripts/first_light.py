@@ -434,6 +434,34 @@ def stage_pack_occ():
 STAGES["pack_occ"] = stage_pack_occ
 
 
+def stage_distances():
+    """distances(genomes) pair kernel: entries x entries and loci x loci at C3's entry count (device-resident input)."""
+    import ctypes as C
+    from grm_b200 import _lib
+    ctx = grm_b200.default_context(0)
+    for (n, p, t, what) in [(20000, 2000, 100, ("euclidean", "correlation", "mad", "rmsd", "chi2")),
+                            (20000, 2000, 100, ("euclidean",)), (5000, 4000, 2000, ("euclidean", "correlation", "mad", "rmsd", "chi2"))]:
+        At = synth.continuous_device(n, p, 3, dev)
+        idx0 = np.sort(np.random.default_rng(0).choice(p, t, replace=False)).astype(np.int64)
+        for dim, r, c in ((_lib.DIM_ENTRIES, n, t), (_lib.DIM_LOCI, t, n)):
+            mats = {k: torch.empty((r, r), dtype=torch.float64, device=dev) for k in what}
+            cnt = torch.empty((r, r), dtype=torch.float64, device=dev)
+            ptr = lambda k: C.c_void_p(mats[k].data_ptr()) if k in mats else None
+            torch.cuda.synchronize()
+            def call():
+                _lib.check(ctx.lib.grm_cuda_distances(ctx.handle, C.c_void_p(At.data_ptr()), n, p, n, _lib.LOC_DEVICE,
+                                                      idx0.ctypes.data, t, dim, ptr("euclidean"), ptr("correlation"), ptr("mad"),
+                                                      ptr("rmsd"), ptr("chi2"), C.c_void_p(cnt.data_ptr()), r, _lib.LOC_DEVICE))
+            tms, ts = ev_time(call, ctx, reps=3)
+            pe = float(r) * r * c
+            print(f"[distances n={n} t={t} dim={'entries' if dim else 'loci'} metrics={len(what)}] {tms:.3f} ms -> "
+                  f"{pe / tms / 1e6:.1f} G pair-elements/s ({r}x{r} pairs x {c} positions)", flush=True)
+        del At
+
+
+STAGES["distances"] = stage_distances
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:
