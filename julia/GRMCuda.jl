@@ -12,6 +12,7 @@ module GRMCuda
 
 using GenomicBreedingCore: Genomes, GRM, checkdims
 import LinearAlgebra
+import StatsBase
 
 const LIB = get(ENV, "GRM_CUDA_LIB", joinpath(@__DIR__, "..", "genomicbreedingcore.jl_b200", "libgrm_cuda.so"))
 
@@ -159,6 +160,55 @@ function lastfactor(n::Integer)::Matrix{Float64}
         context(), n, U, n, 0)
     st == 0 || throwstatus(st)
     U
+end
+
+# ---- distances(genomes) (SURVEY.md §8 f4; src/genomes/genomes.jl:454-654) -------------------------------------------
+# Same keyword arguments and return value as the reference; the pair loops run in grm_cuda_distances.
+function distances(genomes::Genomes;
+        distance_metrics::Vector{String} = ["euclidean", "correlation", "mad", "rmsd", "χ²"],
+        idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing, include_loci_alleles::Bool = true,
+        include_entries::Bool = true, include_counts::Bool = true,
+        verbose::Bool = false)::Tuple{Vector{String},Vector{String},Dict{String,Matrix{Float64}}}
+    checkdims(genomes) || throw(ArgumentError("The genomes struct is corrupted ☹."))
+    recognised = ["euclidean", "correlation", "mad", "rmsd", "χ²"]
+    metrics = unique(distance_metrics)
+    length(metrics) >= 1 || throw(ArgumentError("Please supply at least 1 distance metric. Choose from:\n\t‣ " * join(recognised, "\n\t‣ ")))
+    bad = filter(m -> !(m in recognised), metrics)
+    isempty(bad) || throw(ArgumentError("Unrecognised metric/s:\n\t‣ " * join(bad, "\n\t‣ ") * "\nPlease choose from:\n\t‣ " * join(recognised, "\n\t‣ ")))
+    A = dense(genomes.allele_frequencies)
+    n, p = size(A)
+    idx = if isnothing(idx_loci_alleles)
+        sort(StatsBase.sample(1:p, 100, replace = false))
+    else
+        (minimum(idx_loci_alleles) < 1 || maximum(idx_loci_alleles) > p) &&
+            throw(ArgumentError("We accept `idx_loci_alleles` from 1 to `n_loci_alleles` of `genomes`."))
+        unique(sort(idx_loci_alleles))
+    end
+    t = length(idx)
+    idx0 = Int64.(idx .- 1)
+    slot = Dict("euclidean" => 1, "correlation" => 2, "mad" => 3, "rmsd" => 4, "χ²" => 5)
+    out = Dict{String,Matrix{Float64}}()
+    for (name, dim, r, on) in (("loci_alleles", 0, t, include_loci_alleles && t > 1), ("entries", 1, n, include_entries && n > 1))
+        on || continue
+        mats = Vector{Union{Nothing,Matrix{Float64}}}(nothing, 6)
+        for m in metrics
+            mats[slot[m]] = Matrix{Float64}(undef, r, r)
+        end
+        include_counts && (mats[6] = Matrix{Float64}(undef, r, r))
+        ptr(x) = isnothing(x) ? Ptr{Float64}(C_NULL) : pointer(x)
+        st = GC.@preserve A idx0 mats ccall((:grm_cuda_distances, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int32, Ptr{Int64}, Int64, Int32, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int32),
+            context(), A, n, p, n, 0, idx0, t, dim, ptr(mats[1]), ptr(mats[2]), ptr(mats[3]), ptr(mats[4]), ptr(mats[5]),
+            ptr(mats[6]), r, 0)
+        st == 0 || throwstatus(st)
+        for m in metrics
+            out[string(name, "|", m)] = mats[slot[m]]
+        end
+        include_counts && (out[string(name, "|counts")] = mats[6])
+    end
+    isempty(out) && throw(ErrorException("Genomes struct is too sparse. No distance matrix was calculated."))
+    (genomes.loci_alleles[idx], genomes.entries, out)
 end
 
 end # module
