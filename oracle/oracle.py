@@ -286,7 +286,7 @@ def _pair_metric(metric, y1, y2):
     raise ValueError(metric)
 
 
-def np_distances(A, idx_loci0, metrics, include_counts=True):
+def np_distances(A, idx_loci0, metrics, include_counts=True, dims=("loci_alleles", "entries")):
     """Dict "dimension|metric" -> matrix for the loci idx_loci0 (0-based, sorted, unique) of A (n x p, NaN = missing),
     following the reference's loops: loci pairs i <= j mirrored (counts upper triangle only), entry pairs all (i, j);
     fill +Inf (-Inf for correlation); pairs with fewer than 2 jointly usable positions keep the fill."""
@@ -295,7 +295,7 @@ def np_distances(A, idx_loci0, metrics, include_counts=True):
     n, t = S.shape
     ok = np.isfinite(S)
     out = {}
-    if t > 1:
+    if t > 1 and "loci_alleles" in dims:
         for m in metrics:
             D = np.full((t, t), -np.inf if m == "correlation" else np.inf)
             cnt = np.zeros((t, t))
@@ -311,7 +311,7 @@ def np_distances(A, idx_loci0, metrics, include_counts=True):
             out[f"loci_alleles|{m}"] = D
             if include_counts:
                 out["loci_alleles|counts"] = cnt
-    if n > 1:
+    if n > 1 and "entries" in dims:
         for m in metrics:
             D = np.full((n, n), -np.inf if m == "correlation" else np.inf)
             cnt = np.zeros((n, n))

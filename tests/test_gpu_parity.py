@@ -829,6 +829,29 @@ def test_distances_match_the_pairwise_restatement(n, p, t, missing):
     assert np.array_equal(np.tril(got["loci_alleles|counts"], -1), np.zeros_like(got["loci_alleles|counts"]))
 
 
+@pytest.mark.parametrize("n,p,t,dims", [(3000, 20, 20, ("loci_alleles",)), (40, 1200, 1000, ("loci_alleles", "entries")),
+                                         (700, 33, 33, ("loci_alleles",))])
+def test_distances_split_form_for_few_pairs_and_long_vectors(n, p, t, dims):
+    """Few pairs over long vectors (the reference's default: 100 loci x 100 loci over all entries) run as position
+    slices + fixed-order reductions; same results as the pair-by-pair restatement."""
+    rng = np.random.default_rng(n + t)
+    A = synth.continuous(n, p, seed=n + 1)
+    A[rng.random(A.shape) < 0.05] = np.nan
+    A[:, 3] = 0.75
+    idx1 = np.sort(rng.choice(p, t, replace=False)) + 1
+    g = Genomes.from_matrix(A)
+    metrics = ["euclidean", "correlation", "mad", "rmsd", "χ²"]
+    _, _, got = grm_b200.distances(g, metrics, idx1.tolist(), include_entries="entries" in dims)
+    ref = O.np_distances(A, idx1 - 1, metrics, dims=dims)
+    assert sorted(got) == sorted(ref)
+    for key in ref:
+        _assert_dist_equal(got[key], ref[key], key)
+    # deterministic: a second call gives the same bits
+    _, _, again = grm_b200.distances(g, metrics, idx1.tolist(), include_entries="entries" in dims)
+    for key in got:
+        assert np.array_equal(got[key], again[key], equal_nan=True), key
+
+
 def test_distances_argument_handling_and_device_buffers(ctx):
     import ctypes as C
 
