@@ -255,6 +255,7 @@ constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 // slowest pair never waits (no deadlock; all CTAs of the grid are co-resident: one per SM), and with a static tile
 // assignment the fast pairs would only have idled at the end anyway.  Measured on C3: 102 ms -> 66 ms.
 constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW_DEFAULT = 64;
+constexpr long EPI_SLEEP_DEFAULT = 0;  // ns
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
     uint32_t v;
@@ -268,7 +269,11 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
-                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_window) {
+                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_params) {
+    // sync_params: low 16 bits = K window of the pair synchronisation, high 16 bits = optional back-off (ns) of the
+    // epilogue warps while they wait for an accumulator (GRM_CUDA_EPI_SLEEP; measured on C3 at 200 / 1000 / 4000 ns:
+    // no gain over flat-out polling, so the default is 0)
+    const uint32_t sync_window = sync_params & 0xffffu, epi_sleep = sync_params >> 16;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
@@ -397,7 +402,15 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             const int2 tc = tiles[t];
-            mbar_wait(&tmem_full[acc], acc_phase);
+            if (epi_sleep == 0) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+            } else {
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&tmem_full[acc], acc_phase)) {
+                    __nanosleep(epi_sleep);
+                    if (++spins > (1u << 24)) __trap();  // bounded like mbar_wait
+                }
+            }
             tc_fence_after();
             const int64_t row = static_cast<int64_t>(tc.x) + 128 * cta + quarter * 32 + lane;
             const bool row_ok = row < ep.n;
@@ -551,7 +564,10 @@ int32_t sync_buffer(grm_cuda_ctx *ctx, int pairs, int tiles, int64_t operand_byt
 uint32_t sync_window() {
     const char *e = getenv("GRM_CUDA_SYRK_WINDOW");
     const long v = e ? atol(e) : 0;
-    return v > 0 ? static_cast<uint32_t>(v) : SYNC_WINDOW_DEFAULT;
+    const uint32_t window = (v > 0 && v < 65536) ? static_cast<uint32_t>(v) : SYNC_WINDOW_DEFAULT;
+    const char *s = getenv("GRM_CUDA_EPI_SLEEP");  // ns; 0 = poll flat out
+    const long ns = s ? atol(s) : EPI_SLEEP_DEFAULT;
+    return window | (static_cast<uint32_t>(std::max(0l, std::min(ns, 65535l))) << 16);
 }
 
 bool use_2cta() {

@@ -462,6 +462,27 @@ def stage_distances():
 STAGES["distances"] = stage_distances
 
 
+def stage_epi_sleep():
+    """C3 step (serial flow) with the idle epilogue warps polling flat out vs backing off between polls."""
+    ctx = grm_b200.default_context(0)
+    n, p, ploidy = 20000, 500000, 4
+    A = torch.empty((p, n), dtype=torch.float64, device=dev)
+    for c0 in range(0, p, 2500):
+        A[c0:c0 + 2500] = synth.dosage_device(n, 2500, ploidy, 1000 + c0 // 2500, dev, chunk=2500)
+    G = torch.empty((n, n), dtype=torch.float64, device=dev)
+    for rep in range(3):
+        for ns in ("0", "200", "1000", "4000"):
+            os.environ["GRM_CUDA_EPI_SLEEP"] = ns
+            infos = []
+            t, ts = ev_time(lambda: infos.append(D.grm_device(ctx, A, ploidy, denominator=ploidy, skip_repair=True, out=G)[1]),
+                            ctx, reps=4)
+            print(f"[C3 epi_sleep={ns} ns] best {t:.2f} ms mean {sum(ts)/len(ts):.2f} syrk {infos[-1]['ms_syrk']:.2f}", flush=True)
+    os.environ.pop("GRM_CUDA_EPI_SLEEP", None)
+
+
+STAGES["epi_sleep"] = stage_epi_sleep
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or list(STAGES)
     for nm in names:
