@@ -56,3 +56,40 @@ def test_synthetic_generators_have_the_simulator_shape():
     assert set(np.unique(D)) <= {0.0, 0.25, 0.5, 0.75, 1.0}
     M = synth.add_missing(D, 0.1, seed=1)
     assert np.isnan(M).sum() == round(0.1 * 50 * 400)  # simulate_genomes.jl:738
+
+
+def test_distances_validates_like_the_reference_before_any_gpu_work():
+    # genomes.jl:463-500 — corrupted struct, metric list, index range; all raised before the backend is touched
+    g = Genomes.from_matrix(synth.continuous(6, 120, seed=3))
+    with pytest.raises(ArgumentError, match="Unrecognised metric/s"):
+        grm_b200.distances(g, ["euclidean", "covariance"], [1, 2])   # "covariance" is not recognised (:470)
+    with pytest.raises(ArgumentError, match="at least 1 distance metric"):
+        grm_b200.distances(g, [], [1, 2])
+    with pytest.raises(ArgumentError, match="from 1 to `n_loci_alleles`"):
+        grm_b200.distances(g, ["mad"], [0, 5])
+    with pytest.raises(ArgumentError, match="from 1 to `n_loci_alleles`"):
+        grm_b200.distances(g, ["mad"], [1, 121])
+    small = Genomes.from_matrix(synth.continuous(6, 50, seed=3))
+    with pytest.raises(ArgumentError, match="sample of 100"):
+        grm_b200.distances(small, ["mad"])                            # sample(1:50, 100, replace = false) throws too
+    g.populations = g.populations[:-1]
+    with pytest.raises(ArgumentError, match="corrupted"):
+        grm_b200.distances(g, ["mad"], [1, 2])
+
+
+def test_simulatecovariancekinship_checks_the_entry_count_first():
+    g = Genomes.from_matrix(synth.continuous(6, 120, seed=3))
+    with pytest.raises(ArgumentError, match="p must match the number of entries"):  # simulate_effects.jl:345-347
+        grm_b200.simulatecovariancekinship(7, g)
+
+
+def test_product_package_never_imports_the_oracle():
+    # the oracle is test infrastructure: nothing under the package may import, load or execute it
+    import pathlib
+    import re
+
+    pkg = pathlib.Path(grm_b200.__file__).parent
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libgrm_oracle|grm_oracle", re.M)
+    for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        if path.is_file() and path.suffix in (".py", ".cu", ".cuh", ".cpp", ".h", "") and path.name != "Makefile":
+            assert not pat.search(path.read_text(errors="ignore")), path
