@@ -298,3 +298,32 @@ def distances(genomes: Genomes, distance_metrics=None, idx_loci_alleles=None, in
     if not out:
         raise ErrorException("Genomes struct is too sparse. No distance matrix was calculated.")
     return [genomes.loci_alleles[k] for k in idx0], list(genomes.entries), out
+
+
+def estimateld(genomes: Genomes, chromosomes=None, verbose: bool = False, *, ctx: Optional[_lib.Context] = None):
+    """estimateld(genomes; chromosomes, verbose) (src/genomes/impute.jl:172-279): per chromosome (or per caller-defined
+    scaffold label of each locus-allele) the loci x loci correlation matrix `distances(...)["loci_alleles|correlation"]`
+    over all its loci.  Returns (sorted unique chromosomes, list of matrices; None where a chromosome has fewer than 2
+    loci — the reference leaves that slot undefined).  The reference's JLD2 checkpoint / resume files are storage, not
+    arithmetic, and are not reproduced."""
+    if not checkdims(genomes):
+        raise ArgumentError("The Genomes struct is corrupted ☹.")
+    if chromosomes is None:
+        chromosomes = [x.split("\t")[0] for x in genomes.loci_alleles]
+    chromosomes = [str(c) for c in chromosomes]
+    if len(chromosomes) != len(genomes.loci_alleles):
+        raise ArgumentError("`chromosomes` must label every locus-allele of `genomes`.")
+    chroms_uniq = sorted(set(chromosomes))
+    lab = np.asarray(chromosomes)
+    LDs = []
+    for i, chrom in enumerate(chroms_uniq):
+        if verbose:
+            print(f"Esimtating LD of chromosome: {chrom} ({i + 1} of {len(chroms_uniq)})")
+        idx = np.flatnonzero(lab == chrom) + 1
+        if idx.size < 2:
+            LDs.append(None)
+            continue
+        _, _, corr = distances(genomes, ["correlation"], idx.tolist(), include_loci_alleles=True, include_counts=False,
+                               include_entries=False, verbose=verbose, ctx=ctx)
+        LDs.append(corr["loci_alleles|correlation"])
+    return chroms_uniq, LDs

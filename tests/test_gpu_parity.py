@@ -885,3 +885,27 @@ def test_distances_argument_handling_and_device_buffers(ctx):
     ref = O.np_distances(A, idx0, ["euclidean"])["entries|euclidean"]
     assert np.abs(got[:, :n].T - ref).max() <= RTOL_DIST * ref.max()
     assert np.all(got[:, n:] == -7.0)                                    # padding rows untouched
+
+
+def test_estimateld_per_chromosome_correlation_matrices():
+    """estimateld (src/genomes/impute.jl:172-279): one loci x loci correlation matrix per chromosome / scaffold label."""
+    n, per = 60, [40, 1, 75]
+    A = synth.continuous(n, sum(per), seed=77)
+    A[np.random.default_rng(5).random(A.shape) < 0.3] = np.nan      # the doctest uses sparsity = 0.3
+    names = [f"chrom_{c + 1}\t{k + 1}\tA|T\tA" for c, m in enumerate(per) for k in range(m)]
+    g = Genomes.from_matrix(A, loci_alleles=names)
+    chroms, LDs = grm_b200.estimateld(g)
+    assert chroms == ["chrom_1", "chrom_2", "chrom_3"] and len(LDs) == 3
+    assert LDs[1] is None                                            # fewer than 2 loci: skipped (impute.jl:252-254)
+    off = 0
+    for c, m in enumerate(per):
+        if m >= 2:
+            ref = O.np_distances(A, np.arange(off, off + m), ["correlation"], dims=("loci_alleles",))
+            _assert_dist_equal(LDs[c], ref["loci_alleles|correlation"], f"chrom_{c + 1}")
+            dg = np.diag(LDs[c])
+            assert np.all((dg == 1.0) | np.isneginf(dg))               # -Inf: a locus with var < 1e-7 (genomes.jl:560)
+        off += m
+    # caller-defined scaffolds (divideintomockscaffolds-style labels)
+    labels = [f"mock_{k // 29}" for k in range(sum(per))]
+    chroms2, LDs2 = grm_b200.estimateld(g, chromosomes=labels)
+    assert chroms2 == sorted(set(labels)) and [x.shape[0] for x in LDs2] == [labels.count(c) for c in chroms2]
