@@ -440,10 +440,13 @@ def stage_distances():
     from grm_b200 import _lib
     ctx = grm_b200.default_context(0)
     for (n, p, t, what) in [(20000, 2000, 100, ("euclidean", "correlation", "mad", "rmsd", "chi2")),
-                            (20000, 2000, 100, ("euclidean",)), (5000, 4000, 2000, ("euclidean", "correlation", "mad", "rmsd", "chi2"))]:
+                            (20000, 2000, 100, ("euclidean",)), (5000, 4000, 2000, ("euclidean", "correlation", "mad", "rmsd", "chi2")),
+                            (1000, 8192, 8192, ("correlation",))]:  # estimateld scale: one chromosome of 8192 loci
         At = synth.continuous_device(n, p, 3, dev)
         idx0 = np.sort(np.random.default_rng(0).choice(p, t, replace=False)).astype(np.int64)
         for dim, r, c in ((_lib.DIM_ENTRIES, n, t), (_lib.DIM_LOCI, t, n)):
+            if what == ("correlation",) and dim == _lib.DIM_ENTRIES:
+                continue
             mats = {k: torch.empty((r, r), dtype=torch.float64, device=dev) for k in what}
             cnt = torch.empty((r, r), dtype=torch.float64, device=dev)
             ptr = lambda k: C.c_void_p(mats[k].data_ptr()) if k in mats else None
