@@ -400,7 +400,8 @@ def run_b200(args, wl):
             dt = float(t[0])
             d2h = 8 * n * n if rank == 0 else 0
             e2e_detail = {"repair_iters": it, "eps_total": tot, "pinned": pinned,
-                          "includes": "per-rank H2D of its loci slab, pack, all-gather, stats, rowdot, SYRK, all-reduce gather, "
+                          "includes": "per-rank H2D of its loci slab, pack, integer statistics + int64 all-reduce, SYRK over own loci, "
+                                      "int32 reduce-scatter onto the tile owners, finalize, all-reduce gather of G, "
                                       "inflatediagonals! with its rounds probed in parallel (one per rank), D2H on rank 0"}
         e2e = {"value": macs(n, p) / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3, "steps": esteps, **e2e_detail}
