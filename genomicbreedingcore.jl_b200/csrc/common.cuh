@@ -227,6 +227,16 @@ __device__ __forceinline__ void tma_load_3d_2cta(void *smem_dst, const void *tma
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// The same load multicast to the CTAs of `mask` (same shared-memory offset in each); each destination's bytes are
+// credited to the mbarrier at the same offset in the LEADER of the destination's CTA pair
+__device__ __forceinline__ void tma_load_3d_2cta_mc(void *smem_dst, const void *tmap, uint64_t *bar, int32_t c0, int32_t c1,
+                                                    int32_t c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void umma_i8_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(

@@ -255,7 +255,7 @@ constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 // slowest pair never waits (no deadlock; all CTAs of the grid are co-resident: one per SM), and with a static tile
 // assignment the fast pairs would only have idled at the end anyway.  Measured on C3: 102 ms -> 66 ms.
 constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW_DEFAULT = 64;
-constexpr long EPI_SLEEP_DEFAULT = 0;  // ns
+constexpr bool SYRK_QUAD_DEFAULT = false;  // clusters of 4 with multicast of the shared column panel
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
     uint32_t v;
@@ -266,15 +266,19 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
-syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
-                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_params) {
-    // sync_params: low 16 bits = K window of the pair synchronisation, high 16 bits = optional back-off (ns) of the
-    // epilogue warps while they wait for an accumulator (GRM_CUDA_EPI_SLEEP; measured on C3 at 200 / 1000 / 4000 ns:
-    // no gain over flat-out polling, so the default is 0)
-    const uint32_t sync_window = sync_params & 0xffffu, epi_sleep = sync_params >> 16;
-    extern __shared__ uint8_t smem_raw[];
+// QUAD = false: clusters of 2 (one CTA pair per cluster), one 256 x 256 tile per pair at a time.
+// QUAD = true : clusters of 4 = two CTA pairs working on two consecutive tiles of the list.  Consecutive tiles
+//   share their column panel (tile.y) almost always; then each CTA loads only HALF of its 128-row B block (64 rows,
+//   tmap64) and multicasts it to the CTA of the same parity in the other pair, so that a B row crosses the L2 -> SM
+//   fabric once for both pairs: 24 KB instead of 32 KB per CTA and K block.  The int8 SYRK is fed at the chip's
+//   L2 -> SM limit (pairs: 64 B/clk/SM needed, ~52 sustained; profiles/README.md), so fewer bytes per MAC is what buys
+//   tensor-pipe time.  A shared-memory stage of a CTA is then written by two CTAs, so a stage is released by the
+//   commits of BOTH pairs (empty barriers count 2, commit multicast to all four CTAs): the pairs advance in lock-step.
+template <int EPI, bool QUAD>
+__device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensorMap &tmap, const CUtensorMap &tmap64,
+                                               const int2 *__restrict__ tiles, int num_tiles, int num_kb, int kb_per_slab,
+                                               const EpiParams &ep, uint32_t *__restrict__ progress, uint32_t sync_params) {
+    const uint32_t sync_window = sync_params;  // K window of the pair synchronisation
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
     uint64_t *empty_bar = full_bar + STAGES2;
@@ -286,15 +290,38 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t cta = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t cta = crank & 1u;          // rank inside the CTA pair (0 = leader: issues the MMAs)
+    const uint32_t pbase = crank & ~1u;       // cluster rank of the pair's leader
+    const uint32_t pidx = crank >> 1;         // pair inside the cluster (0 unless QUAD)
     const bool leader = cta == 0;
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    // `pair` = work-group index: a CTA pair (clusters of 2) or a quad (clusters of 4, two tiles at a time)
+    const int pair = QUAD ? (blockIdx.x >> 2) : (blockIdx.x >> 1);
+    const int num_pairs = QUAD ? (gridDim.x >> 2) : (gridDim.x >> 1);
+    const int tiles_per_group = QUAD ? 2 : 1;
+    const int num_units = (num_tiles + tiles_per_group - 1) / tiles_per_group;
+    // tile of this CTA's pair in unit u; QUAD: an odd tail leaves pair 1 without a tile — it then shadows pair 0's tile
+    // (keeps the lock-step barriers balanced) and stores nothing
+    auto unit_tile = [&](int u, int &t, bool &active, bool &shared) {
+        if (!QUAD) {
+            t = u;
+            active = true;
+            shared = false;
+            return;
+        }
+        const int t0 = 2 * u, t1 = 2 * u + 1;
+        const bool has1 = t1 < num_tiles;
+        t = (pidx == 0 || !has1) ? t0 : t1;
+        active = pidx == 0 || has1;
+        shared = !has1 || tiles[t0].y == tiles[t1].y;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
+        if (QUAD) tma_prefetch_desc(&tmap64);
         for (int s = 0; s < STAGES2; ++s) {
             mbar_init(&full_bar[s], 1);   // the leader's arrive.expect_tx covers the bytes of BOTH CTAs (leader only)
-            mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit per use, in each CTA
+            mbar_init(&empty_bar[s], QUAD ? 2 : 1);  // one multicast tcgen05.commit per pair and use, in each CTA
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);   // multicast commit, in each CTA
@@ -317,8 +344,11 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, step = 0;
-            const bool throttle = progress != nullptr && leader;
-            for (int t = pair; t < num_tiles; t += num_pairs) {
+            const bool throttle = progress != nullptr && crank == 0;
+            for (int u = pair; u < num_units; u += num_pairs) {
+                int t;
+                bool active, shared;
+                unit_tile(u, t, active, shared);
                 const int2 tc = tiles[t];
                 int slab = 0, kin = 0;
                 for (int kb = 0; kb < num_kb; ++kb, ++step) {
@@ -336,7 +366,14 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                     // negative, the phase cannot complete before the leader's (only) arrival.
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
                     tma_load_3d_2cta(sA, &tmap, &full_bar[stage], kin * BK, tc.x + 128 * static_cast<int>(cta), slab);
-                    tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, tc.y + 128 * static_cast<int>(cta), slab);
+                    if (QUAD && shared) {
+                        // rows [64 pidx, 64 pidx + 64) of this parity's B block, to both CTAs of this parity
+                        tma_load_3d_2cta_mc(sB + 64 * BK * pidx, &tmap64, &full_bar[stage], kin * BK,
+                                            tc.y + 128 * static_cast<int>(cta) + 64 * static_cast<int>(pidx), slab,
+                                            static_cast<uint16_t>(0b0101u << cta));
+                    } else {
+                        tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, tc.y + 128 * static_cast<int>(cta), slab);
+                    }
                     if (++kin == kb_per_slab) {
                         kin = 0;
                         ++slab;
@@ -354,7 +391,7 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
         }
     } else if (warp == 6) {
         // ===================== K-window watcher (leader CTA) =====================
-        if (progress != nullptr && leader) {
+        if (progress != nullptr && crank == 0) {
             while (*sync_done == 0) {
                 uint32_t mn = 0xffffffffu;
                 for (int i = lane; i < num_pairs; i += 32) mn = min(mn, ld_relaxed_u32(&progress[i]));
@@ -370,7 +407,9 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
+            const uint16_t stage_mask = QUAD ? 0b1111 : 0b11;                     // every CTA that fills this stage
+            const uint16_t pair_mask = static_cast<uint16_t>(0b11u << pbase);     // the two CTAs of this pair
+            for (int u = pair; u < num_units; u += num_pairs, ++local) {
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -385,33 +424,34 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_i8_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_2cta(&empty_bar[stage], 0b11);
+                    umma_commit_2cta(&empty_bar[stage], stage_mask);
                     if (++stage == STAGES2) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit_2cta(&tmem_full[acc], 0b11);
+                umma_commit_2cta(&tmem_full[acc], pair_mask);
             }
         }
     } else {
         // ===================== epilogue (warps 2..5 of both CTAs; CTA r owns rows 128 r .. 128 r + 127) ===========
         const int quarter = warp & 3;
         int local = 0;
-        for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
+        for (int u = pair; u < num_units; u += num_pairs, ++local) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
+            int t;
+            bool active, shared;
+            unit_tile(u, t, active, shared);
             const int2 tc = tiles[t];
-            if (epi_sleep == 0) {
-                mbar_wait(&tmem_full[acc], acc_phase);
-            } else {
-                uint32_t spins = 0;
-                while (!mbar_try_wait(&tmem_full[acc], acc_phase)) {
-                    __nanosleep(epi_sleep);
-                    if (++spins > (1u << 24)) __trap();  // bounded like mbar_wait
-                }
-            }
+            mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            if (!active) {  // shadow tile of an odd tail: nothing to store
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], pbase);
+                continue;
+            }
             const int64_t row = static_cast<int64_t>(tc.x) + 128 * cta + quarter * 32 + lane;
             const bool row_ok = row < ep.n;
             double ui = 0.0;
@@ -458,7 +498,7 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], pbase);
         }
     }
 
@@ -470,7 +510,25 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
     }
 }
 
-int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out) {
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
+                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_params) {
+    extern __shared__ uint8_t smem_raw[];
+    syrk_pair_body<EPI, false>(smem_raw, tmap, tmap, tiles, num_tiles, num_kb, kb_per_slab, ep, progress, sync_params);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+syrk_i8_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
+                    const int2 *__restrict__ tiles, int num_tiles, int num_kb, int kb_per_slab, EpiParams ep,
+                    uint32_t *__restrict__ progress, uint32_t sync_params) {
+    extern __shared__ uint8_t smem_raw[];
+    syrk_pair_body<EPI, true>(smem_raw, tmap, tmap64, tiles, num_tiles, num_kb, kb_per_slab, ep, progress, sync_params);
+}
+
+int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out,
+                        uint32_t box_rows = 128u) {
     GrmEncodeTiledFn encode = nullptr;
     GRM_TRY(grm_tmap_encoder(&encode));
     // dim0 = loci of one slab (bytes, contiguous), dim1 = entries, dim2 = slab.  Out-of-range rows/loci are
@@ -478,7 +536,7 @@ int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc
     // to the integer sums.
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(nslabs)};
     cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ldc), static_cast<cuuint64_t>(ldc) * static_cast<cuuint64_t>(n)};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), 128u, 1u};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), box_rows, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(d_codes), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -565,9 +623,12 @@ uint32_t sync_window() {
     const char *e = getenv("GRM_CUDA_SYRK_WINDOW");
     const long v = e ? atol(e) : 0;
     const uint32_t window = (v > 0 && v < 65536) ? static_cast<uint32_t>(v) : SYNC_WINDOW_DEFAULT;
-    const char *s = getenv("GRM_CUDA_EPI_SLEEP");  // ns; 0 = poll flat out
-    const long ns = s ? atol(s) : EPI_SLEEP_DEFAULT;
-    return window | (static_cast<uint32_t>(std::max(0l, std::min(ns, 65535l))) << 16);
+    return window;
+}
+
+bool use_quad() {
+    const char *e = getenv("GRM_CUDA_SYRK_I8");
+    return e ? !strcmp(e, "quad") : SYRK_QUAD_DEFAULT;
 }
 
 bool use_2cta() {
@@ -588,6 +649,50 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
     CUtensorMap tmap;
     GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
     const int kbs = static_cast<int>((p + BK - 1) / BK);
+    if (use_quad()) {
+        // clusters of 4: two CTA pairs on two consecutive tiles, shared column panel multicast (see syrk_pair_body)
+        const int2 *d_tiles;
+        int count;
+        GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+        if (count == 0) return GRM_CUDA_OK;
+        CUtensorMap tmap64;
+        GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap64, 64u));
+        static bool attrq_set[3] = {false, false, false};
+        static int max_quads[3] = {0, 0, 0};
+        if (!attrq_set[EPI]) {
+            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_quad_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(SMEM2_BYTES)));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / 4 * 4));
+            cfg.blockDim = dim3(NUM_THREADS2);
+            cfg.dynamicSmemBytes = SMEM2_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 4;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int mc = 0;
+            GRM_CUDA_TRY(cudaOccupancyMaxActiveClusters(&mc, syrk_i8_quad_kernel<EPI>, &cfg));
+            max_quads[EPI] = mc;
+            if (getenv("GRM_CUDA_DEBUG")) fprintf(stderr, "[grm_cuda] quad clusters co-resident: %d (SMs %d)\n", mc, ctx->num_sms);
+            attrq_set[EPI] = true;
+        }
+        if (max_quads[EPI] < 1) {
+            grm_set_error("syrk_i8: no 4-CTA cluster of the quad kernel fits this device");
+            return GRM_CUDA_ERR_CUDA;
+        }
+        const int units = (count + 1) / 2;
+        const int quads = std::min(units, std::min(max_quads[EPI], ctx->num_sms / 4));
+        uint32_t *prog = nullptr;
+        GRM_TRY(sync_buffer(ctx, quads, units, n * ldc * nslabs, &prog));
+        syrk_i8_quad_kernel<EPI><<<4 * quads, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
+            tmap, tmap64, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
     if (use_2cta()) {
         const int2 *d_tiles;
         int count;

@@ -909,3 +909,21 @@ def test_estimateld_per_chromosome_correlation_matrices():
     labels = [f"mock_{k // 29}" for k in range(sum(per))]
     chroms2, LDs2 = grm_b200.estimateld(g, chromosomes=labels)
     assert chroms2 == sorted(set(labels)) and [x.shape[0] for x in LDs2] == [labels.count(c) for c in chroms2]
+
+
+@pytest.mark.parametrize("n,p,m,ploidy", [(300, 1000, 2, None), (700, 3001, 4, 4), (1100, 777, 2, None), (2049, 5001, 4, 2)])
+def test_quad_cluster_kernel_is_bit_identical_to_the_pair_kernel(ctx, monkeypatch, n, p, m, ploidy):
+    """GRM_CUDA_SYRK_I8=quad: clusters of 4 (two CTA pairs on consecutive tiles, shared column panel by TMA multicast;
+    odd tile counts leave a shadow tile).  Opt-in (measured slower than the pair kernel), but it must stay exact."""
+    import torch
+
+    from grm_b200 import device as D
+
+    At = synth.dosage_device(n, p, m, 31, dev())
+    torch.cuda.synchronize()
+    monkeypatch.setenv("GRM_CUDA_SYRK_I8", "2cta")
+    G0 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0].clone()
+    monkeypatch.setenv("GRM_CUDA_SYRK_I8", "quad")
+    G1 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0]
+    ctx.synchronize()
+    assert torch.equal(G0, G1)
