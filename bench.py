@@ -284,7 +284,8 @@ def run_b200(args, wl):
     tr = ncu_traffic() if world == 1 else {}
     wk = args.workload
     roofline = {
-        "bound": "tensor", "kernel": "syrk_i8_2cta_kernel (tcgen05.mma cta_group::2 kind::i8, TMA, TMEM)", "achieved": achieved,
+        "bound": "tensor", "kernel": ("syrk_i8_wide_kernel" if (world == 1 and (p + 127) // 128 >= 2048 and T * (T + 1) // 2 >= 296)
+                                     else "syrk_i8_2cta_kernel") + " (tcgen05.mma cta_group::2 kind::i8, TMA, TMEM)", "achieved": achieved,
         "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
         "frac_of_nominal_int8": achieved / 4500.0, "frac_of_burst_derived": achieved / (2.0 * peaks["bf16_burst"]),
         "traffic": tr.get(f"syrk_i8_dram_bytes_per_launch_{wk}"),

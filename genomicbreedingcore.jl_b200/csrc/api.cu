@@ -167,7 +167,7 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     if (ctx->cusolver) grm_cusolver_destroy(ctx->cusolver);
     DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
                       &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->lu, &ctx->lu_work, &ctx->ipiv, &ctx->misc,
-                      &ctx->tiles_i8.buf, &ctx->tiles_i8_2cta.buf, &ctx->tiles_f64.buf, &ctx->tiles_packed.buf, &ctx->planes,
+                      &ctx->tiles_i8.buf, &ctx->tiles_i8_2cta.buf, &ctx->tiles_f64.buf, &ctx->tiles_packed.buf, &ctx->tiles_wide.buf, &ctx->planes,
                       &ctx->rT, &ctx->cnt, &ctx->keep, &ctx->misc2, &ctx->progress, &ctx->acc};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);

@@ -59,7 +59,7 @@ struct grm_cuda_ctx {
     void *cusolver = nullptr;  // cusolverDnHandle_t
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
     DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt, keep, progress, acc;
-    TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed;
+    TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed, tiles_wide;
     int64_t factor_n = -1;  // >= 0: ctx->lu holds the upper Cholesky factor of the n x n matrix the last repair returned
     int32_t launches = 0;  // kernels launched since last reset
 };

@@ -255,6 +255,8 @@ constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 // slowest pair never waits (no deadlock; all CTAs of the grid are co-resident: one per SM), and with a static tile
 // assignment the fast pairs would only have idled at the end anyway.  Measured on C3: 102 ms -> 66 ms.
 constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW_DEFAULT = 64;
+constexpr bool SYRK_WIDE_DEFAULT = true;  // two tiles per CTA pair sharing the column panel (long contractions)
+constexpr int SYRK_WIDE_MIN_KB = 2048;
 constexpr bool SYRK_QUAD_DEFAULT = false;  // clusters of 4 with multicast of the shared column panel
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
@@ -264,6 +266,57 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
 }
 __device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Epilogue of one 256 x 256 tile for one warp of a CTA pair: CTA `cta` (0 / 1) owns rows 128 cta .. 128 cta + 127 of the
+// tile, warp `quarter` 32 of them, one thread per row; the accumulator starts at TMEM column address `tmem_acc`.
+template <int EPI>
+__device__ __forceinline__ void drain_tile(const EpiParams &ep, int t, int2 tc, uint32_t tmem_acc, uint32_t cta, int quarter,
+                                           int lane) {
+    const int64_t row = static_cast<int64_t>(tc.x) + 128 * cta + quarter * 32 + lane;
+    const bool row_ok = row < ep.n;
+    double ui = 0.0;
+    if (EPI == 2 && row_ok) ui = ep.u[row];
+    const int64_t slot = ep.slots ? static_cast<int64_t>(ep.slots[t]) : static_cast<int64_t>(t);
+    int32_t *packed = nullptr;
+    if (EPI == 3) {
+        if (ep.tiles_max > 0) {
+            const int64_t o = slot / ep.tiles_max, sl = slot - o * ep.tiles_max;
+            packed = ep.peers[o] + (static_cast<int64_t>(ep.src_rank) * ep.tiles_max + sl) * 65536;
+        } else {
+            packed = ep.C + slot * 65536;
+        }
+    }
+    const int row_local = 128 * static_cast<int>(cta) + quarter * 32 + lane;
+    const int32_t *prev = (EPI != 0 && ep.prev) ? ep.prev + slot * 65536 + row_local : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t r[32];
+        if (prev) {
+            // partial sums of the earlier loci chunks: issue the (coalesced) loads before waiting on TMEM
+            int32_t pv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pv[j] = prev[(c0 + j) * 256];
+            tmem_ld_32x32(tmem_acc + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] += static_cast<uint32_t>(pv[j]);
+        } else {
+            tmem_ld_32x32(tmem_acc + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+            tmem_wait_ld();
+        }
+        if (EPI == 3) {
+            epilogue_store_packed(r, packed, row_local, c0);
+        } else if ((EPI == 1 || EPI == 2) && ep.Gt != nullptr) {
+            // sharded output: the same arithmetic, addressed tile-locally (leading dimension 256)
+            EpiParams lt = ep;
+            lt.G = ep.Gt + static_cast<int64_t>(t) * 65536 - (static_cast<int64_t>(tc.x) + static_cast<int64_t>(tc.y) * 256);
+            lt.ldg = 256;
+            epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, lt);
+        } else {
+            epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
+        }
+    }
 }
 
 // QUAD = false: clusters of 2 (one CTA pair per cluster), one 256 x 256 tile per pair at a time.
@@ -452,50 +505,7 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
                 if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], pbase);
                 continue;
             }
-            const int64_t row = static_cast<int64_t>(tc.x) + 128 * cta + quarter * 32 + lane;
-            const bool row_ok = row < ep.n;
-            double ui = 0.0;
-            if (EPI == 2 && row_ok) ui = ep.u[row];
-            const int64_t slot = ep.slots ? static_cast<int64_t>(ep.slots[t]) : static_cast<int64_t>(t);
-            int32_t *packed = nullptr;
-            if (EPI == 3) {
-                if (ep.tiles_max > 0) {
-                    const int64_t o = slot / ep.tiles_max, sl = slot - o * ep.tiles_max;
-                    packed = ep.peers[o] + (static_cast<int64_t>(ep.src_rank) * ep.tiles_max + sl) * 65536;
-                } else {
-                    packed = ep.C + slot * 65536;
-                }
-            }
-            const int row_local = 128 * static_cast<int>(cta) + quarter * 32 + lane;
-            const int32_t *prev = (EPI != 0 && ep.prev) ? ep.prev + slot * 65536 + row_local : nullptr;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t r[32];
-                if (prev) {
-                    // partial sums of the earlier loci chunks: issue the (coalesced) loads before waiting on TMEM
-                    int32_t pv[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) pv[j] = prev[(c0 + j) * 256];
-                    tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] += static_cast<uint32_t>(pv[j]);
-                } else {
-                    tmem_ld_32x32(tmem_base + acc * 256 + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
-                    tmem_wait_ld();
-                }
-                if (EPI == 3) {
-                    epilogue_store_packed(r, packed, row_local, c0);
-                } else if ((EPI == 1 || EPI == 2) && ep.Gt != nullptr) {
-                    // sharded output: the same arithmetic, addressed tile-locally (leading dimension 256)
-                    EpiParams lt = ep;
-                    lt.G = ep.Gt + static_cast<int64_t>(t) * 65536 - (static_cast<int64_t>(tc.x) + static_cast<int64_t>(tc.y) * 256);
-                    lt.ldg = 256;
-                    epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, lt);
-                } else {
-                    epilogue_store<EPI>(r, row, row_ok, static_cast<int64_t>(tc.y) + c0, ui, ep);
-                }
-            }
+            drain_tile<EPI>(ep, t, tc, tmem_base + acc * 256, cta, quarter, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], pbase);
@@ -525,6 +535,171 @@ syrk_i8_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                     uint32_t *__restrict__ progress, uint32_t sync_params) {
     extern __shared__ uint8_t smem_raw[];
     syrk_pair_body<EPI, true>(smem_raw, tmap, tmap64, tiles, num_tiles, num_kb, kb_per_slab, ep, progress, sync_params);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// "Wide" CTA-pair kernel for long contractions: a pair works on TWO tiles that share their column panel at once
+// (units from make_wide_units: consecutive tiles (ti, tj), (ti+1, tj) of the list).  Per K block a CTA then stages its
+// 128 rows of both row panels and its half of the ONE column panel: 48 KB for two tiles' worth of MMAs instead of
+// 2 x 32 KB — 25 % fewer bytes through the TMA / L2 path that limits the pair kernel — with no coupling between pairs
+// (the quad variant pays for its multicast with a lock-step).  Both 256-column accumulators are live, so the epilogue
+// cannot overlap the next unit's main loop: ~2 x 10 us per unit, which is why this form is only chosen when a unit's
+// main loop is milliseconds long (launch()).  4 stages of 48 KB; everything else as in syrk_pair_body.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int STAGESW = 4;
+constexpr uint32_t STAGEW_BYTES = 3 * A_BYTES;  // row panel 0, row panel 1, half of the column panel: 48 KiB
+constexpr size_t SMEMW_BYTES = STAGESW * STAGEW_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+syrk_i8_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, const int2 *__restrict__ units,
+                    int num_units, int num_kb, int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress,
+                    uint32_t sync_window) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGESW * STAGEW_BYTES);
+    uint64_t *empty_bar = full_bar + STAGESW;
+    uint64_t *tmem_full = empty_bar + STAGESW;   // one accumulator generation at a time
+    uint64_t *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    volatile uint32_t *sync_allowed = tmem_slot + 1;
+    volatile uint32_t *sync_done = tmem_slot + 2;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const bool leader = cta == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < STAGESW; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 8);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    if (threadIdx.x == 0) {
+        *sync_allowed = sync_window;
+        *sync_done = 0;
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, step = 0;
+            const bool throttle = progress != nullptr && leader;
+            for (int u = pair; u < num_units; u += num_pairs) {
+                const int2 un = units[u];
+                const bool two = un.y >= 0;
+                const int2 t0 = tiles[un.x];
+                const int2 t1 = two ? tiles[un.y] : t0;
+                const uint32_t bytes = 2 * (two ? STAGEW_BYTES : 2 * A_BYTES);
+                int slab = 0, kin = 0;
+                for (int kb = 0; kb < num_kb; ++kb, ++step) {
+                    if (throttle) {
+                        if ((step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
+                        uint32_t spins = 0;
+                        while (step > *sync_allowed) {
+                            if (++spins > (1u << 28)) __trap();
+                        }
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *sA0 = smem + stage * STAGEW_BYTES;
+                    uint8_t *sA1 = sA0 + A_BYTES;
+                    uint8_t *sB = sA1 + A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                    tma_load_3d_2cta(sA0, &tmap, &full_bar[stage], kin * BK, t0.x + 128 * static_cast<int>(cta), slab);
+                    if (two) tma_load_3d_2cta(sA1, &tmap, &full_bar[stage], kin * BK, t1.x + 128 * static_cast<int>(cta), slab);
+                    tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, t0.y + 128 * static_cast<int>(cta), slab);
+                    if (++kin == kb_per_slab) {
+                        kin = 0;
+                        ++slab;
+                    }
+                    if (++stage == STAGESW) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            if (throttle) {
+                st_relaxed_u32(&progress[pair], 0xffffffffu);
+                *sync_done = 1;
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== K-window watcher (leader CTA) =====================
+        if (progress != nullptr && leader) {
+            while (*sync_done == 0) {
+                uint32_t mn = 0xffffffffu;
+                for (int i = lane; i < num_pairs; i += 32) mn = min(mn, ld_relaxed_u32(&progress[i]));
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                if (lane == 0) *sync_allowed = (mn > 0xffffffffu - sync_window) ? 0xffffffffu : mn + sync_window;
+                __nanosleep(2000);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(256, 256);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int u = pair; u < num_units; u += num_pairs, ++local) {
+                const bool two = units[u].y >= 0;
+                mbar_wait(tmem_empty, (local & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA0 = smem_u32(smem + stage * STAGEW_BYTES);
+                    const uint64_t a0 = umma_desc_k_sw128(sA0);
+                    const uint64_t a1 = umma_desc_k_sw128(sA0 + A_BYTES);
+                    const uint64_t bd = umma_desc_k_sw128(sA0 + 2 * A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_i8_2cta(tmem_base, a0 + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        if (two) umma_i8_2cta(tmem_base + 256, a1 + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit_2cta(&empty_bar[stage], 0b11);
+                    if (++stage == STAGESW) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_2cta(tmem_full, 0b11);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 of both CTAs) =====================
+        const int quarter = warp & 3;
+        int local = 0;
+        for (int u = pair; u < num_units; u += num_pairs, ++local) {
+            const int2 un = units[u];
+            mbar_wait(tmem_full, local & 1);
+            tc_fence_after();
+            drain_tile<EPI>(ep, un.x, tiles[un.x], tmem_base, cta, quarter, lane);
+            if (un.y >= 0) drain_tile<EPI>(ep, un.y, tiles[un.y], tmem_base + 256, cta, quarter, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty, 0);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+    }
 }
 
 int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out,
@@ -626,6 +801,49 @@ uint32_t sync_window() {
     return window;
 }
 
+// units of the wide kernel: two consecutive tiles of the list that share their column panel, or one leftover tile
+int32_t get_wide_units(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_units, int *num_units) {
+    TileListCache &tc = ctx->tiles_wide;
+    if (tc.n != n || tc.rank != rank || tc.world != world) {
+        std::vector<int2> order;
+        grm_tile_order(n, order);
+        int64_t b, e;
+        grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
+        std::vector<int2> units;
+        for (int64_t t = b; t < e;) {
+            if (t + 1 < e && order[t].y == order[t + 1].y) {
+                units.push_back(make_int2(static_cast<int>(t - b), static_cast<int>(t + 1 - b)));
+                t += 2;
+            } else {
+                units.push_back(make_int2(static_cast<int>(t - b), -1));
+                t += 1;
+            }
+        }
+        GRM_TRY(tc.buf.reserve(std::max<size_t>(units.size(), 1) * sizeof(int2)));
+        if (!units.empty())
+            GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, units.data(), units.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                                         ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        tc.n = n;
+        tc.rank = rank;
+        tc.world = world;
+        tc.count = static_cast<int32_t>(units.size());
+    }
+    *d_units = tc.buf.as<int2>();
+    *num_units = tc.count;
+    return GRM_CUDA_OK;
+}
+
+// wide kernel: "wide" forces it, "2cta"/"quad"/"1cta" exclude it; by default it is used when a unit's main loop is
+// long enough to dwarf its un-overlapped epilogue (>= SYRK_WIDE_MIN_KB K blocks) and there are enough tiles to keep
+// every pair busy with two-tile units.  Measured: C3 (3907 K blocks, 3160 tiles) SYRK 56.5 -> 51.7 ms; C2 (781 K
+// blocks, 210 tiles) 0.76 -> 0.97 ms, hence the thresholds.
+bool use_wide(int num_kb, int num_tiles, int num_sms) {
+    const char *e = getenv("GRM_CUDA_SYRK_I8");
+    if (e) return !strcmp(e, "wide");
+    return SYRK_WIDE_DEFAULT && num_kb >= SYRK_WIDE_MIN_KB && num_tiles >= 4 * (num_sms / 2);
+}
+
 bool use_quad() {
     const char *e = getenv("GRM_CUDA_SYRK_I8");
     return e ? !strcmp(e, "quad") : SYRK_QUAD_DEFAULT;
@@ -649,6 +867,27 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
     CUtensorMap tmap;
     GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
     const int kbs = static_cast<int>((p + BK - 1) / BK);
+    if (use_wide(kbs * static_cast<int>(nslabs), static_cast<int>(grm_cuda_tile_count(n, rank, world)), ctx->num_sms)) {
+        const int2 *d_tiles, *d_units;
+        int count, nunits;
+        GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+        if (count == 0) return GRM_CUDA_OK;
+        GRM_TRY(get_wide_units(ctx, n, rank, world, &d_units, &nunits));
+        static bool attrw_set[3] = {false, false, false};
+        if (!attrw_set[EPI]) {
+            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_wide_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(SMEMW_BYTES)));
+            attrw_set[EPI] = true;
+        }
+        const int pairs = std::min(nunits, ctx->num_sms / 2);
+        uint32_t *prog = nullptr;
+        GRM_TRY(sync_buffer(ctx, pairs, nunits, n * ldc * nslabs, &prog));
+        syrk_i8_wide_kernel<EPI><<<2 * pairs, NUM_THREADS2, SMEMW_BYTES, ctx->stream>>>(
+            tmap, d_tiles, d_units, nunits, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
     if (use_quad()) {
         // clusters of 4: two CTA pairs on two consecutive tiles, shared column panel multicast (see syrk_pair_body)
         const int2 *d_tiles;

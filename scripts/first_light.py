@@ -469,23 +469,27 @@ def stage_syrk_quad():
     """Clusters of 4 (two CTA pairs, shared column panel multicast) against the CTA-pair kernel: bit-identity on ragged
     shapes (odd and even tile counts, both epilogues), then timing at C2 and C3."""
     os.environ["GRM_CUDA_DEBUG"] = "1"
+    MODES = os.environ.get("SYRK_MODES", "2cta,wide").split(",")
     ctx = grm_b200.default_context(0)
     for (n, p, m, ploidy) in [(300, 1000, 2, None), (700, 3001, 4, 4), (1100, 777, 2, None), (2049, 5001, 4, 2), (5000, 20000, 2, 2)]:
         At = synth.dosage_device(n, p, m, 5, dev)
         os.environ["GRM_CUDA_SYRK_I8"] = "2cta"
         G0 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0].clone()
-        os.environ["GRM_CUDA_SYRK_I8"] = "quad"
-        G1 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0]
-        torch.cuda.synchronize()
-        print(f"[quad n={n} p={p} ploidy={ploidy}] tiles={((n + 255) // 256) * ((n + 255) // 256 + 1) // 2} "
-              f"bit-identical={bool(torch.equal(G0, G1))}", flush=True)
+        res = {}
+        for mode in MODES[1:]:
+            os.environ["GRM_CUDA_SYRK_I8"] = mode
+            G1 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0]
+            torch.cuda.synchronize()
+            res[mode] = bool(torch.equal(G0, G1))
+        print(f"[n={n} p={p} ploidy={ploidy}] tiles={((n + 255) // 256) * ((n + 255) // 256 + 1) // 2} bit-identical={res}",
+              flush=True)
     # C2: SYRK alone
     n2, p2 = 5000, 100000
     codes = torch.randint(0, 3, (n2, D.padded_loci(p2)), dtype=torch.int8, device=dev)
     codes[:, p2:] = 0
     G2 = torch.zeros((n2, n2), dtype=torch.float64, device=dev)
     for rep in range(2):
-        for mode in ("2cta", "quad"):
+        for mode in MODES:
             os.environ["GRM_CUDA_SYRK_I8"] = mode
             t, ts = ev_time(lambda: D.syrk_i8_f64(ctx, codes, p2, 0.25, 0.0, 0.0, float(p2), out=G2), ctx, reps=5)
             print(f"[C2 syrk {mode}] best {t:.3f} ms", flush=True)
@@ -498,7 +502,7 @@ def stage_syrk_quad():
     G = torch.empty((n, n), dtype=torch.float64, device=dev)
     ref = None
     for rep in range(3):
-        for mode in ("2cta", "quad"):
+        for mode in MODES:
             os.environ["GRM_CUDA_SYRK_I8"] = mode
             infos = []
             t, ts = ev_time(lambda: infos.append(D.grm_device(ctx, A, ploidy, denominator=ploidy, skip_repair=True, out=G)[1]),

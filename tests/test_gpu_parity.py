@@ -911,10 +911,13 @@ def test_estimateld_per_chromosome_correlation_matrices():
     assert chroms2 == sorted(set(labels)) and [x.shape[0] for x in LDs2] == [labels.count(c) for c in chroms2]
 
 
+@pytest.mark.parametrize("mode", ["wide", "quad"])
 @pytest.mark.parametrize("n,p,m,ploidy", [(300, 1000, 2, None), (700, 3001, 4, 4), (1100, 777, 2, None), (2049, 5001, 4, 2)])
-def test_quad_cluster_kernel_is_bit_identical_to_the_pair_kernel(ctx, monkeypatch, n, p, m, ploidy):
-    """GRM_CUDA_SYRK_I8=quad: clusters of 4 (two CTA pairs on consecutive tiles, shared column panel by TMA multicast;
-    odd tile counts leave a shadow tile).  Opt-in (measured slower than the pair kernel), but it must stay exact."""
+def test_syrk_kernel_variants_are_bit_identical_to_the_pair_kernel(ctx, monkeypatch, mode, n, p, m, ploidy):
+    """GRM_CUDA_SYRK_I8=wide: a CTA pair works on two tiles that share their column panel (the default for long
+    contractions with many tiles, i.e. C3; forced here on small ragged shapes incl. leftover single-tile units).
+    GRM_CUDA_SYRK_I8=quad: clusters of 4 with TMA multicast of the shared panel (opt-in; odd tile counts leave a shadow
+    tile).  Both must reproduce the pair kernel bit for bit."""
     import torch
 
     from grm_b200 import device as D
@@ -923,7 +926,7 @@ def test_quad_cluster_kernel_is_bit_identical_to_the_pair_kernel(ctx, monkeypatc
     torch.cuda.synchronize()
     monkeypatch.setenv("GRM_CUDA_SYRK_I8", "2cta")
     G0 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0].clone()
-    monkeypatch.setenv("GRM_CUDA_SYRK_I8", "quad")
+    monkeypatch.setenv("GRM_CUDA_SYRK_I8", mode)
     G1 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0]
     ctx.synchronize()
     assert torch.equal(G0, G1)
