@@ -257,6 +257,8 @@ constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW_DEFAULT = 64;
 constexpr bool SYRK_WIDE_DEFAULT = true;  // two tiles per CTA pair sharing the column panel (long contractions)
 constexpr int SYRK_WIDE_MIN_KB = 2048;
+constexpr bool SYRK_WIDE_PACKED_DEFAULT = false;
+constexpr int SYRK_WIDE_PACKED_MIN_KB = 1900;
 constexpr bool SYRK_QUAD_DEFAULT = false;  // clusters of 4 with multicast of the shared column panel
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
@@ -844,6 +846,13 @@ bool use_wide(int num_kb, int num_tiles, int num_sms) {
     return SYRK_WIDE_DEFAULT && num_kb >= SYRK_WIDE_MIN_KB && num_tiles >= 4 * (num_sms / 2);
 }
 
+// K-split multi-GPU path (grm_cuda_syrk_i8_packed / _scatter): GRM_CUDA_SYRK_PACKED=wide|2cta forces a kernel
+bool use_wide_packed(int num_kb, int num_tiles, int num_sms) {
+    const char *e = getenv("GRM_CUDA_SYRK_PACKED");
+    if (e) return !strcmp(e, "wide");
+    return SYRK_WIDE_PACKED_DEFAULT && num_kb >= SYRK_WIDE_PACKED_MIN_KB && num_tiles >= 4 * (num_sms / 2);
+}
+
 bool use_quad() {
     const char *e = getenv("GRM_CUDA_SYRK_I8");
     return e ? !strcmp(e, "quad") : SYRK_QUAD_DEFAULT;
@@ -1138,15 +1147,31 @@ static int32_t syrk_i8_packed_impl(grm_cuda_ctx *ctx, const int8_t *d_codes, int
         PackedPlan pl;
         make_packed_plan(n, world, pl);
         const size_t nt = pl.tiles.size();
-        GRM_TRY(tc.buf.reserve(nt * (sizeof(int2) + sizeof(int32_t))));
+        // units of the wide kernel over the same list: consecutive tiles that share their column panel
+        std::vector<int2> units;
+        for (size_t t = 0; t < nt;) {
+            if (t + 1 < nt && pl.tiles[t].y == pl.tiles[t + 1].y) {
+                units.push_back(make_int2(static_cast<int>(t), static_cast<int>(t + 1)));
+                t += 2;
+            } else {
+                units.push_back(make_int2(static_cast<int>(t), -1));
+                t += 1;
+            }
+        }
+        // layout: [tiles: nt int2][slots: nt int32, padded to a multiple of 2][units: nu int2]
+        const size_t slots_padded = (nt + 1) / 2 * 2;
+        GRM_TRY(tc.buf.reserve(nt * sizeof(int2) + slots_padded * sizeof(int32_t) + units.size() * sizeof(int2)));
         GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, pl.tiles.data(), nt * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.as<int2>() + nt, pl.slots.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice,
                                      ctx->stream));
+        GRM_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int32_t *>(tc.buf.as<int2>() + nt) + slots_padded, units.data(),
+                                     units.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         tc.n = n;
         tc.world = world;
         tc.rank = 0;
         tc.count = static_cast<int32_t>(nt);
+        tc.kind = static_cast<int32_t>(units.size());
     }
     const int count = tc.count;
     EpiParams ep{};
@@ -1176,6 +1201,27 @@ static int32_t syrk_i8_packed_impl(grm_cuda_ctx *ctx, const int8_t *d_codes, int
                                      ctx->stream));
     }
     const int kbs = static_cast<int>((p + BK - 1) / BK);
+    if (use_wide_packed(kbs, count, ctx->num_sms)) {
+        // every GPU contracts ALL tiles over its loci, so there are always enough two-tile units; the K threshold is
+        // lower than in launch() (use_wide_packed)
+        static bool attrw_set = false;
+        if (!attrw_set) {
+            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(SMEMW_BYTES)));
+            attrw_set = true;
+        }
+        const int nunits = tc.kind;
+        const int2 *d_units = reinterpret_cast<const int2 *>(reinterpret_cast<const int32_t *>(tc.buf.as<int2>() + count) +
+                                                             (count + 1) / 2 * 2);
+        const int wpairs = std::min(nunits, ctx->num_sms / 2);
+        uint32_t *wprog = nullptr;
+        GRM_TRY(sync_buffer(ctx, wpairs, nunits, n * ldc, &wprog));
+        syrk_i8_wide_kernel<3><<<2 * wpairs, NUM_THREADS2, SMEMW_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), d_units, nunits,
+                                                                                       kbs, kbs, ep, wprog, sync_window());
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
     const int pairs = std::min(count, ctx->num_sms / 2);
     uint32_t *prog = nullptr;
     GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc, &prog));

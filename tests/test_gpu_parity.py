@@ -491,13 +491,17 @@ def test_sharded_tiles_union_is_bit_identical(world):
     assert relerr(accc[iu] / 500.0, fullc[iu]) <= 1e-13  # sharded FP64 calls return raw sums
 
 
+@pytest.mark.parametrize("kernel", ["2cta", "wide"])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("ploidy", [None, 4])
-def test_loci_split_packed_tiles_emulated_ranks(ctx, world, ploidy):
+def test_loci_split_packed_tiles_emulated_ranks(ctx, monkeypatch, world, ploidy, kernel):
     """The "ksplit" multi-GPU decomposition with the ranks emulated on one GPU: every rank contracts its own loci
     over all tiles (raw int32 tiles in reduce-scatter layout), the tile buffers are summed (what the NCCL
-    reduce-scatter does), every rank finalises the tiles it owns; the union must be bit-identical to one call."""
+    reduce-scatter does), every rank finalises the tiles it owns; the union must be bit-identical to one call.
+    `kernel`: the CTA-pair kernel or the two-tiles-per-pair kernel on the packed path (GRM_CUDA_SYRK_PACKED)."""
     import torch
+
+    monkeypatch.setenv("GRM_CUDA_SYRK_PACKED", kernel)
 
     from grm_b200 import device as D, dist as GD
 
