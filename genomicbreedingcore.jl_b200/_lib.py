@@ -25,11 +25,14 @@ ERR_NOT_DOSAGE = 9
 ERR_OVERFLOW = 10
 ERR_ALL_FILTERED = 11
 ERR_NOT_POSDEF = 12
+ERR_COMM = 13
 DIM_LOCI, DIM_ENTRIES = 0, 1
 
 PATH_AUTO, PATH_I8, PATH_F64 = 0, 1, 2
 MISSING_ERROR, MISSING_MEANFILL = 0, 1
 LOC_HOST, LOC_DEVICE = 0, 1
+OUT_DENSE, OUT_TILES = 0, 1
+INGEST_AUTO, INGEST_STREAM, INGEST_HOSTQ = 0, 1, 2
 
 
 class Options(C.Structure):
@@ -47,6 +50,10 @@ class Options(C.Structure):
         ("chunk_loci", C.c_int64),
         ("maf", C.c_double),
         ("max_locus_sparsity", C.c_double),
+        ("distributed", C.c_int32),
+        ("input_slab", C.c_int32),
+        ("output_mode", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -69,6 +76,15 @@ class Info(C.Structure):
         ("ms_total", C.c_float),
         ("kernel_launches", C.c_int32),
         ("loci_kept", C.c_int32),
+        ("ms_exchange", C.c_float),
+        ("ms_gather", C.c_float),
+        ("ms_host_busy", C.c_float),
+        ("ingest", C.c_int32),
+        ("host_threads", C.c_int32),
+        ("world", C.c_int32),
+        ("exchange_waves", C.c_int32),
+        ("syrk_window", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
     def as_dict(self):
@@ -87,8 +103,23 @@ SIGNATURES = {
     "grm_cuda_ctx_destroy": (_i32, [_vp]),
     "grm_cuda_ctx_stream": (_vp, [_vp]),
     "grm_cuda_ctx_synchronize": (_i32, [_vp]),
+    "grm_cuda_ctx_set_tuning": (_i32, [_vp, C.c_char_p, _i64]),
+    "grm_cuda_ctx_get_tuning": (_i32, [_vp, C.c_char_p, C.POINTER(_i64)]),
+    "grm_cuda_comm_unique_id": (_i32, [_vp]),
+    "grm_cuda_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "grm_cuda_comm_destroy": (_i32, [_vp]),
+    "grm_cuda_comm_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "grm_cuda_simple": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
     "grm_cuda_ploidyaware": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, C.POINTER(Options), C.POINTER(Info)]),
+    "grm_cuda_simple_union": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _i64, C.POINTER(Options),
+                                     C.POINTER(Info)]),
+    "grm_cuda_ploidyaware_union": (_i32, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i32, _vp, _i64, C.POINTER(Options),
+                                          C.POINTER(Info)]),
+    "grm_cuda_from_codes": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _i64, C.POINTER(Options),
+                                   C.POINTER(Info)]),
+    "grm_cuda_host_quantise": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _vp, _i64, _i32, C.POINTER(C.c_uint32)]),
+    "grm_cuda_host_detect": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
+    "grm_cuda_host_simd": (C.c_char_p, []),
     "grm_cuda_inflate_diagonals": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
     "grm_cuda_repair_probe": (_i32, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(C.c_uint32),
                                      C.POINTER(_f64)]),
@@ -99,6 +130,9 @@ SIGNATURES = {
                                   _i32]),
     "grm_cuda_detect_denominator": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
     "grm_cuda_pack_dosage": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "grm_cuda_pack_codes": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "grm_cuda_locus_keep": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _f64, _f64, _i32, _vp, _vp, _vp]),
+    "grm_cuda_mask_codes": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "grm_cuda_locus_qc": (_i32, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "grm_cuda_syrk_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32]),
     "grm_cuda_syrk_i8_f64": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
@@ -106,12 +140,6 @@ SIGNATURES = {
     "grm_cuda_packed_tiles_max": (_i64, [_i64, _i32]),
     "grm_cuda_syrk_i8_packed": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "grm_cuda_finalize_tiles": (_i32, [_vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
-    "grm_cuda_syrk_i8_scatter": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
-    "grm_cuda_finalize_tiles_parts": (_i32, [_vp, _vp, _i64, _f64, _f64, _f64, _f64, _vp, _vp, _i64, _i32, _i32]),
-    "grm_cuda_ipc_alloc": (_i32, [_vp, _i64, C.POINTER(_vp), _vp]),
-    "grm_cuda_ipc_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
-    "grm_cuda_ipc_close": (_i32, [_vp, _vp]),
-    "grm_cuda_ipc_free": (_i32, [_vp, _vp]),
     "grm_cuda_dosage_stats": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _i32]),
     "grm_cuda_dosage_centre": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, C.POINTER(_f64)]),
     "grm_cuda_rowdot_i8": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
@@ -191,6 +219,28 @@ class Context:
     def synchronize(self) -> None:
         check(self.lib.grm_cuda_ctx_synchronize(self.handle))
 
+    def set_tuning(self, key: str, value: int) -> None:
+        """Per-context tuning knob (include/grm_cuda.h lists the keys); the library never reads the environment."""
+        check(self.lib.grm_cuda_ctx_set_tuning(self.handle, key.encode(), int(value)))
+
+    def get_tuning(self, key: str) -> int:
+        v = _i64(0)
+        check(self.lib.grm_cuda_ctx_get_tuning(self.handle, key.encode(), C.byref(v)))
+        return v.value
+
+    # ---- communicator (one process per GPU; NCCL lives inside the library) --------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self.lib.grm_cuda_comm_init(self.handle, buf, int(rank), int(world)))
+
+    def comm_info(self):
+        r, w, v = _i32(0), _i32(1), _i32(0)
+        check(self.lib.grm_cuda_comm_info(self.handle, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def comm_destroy(self) -> None:
+        check(self.lib.grm_cuda_comm_destroy(self.handle))
+
     def close(self) -> None:
         if getattr(self, "handle", None):
             self.lib.grm_cuda_ctx_destroy(self.handle)
@@ -201,6 +251,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def comm_unique_id() -> bytes:
+    """128 opaque bytes created on ONE rank; hand them to the others and call Context.comm_init on every rank."""
+    buf = (C.c_uint8 * 128)()
+    check(load().grm_cuda_comm_unique_id(buf))
+    return bytes(buf)
 
 
 _default_ctx = {}

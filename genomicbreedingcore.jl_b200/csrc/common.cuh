@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/grm_cuda.h"
@@ -46,27 +47,71 @@ struct TileListCache {
     DevBuf buf;
 };
 
+// Explicit per-context tuning knobs (grm_cuda_ctx_set_tuning): the library never reads the environment.  Defaults are
+// the measured best (DESIGN.md / profiles/README.md); tests use the knobs to force every kernel variant on small shapes.
+struct GrmTuning {
+    int syrk_i8 = 0;        // fused-epilogue int8 SYRK: 0 auto, 1 single-CTA, 2 CTA pair, 3 wide (two tiles per pair)
+    int syrk_packed = 0;    // K-split packed-tile SYRK: 0 auto (CTA pair), 2 CTA pair, 3 wide
+    int syrk_sync = -1;     // K-window synchronisation of the persistent pairs: -1 auto, 0 off, 1 forced
+    int syrk_window = 64;   // K blocks a pair may run ahead of the slowest one
+    int pack = 0;           // FP64 -> int8 pack kernel: 0 auto (TMA-staged when aligned), 1 register-staged
+    int ieee_div = 0;       // 1: IEEE division in the epilogue instead of reciprocal + 2 FMA corrections (bit-identical)
+    int tile_band = 0;      // band height (tile rows) of the tile enumeration; 0 = default
+    int host_threads = 0;   // host ingest threads; 0 = automatic
+    int ingest = 0;         // host input: 0 auto, 1 stream FP64 and pack on the device, 2 quantise on the host
+    int ksplit_waves = 0;   // K-split exchange waves (reduce-scatter of wave w under the SYRK of wave w+1); 0 = auto
+    int f64_kernel = 0;     // FP64 SYRK operand staging: 0 auto (TMA when aligned), 1 register-staged
+    int ring_mb = 0;        // bytes (MiB) of one pinned ingest slot; 0 = automatic
+};
+
+// tile lists of the K-split contraction, per exchange wave (syrk_i8.cu)
+struct PackedPlanCache {
+    int64_t n = -1;
+    int32_t world = -1, waves = -1, band = -1;
+    std::vector<int32_t> tile_off, tile_cnt, unit_off, unit_cnt;  // per wave, in elements of the lists below
+    int32_t total_tiles = 0, slots_padded = 0;
+    DevBuf buf;  // [tiles: int2 x total][slots: int32 x total, padded to even][units of the wide kernel: int2]
+};
+
+struct GrmHostPool;  // ingest_host.cpp
+struct GrmComm;      // comm.cu
+
 struct grm_cuda_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;   // compute
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;  // lower priority than `stream`: the pack / statistics side of the pipelined flow
-    bool pack_small_footprint = false;  // pack with the register-staged variant (co-resides with a persistent SYRK CTA)
+    cudaStream_t comm_stream = nullptr;  // NCCL collectives that overlap the compute stream
     cudaEvent_t ev[16] = {};
-    cudaEvent_t pipe_ev[40] = {};       // pipelined flow: [0..15] chunk packed, [16..39] SYRK launch begin / end
-    cudaEvent_t copy_done[2] = {}, stage_free[2] = {};
+    cudaEvent_t wave_ev[16] = {};        // K-split waves: SYRK of wave w finished / exchange of wave w finished
+    cudaEvent_t copy_done[4] = {}, stage_free[4] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
-    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[2], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt, keep, progress, acc;
-    TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed, tiles_wide;
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[4], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt,
+        keep, progress, packed, reduced, gtiles, gtiles_all, codes_all, cons;
+    TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed, tiles_wide, tiles_f64_all;
     int64_t factor_n = -1;  // >= 0: ctx->lu holds the upper Cholesky factor of the n x n matrix the last repair returned
     int32_t launches = 0;  // kernels launched since last reset
+    GrmTuning tune;
+    std::vector<const void *> attr_done;  // kernels whose dynamic shared memory limit was raised ON THIS CONTEXT'S DEVICE
+    std::vector<std::pair<const void *, int>> max_clusters;  // co-resident CTA pairs of a kernel on the idle device
+    int32_t last_syrk_window = 0;  // 1 if the last pair-kernel launch used the K-window synchronisation
+    PackedPlanCache packed_plan[2];  // [0]: waves > 1 (K-split exchange waves), [1]: waves == 1
+    // pinned host ring of the threaded ingest (grow-only) and the worker pool
+    void *pin[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t pin_cap = 0;
+    GrmHostPool *pool = nullptr;
+    GrmComm *comm = nullptr;
 };
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property: remember it per context, not per process
+// (a second context on another GPU of the same process must raise the limit again).
+int32_t grm_func_smem(grm_cuda_ctx *ctx, const void *func, size_t bytes);
 
 // tile partition (tiles.cpp part of api.cu)
 constexpr int GRM_TILE = 256;  // edge, in entries, of the unit of multi-GPU sharding
-void grm_tile_order(int64_t n, std::vector<int2> &tiles);  // all upper-triangular (ti<=tj) tiles, L2-friendly order
+// all upper-triangular (ti <= tj) tiles in an L2-friendly order: bands of `band` tile rows (<= 0: default)
+void grm_tile_order(int64_t n, int band, std::vector<int2> &tiles);
 void grm_tile_range(int64_t total, int32_t rank, int32_t world, int64_t *begin, int64_t *end);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
@@ -75,14 +120,38 @@ typedef CUresult (*GrmEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint3
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int32_t grm_tmap_encoder(GrmEncodeTiledFn *fn);
 
-// pipelined single-GPU int8 flow (syrk_i8.cu): partial sums per loci chunk, then the fused FP64 epilogue on the last one
-int64_t grm_syrk_i8_partial_bytes(int64_t n);
-int32_t grm_syrk_i8_partial(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t *d_acc,
-                            int accumulate);
-int32_t grm_syrk_i8_f64_prev(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs,
-                             double alpha, double beta, double gamma, double denom, const double *d_u, double *d_G,
-                             int64_t ldg, int32_t rank, int32_t world, const int32_t *d_prev);
-bool grm_syrk_i8_pairs();  // CTA-pair kernel selected (the default)
+// communicator (comm.cu): thin wrappers over the dlopen'ed NCCL; dtype = GRM_DT_*
+constexpr int GRM_DT_F64 = 0, GRM_DT_I32 = 1, GRM_DT_I64 = 2, GRM_DT_U8 = 3;
+int grm_comm_rank(const grm_cuda_ctx *ctx);
+int grm_comm_world(const grm_cuda_ctx *ctx);
+int32_t grm_comm_allreduce(grm_cuda_ctx *ctx, const void *send, void *recv, size_t count, int dtype, int op_max,
+                           cudaStream_t s);
+int32_t grm_comm_reduce_scatter(grm_cuda_ctx *ctx, const void *send, void *recv, size_t recvcount, int dtype,
+                                cudaStream_t s);
+int32_t grm_comm_allgather(grm_cuda_ctx *ctx, const void *send, void *recv, size_t sendcount, int dtype, cudaStream_t s);
+
+// tile-layout helpers of the distributed paths (tiles.cu)
+int32_t grm_packed_plan(grm_cuda_ctx *ctx, int64_t n, int32_t world, int32_t waves, PackedPlanCache **out);
+// gathered FP64 tiles [world][tiles_max][256 x 256] -> dense n x n matrix, both triangles (exact mirror)
+int32_t grm_unpack_tiles(grm_cuda_ctx *ctx, const double *d_tiles_all, int64_t n, int32_t world, double *d_G, int64_t ldg);
+// dense upper triangle -> reduce-scatter layout [world][tiles_max][256 x 256] (FP64 K-split)
+int32_t grm_pack_tiles_f64(grm_cuda_ctx *ctx, const double *d_G, int64_t n, int64_t ldg, int32_t world, double *d_packed);
+// owned reduced FP64 tiles: t /= denom, zeros outside the matrix
+int32_t grm_scale_tiles_f64(grm_cuda_ctx *ctx, double *d_tiles, int64_t n, int32_t rank, int32_t world, double denom);
+// owned tiles of a dense matrix: upper-triangle elements /= denom
+int32_t grm_scale_dense_tiles(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, int32_t rank, int32_t world,
+                              double denom);
+// packed owned tiles [count][256 x 256] -> this rank's tiles inside a dense matrix (upper triangle only)
+int32_t grm_scatter_tiles(grm_cuda_ctx *ctx, const double *d_tiles, int64_t n, int32_t rank, int32_t world, double *d_G,
+                          int64_t ldg);
+
+// K-split contraction in exchange waves and the finalisation of reduced tiles (syrk_i8.cu)
+void grm_packed_wave_range(int64_t n, int32_t world, int32_t waves, int32_t w, int64_t *s0, int64_t *s1);
+int32_t grm_syrk_i8_packed_wave(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t world,
+                                int32_t waves, int32_t wave, int32_t *d_packed);
+int32_t grm_finalize_tiles_range(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha, double beta,
+                                 double gamma, double denom, const double *d_u, double *d_G, int64_t ldg, double *d_Gt,
+                                 int32_t rank, int32_t world, int64_t t0, int64_t cnt, cudaStream_t stream);
 
 // kernels' host launchers (implemented across the .cu files)
 int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, int64_t max_cells,

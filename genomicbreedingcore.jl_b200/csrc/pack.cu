@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr uint32_t FLAG_NAN = 1u, FLAG_INF = 2u, FLAG_NOT_DOSAGE = 4u;
+constexpr uint32_t FLAG_NAN = 1u, FLAG_INF = 2u, FLAG_NOT_DOSAGE = 4u, FLAG_NAN_PAYLOAD = 16u;
 
 // -------------------------------------------------------------------------------------------------------------
 // detection: OR of round(64*x) over the sampled cells; any cell that is not k/64 in [0,1] raises a flag.
@@ -64,16 +64,18 @@ template <int EITERS, bool MASK>
 __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__restrict__ A, int64_t n, int64_t pc,
                                                           int64_t lda, int m, int8_t *__restrict__ codes, int64_t ldc,
                                                           int32_t *__restrict__ colsum, uint32_t *__restrict__ flags,
-                                                          const uint8_t *__restrict__ keep) {
+                                                          int32_t *__restrict__ miss) {
+    // MASK (QC mode): a NaN cell is not an error here — it is packed as 0 and counted per locus in miss[]; the keep
+    // decision (locus_keep_kernel) then flags the missing cells of KEPT loci only
     __shared__ uint32_t tile[PK_SLAB][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t k0 = static_cast<int64_t>(blockIdx.x) * PK_LOCI;
     const int64_t e_base = static_cast<int64_t>(blockIdx.y) * (PK_SLAB * EITERS);
     const double mf = static_cast<double>(m);
 
-    int32_t acc[16];
+    int32_t acc[16], mis[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0;
+    for (int i = 0; i < 16; ++i) acc[i] = mis[i] = 0;
     uint32_t bad = 0;
 
 #pragma unroll 1
@@ -87,9 +89,7 @@ __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__res
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int64_t k = k0 + warp * 16 + j;
-            // a locus dropped by the QC mask is packed as zeros (it then contributes nothing to any integer sum)
-            bool vk = k < pc;
-            if (MASK) vk = vk && keep[k] != 0;
+            const bool vk = k < pc;
             xa[j] = (vk && va) ? ld_stream(A + ea + k * lda) : 0.0;
             xb[j] = (vk && vb) ? ld_stream(A + eb + k * lda) : 0.0;
         }
@@ -102,11 +102,13 @@ __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__res
                 const double ta = va_ * mf, tb = vb_ * mf;
                 int ca = __double2int_rn(ta), cb = __double2int_rn(tb);
                 if (!(static_cast<double>(ca) == ta && ca >= 0 && ca <= m)) {
-                    bad |= (va_ != va_) ? FLAG_NAN : (isinf(va_) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    if (MASK && va_ != va_) ++mis[g * 4 + kk];
+                    else bad |= (va_ != va_) ? FLAG_NAN : (isinf(va_) ? FLAG_INF : FLAG_NOT_DOSAGE);
                     ca = 0;
                 }
                 if (!(static_cast<double>(cb) == tb && cb >= 0 && cb <= m)) {
-                    bad |= (vb_ != vb_) ? FLAG_NAN : (isinf(vb_) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    if (MASK && vb_ != vb_) ++mis[g * 4 + kk];
+                    else bad |= (vb_ != vb_) ? FLAG_NAN : (isinf(vb_) ? FLAG_INF : FLAG_NOT_DOSAGE);
                     cb = 0;
                 }
                 wa |= static_cast<uint32_t>(ca) << (8 * kk);
@@ -135,6 +137,10 @@ __global__ void __launch_bounds__(256, 2) pack_dosage_kernel(const double *__res
         const int32_t s = __reduce_add_sync(0xffffffffu, acc[i]);
         const int64_t k = k0 + warp * 16 + i;
         if (lane == 0 && k < pc && s != 0) atomicAdd(&colsum[k], s);
+        if (MASK) {
+            const int32_t ms = __reduce_add_sync(0xffffffffu, mis[i]);
+            if (lane == 0 && k < pc && ms != 0) atomicAdd(&miss[k], ms);
+        }
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
     if (lane == 0 && bad) atomicOr(flags, bad);
@@ -155,7 +161,7 @@ template <bool MASK>
 __global__ void __launch_bounds__(288, 2)
 pack_dosage_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n, int64_t pc, int m, int8_t *__restrict__ codes,
                        int64_t ldc, int32_t *__restrict__ colsum, uint32_t *__restrict__ flags,
-                       const uint8_t *__restrict__ keep, int64_t ent_blocks, int64_t units) {
+                       int32_t *__restrict__ miss, int64_t ent_blocks, int64_t units) {
     extern __shared__ uint8_t pt_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(pt_raw) + 127) & ~uintptr_t(127));
     double *stage = reinterpret_cast<double *>(base);
@@ -198,9 +204,9 @@ pack_dosage_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n, int6
     }
 
     const double mf = static_cast<double>(m);
-    int32_t acc[16];
+    int32_t acc[16], mis[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0;
+    for (int i = 0; i < 16; ++i) acc[i] = mis[i] = 0;
     uint32_t bad = 0;
     int64_t cur_kb = -1;
     int s = 0;
@@ -213,6 +219,11 @@ pack_dosage_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n, int6
             const int64_t k = kb * PT_LOCI + warp * 16 + i;
             if (lane == 0 && k < pc && sum != 0) atomicAdd(&colsum[k], sum);
             acc[i] = 0;
+            if (MASK) {
+                const int32_t ms = __reduce_add_sync(0xffffffffu, mis[i]);
+                if (lane == 0 && k < pc && ms != 0) atomicAdd(&miss[k], ms);
+                mis[i] = 0;
+            }
         }
     };
     for (int64_t u = u0; u < u1; ++u) {
@@ -240,15 +251,15 @@ pack_dosage_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n, int6
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int64_t k = k0 + warp * 16 + g * 4 + kk;
-                bool vk = k < pc && ve;  // out-of-range cells were zero-filled by TMA
-                if (MASK) vk = vk && keep[k < pc ? k : 0] != 0;
+                const bool vk = k < pc && ve;  // out-of-range cells were zero-filled by TMA
                 const double v = x[g * 4 + kk];
                 const double t = v * mf;
                 int c = __double2int_rn(t);
                 if (!vk) {
                     c = 0;
                 } else if (!(static_cast<double>(c) == t && c >= 0 && c <= m)) {
-                    bad |= (v != v) ? FLAG_NAN : (isinf(v) ? FLAG_INF : FLAG_NOT_DOSAGE);
+                    if (MASK && v != v) ++mis[g * 4 + kk];  // QC mode: counted per locus, judged by locus_keep_kernel
+                    else bad |= (v != v) ? FLAG_NAN : (isinf(v) ? FLAG_INF : FLAG_NOT_DOSAGE);
                     c = 0;
                 }
                 w |= static_cast<uint32_t>(c) << (8 * kk);
@@ -580,6 +591,173 @@ __global__ void centre_rows_kernel(const long long *__restrict__ r, const long l
     if (i < n) u[i] = h * static_cast<double>(r[i]) + static_cast<double>(T[i]) / mn;
 }
 
+
+// -------------------------------------------------------------------------------------------------------------
+// pack of HOST-quantised chunks (ingest_host.cpp): int8 codes arrive entry-major ([locus][entry], row stride lds, the
+// layout of the caller's matrix) and leave K-major ([entry][locus], the tcgen05 operand layout) — a byte transpose at
+// 2 bytes of HBM traffic per cell, plus the integer column sums and the decoding of the sentinels the host wrote
+// for cells that are not dosage codes.  Unit = 128 loci x 128 entries; a CTA walks a contiguous run of units (entry
+// block fastest), so column sums stay in registers until the locus block changes.
+//   load : warp w owns locus quads 4w .. 4w+3; lane l reads the 32-bit word of entries 4l .. 4l+3 of each of the 4
+//          loci of a quad (one coalesced 128-byte line per locus), then a 4 x 4 byte transpose in registers
+//   smem : tile[entry][locus word ^ swizzle] (33-word rows): conflict-free in both directions
+//   write: 8 threads x 16 bytes = one 128-byte line per entry row
+// -------------------------------------------------------------------------------------------------------------
+constexpr int PC_TILE = 128;
+
+template <bool MASK>
+__global__ void __launch_bounds__(256, 3)
+pack_codes_kernel(const int8_t *__restrict__ src, int64_t lds, int64_t n, int64_t pc, int8_t *__restrict__ codes,
+                  int64_t ldc, int32_t *__restrict__ colsum, int32_t *__restrict__ miss, uint32_t *__restrict__ flags,
+                  int64_t ent_blocks, int64_t units) {
+    __shared__ uint32_t tile[PC_TILE][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+    int32_t acc[16], mis[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = mis[i] = 0;
+    uint32_t bad = 0;
+    int64_t cur_kb = -1;
+    auto flush = [&](int64_t kb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int32_t sum = __reduce_add_sync(0xffffffffu, acc[i]);
+            const int64_t k = kb * PC_TILE + warp * 16 + i;
+            if (lane == 0 && k < pc && sum != 0) atomicAdd(&colsum[k], sum);
+            acc[i] = 0;
+            if (MASK) {
+                const int32_t ms = __reduce_add_sync(0xffffffffu, mis[i]);
+                if (lane == 0 && k < pc && ms != 0) atomicAdd(&miss[k], ms);
+                mis[i] = 0;
+            }
+        }
+    };
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t kb = u / ent_blocks, eb = u - kb * ent_blocks;
+        if (kb != cur_kb) {
+            if (cur_kb >= 0) flush(cur_kb);
+            cur_kb = kb;
+        }
+        const int64_t k0 = kb * PC_TILE, e0 = eb * PC_TILE;
+        const int64_t e = e0 + 4 * lane;
+        // bytes of this lane's word that are real entries (the staging rows are only written up to n)
+        const uint32_t emask = e + 3 < n ? 0xffffffffu : (e >= n ? 0u : (1u << (8 * static_cast<int>(n - e))) - 1u);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int64_t k = k0 + warp * 16 + i;
+            w[i] = (k < pc && emask) ? (__ldg(reinterpret_cast<const uint32_t *>(src + k * lds + e)) & emask) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (w[i] & 0x80808080u) {  // sentinels (negative bytes): decode, then pack the cell as 0
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t v = (w[i] >> (8 * b)) & 0xffu;
+                    if (v & 0x80u) {
+                        if (v == 0x80u) {
+                            if (MASK) ++mis[i];
+                            else bad |= FLAG_NAN;
+                        } else {
+                            bad |= v == 0x81u ? FLAG_NAN_PAYLOAD : (v == 0x82u ? FLAG_INF : FLAG_NOT_DOSAGE);
+                        }
+                        w[i] &= ~(0xffu << (8 * b));
+                    }
+                }
+            }
+            acc[i] = __dp4a(static_cast<int>(w[i]), 0x01010101, acc[i]);  // bytes are 0..64 here: sentinels were cleared
+        }
+        __syncthreads();  // the previous unit's tile has been written out
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const uint32_t a = w[4 * qq], b = w[4 * qq + 1], c = w[4 * qq + 2], d = w[4 * qq + 3];
+            const uint32_t ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);
+            const uint32_t cd_lo = __byte_perm(c, d, 0x5140), cd_hi = __byte_perm(c, d, 0x7362);
+            const int q = warp * 4 + qq, sw = lane >> 3;
+            tile[4 * lane + 0][q ^ sw] = __byte_perm(ab_lo, cd_lo, 0x5410);  // entry 4l:   loci 4q .. 4q+3
+            tile[4 * lane + 1][q ^ sw] = __byte_perm(ab_lo, cd_lo, 0x7632);
+            tile[4 * lane + 2][q ^ sw] = __byte_perm(ab_hi, cd_hi, 0x5410);
+            tile[4 * lane + 3][q ^ sw] = __byte_perm(ab_hi, cd_hi, 0x7632);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int idx = it * 256 + threadIdx.x;
+            const int r = idx >> 3, g = idx & 7, sw = (r >> 5) & 3;
+            if (e0 + r < n) {
+                const uint4 v = make_uint4(tile[r][4 * g + (0 ^ sw)], tile[r][4 * g + (1 ^ sw)], tile[r][4 * g + (2 ^ sw)],
+                                           tile[r][4 * g + (3 ^ sw)]);
+                *reinterpret_cast<uint4 *>(codes + (e0 + r) * ldc + k0 + 16 * g) = v;
+            }
+        }
+    }
+    if (cur_kb >= 0) flush(cur_kb);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) atomicOr(flags, bad);
+}
+
+// QC locus mask from the integers of the pack pass — the reference's filter semantics (src/genomes/filter.jl):
+//   sparsity_k = mean(ismissing(column))   keep iff sparsity_k <= max_locus_sparsity                 (:202-213, :361-368)
+//   q_k = mean(skipmissing(column))        keep iff maf <= q_k <= 1 - maf                            (:632-635)
+// For dosages sum(skipmissing(column)) = colsum/m exactly (any order), so q_k = fl(fl(colsum/m) / cnt) is the very
+// number the FP64 pass (colmean_f64_kernel) computes.  A dropped locus gets colsum 0 (its codes are zeroed by
+// mask_codes_kernel); a KEPT locus that still holds missing cells raises FLAG_NAN when the policy is "error".
+__global__ void locus_keep_kernel(int32_t *__restrict__ colsum, const int32_t *__restrict__ miss, int64_t n, int64_t p,
+                                  double m, double maf, double max_sparsity, int error_on_missing,
+                                  uint8_t *__restrict__ keep, unsigned long long *__restrict__ kept,
+                                  uint32_t *__restrict__ flags) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int kp = 0;
+    uint32_t bad = 0;
+    if (k < p) {
+        const int32_t cnt = static_cast<int32_t>(n) - miss[k];
+        const double sparsity = static_cast<double>(n - cnt) / static_cast<double>(n);
+        const double qk = (static_cast<double>(colsum[k]) / m) / static_cast<double>(cnt);
+        kp = (sparsity <= max_sparsity) && (qk >= maf) && (qk <= (1.0 - maf));
+        keep[k] = static_cast<uint8_t>(kp);
+        if (!kp) colsum[k] = 0;
+        if (kp && error_on_missing && cnt < n) bad = FLAG_NAN;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, kp);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (mk) atomicAdd(kept, static_cast<unsigned long long>(__popc(mk)));
+        if (bad) atomicOr(flags, bad);
+    }
+}
+
+// codes[i, k] = 0 for every dropped locus k: thread = 16 loci of one entry row; rows whose 16 loci are all kept
+// are not touched (keep is p bytes: L2-resident)
+__global__ void __launch_bounds__(256)
+mask_codes_kernel(int8_t *__restrict__ codes, int64_t n, int64_t p, int64_t ldc, const uint8_t *__restrict__ keep) {
+    const int64_t groups = (p + 15) / 16;
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * 32 + (threadIdx.x & 31);
+    if (g >= groups) return;
+    const int64_t k = g * 16;
+    uint32_t mk[4];
+#pragma unroll
+    for (int wv = 0; wv < 4; ++wv) {
+        uint32_t mw = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t kk = k + 4 * wv + b;
+            if (kk >= p || keep[kk]) mw |= 0xffu << (8 * b);
+        }
+        mk[wv] = mw;
+    }
+    if ((mk[0] & mk[1] & mk[2] & mk[3]) == 0xffffffffu) return;
+    for (int64_t i = static_cast<int64_t>(blockIdx.y) * 8 + (threadIdx.x >> 5); i < n;
+         i += static_cast<int64_t>(gridDim.y) * 8) {
+        uint4 *ptr = reinterpret_cast<uint4 *>(codes + i * ldc + k);
+        uint4 v = *ptr;
+        v.x &= mk[0];
+        v.y &= mk[1];
+        v.z &= mk[2];
+        v.w &= mk[3];
+        *ptr = v;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -626,7 +804,7 @@ extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *
 
 extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
                                         int32_t m, int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
-                                        const uint8_t *d_keep) {
+                                        int32_t *d_miss) {
     if (!ctx || !dA || !d_codes || !d_colsum || !d_flags || n < 1 || pc < 1 || lda < n || m < 1 || m > 64 ||
         (m & (m - 1)) != 0 || (ldc % 128) != 0 || ldc < ((pc + 127) / 128) * 128) {
         grm_set_error("pack_dosage: bad argument (n=%lld pc=%lld lda=%lld m=%d ldc=%lld)", (long long)n, (long long)pc,
@@ -634,8 +812,7 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
-    const char *pack_env = getenv("GRM_CUDA_PACK");  // "ldg" forces the non-TMA variant (read per call: A/B timing)
-    const bool use_tma = !(pack_env && !strcmp(pack_env, "ldg")) && !ctx->pack_small_footprint;
+    const bool use_tma = ctx->tune.pack != 1;
     if (use_tma && (lda % 2) == 0 && (reinterpret_cast<uintptr_t>(dA) % 16) == 0 && n < (1ll << 31) && pc < (1ll << 31)) {
         // TMA-staged variant: needs 16-byte aligned rows of A (global strides are multiples of 16 bytes)
         GrmEncodeTiledFn encode = nullptr;
@@ -652,23 +829,18 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
             grm_set_error("cuTensorMapEncodeTiled (FP64 input) failed with CUresult %d", static_cast<int>(r));
             return GRM_CUDA_ERR_CUDA;
         }
-        static bool attr_set = false;
-        if (!attr_set) {
-            GRM_CUDA_TRY(cudaFuncSetAttribute(pack_dosage_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(PT_SMEM)));
-            GRM_CUDA_TRY(cudaFuncSetAttribute(pack_dosage_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(PT_SMEM)));
-            attr_set = true;
-        }
         const int64_t ent_blocks = (n + PT_ENT - 1) / PT_ENT, loc_blocks = (pc + PT_LOCI - 1) / PT_LOCI;
         const int64_t units = ent_blocks * loc_blocks;
         const int grid = static_cast<int>(std::min<int64_t>(units, 2ll * ctx->num_sms));
-        if (d_keep)
+        if (d_miss) {
+            GRM_TRY(grm_func_smem(ctx, reinterpret_cast<const void *>(pack_dosage_tma_kernel<true>), PT_SMEM));
             pack_dosage_tma_kernel<true><<<grid, 288, PT_SMEM, ctx->stream>>>(tmap, n, pc, m, d_codes, ldc, d_colsum,
-                                                                             d_flags, d_keep, ent_blocks, units);
-        else
+                                                                             d_flags, d_miss, ent_blocks, units);
+        } else {
+            GRM_TRY(grm_func_smem(ctx, reinterpret_cast<const void *>(pack_dosage_tma_kernel<false>), PT_SMEM));
             pack_dosage_tma_kernel<false><<<grid, 288, PT_SMEM, ctx->stream>>>(tmap, n, pc, m, d_codes, ldc, d_colsum,
                                                                               d_flags, nullptr, ent_blocks, units);
+        }
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         return GRM_CUDA_OK;
@@ -676,18 +848,67 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
     constexpr int EITERS = 4;
     dim3 grid(static_cast<unsigned>((pc + PK_LOCI - 1) / PK_LOCI),
               static_cast<unsigned>((n + PK_SLAB * EITERS - 1) / (PK_SLAB * EITERS)));
-    // experiment knob: unused dynamic shared memory (KB) to cap the CTAs resident per SM
-    const char *pad_env = getenv("GRM_CUDA_PACK_PAD");
-    const size_t pad = pad_env ? static_cast<size_t>(atol(pad_env)) << 10 : 0;
-    if (pad > 0)
-        GRM_CUDA_TRY(cudaFuncSetAttribute(pack_dosage_kernel<EITERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(pad)));
-    if (d_keep)
+    if (d_miss)
         pack_dosage_kernel<EITERS, true><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
-                                                                        d_flags, d_keep);
+                                                                        d_flags, d_miss);
     else
-        pack_dosage_kernel<EITERS, false><<<grid, 256, pad, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
-                                                                           d_flags, nullptr);
+        pack_dosage_kernel<EITERS, false><<<grid, 256, 0, ctx->stream>>>(dA, n, pc, lda, m, d_codes, ldc, d_colsum,
+                                                                         d_flags, nullptr);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_pack_codes(grm_cuda_ctx *ctx, const int8_t *d_src, int64_t n, int64_t pc, int64_t lds,
+                                       int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
+                                       int32_t *d_miss) {
+    if (!ctx || !d_src || !d_codes || !d_colsum || !d_flags || n < 1 || pc < 1 || lds < n || (lds % 4) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_src) % 4) != 0 || (ldc % 128) != 0 || ldc < ((pc + 127) / 128) * 128) {
+        grm_set_error("pack_codes: bad argument (n=%lld pc=%lld lds=%lld ldc=%lld)", (long long)n, (long long)pc,
+                      (long long)lds, (long long)ldc);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t ent_blocks = (n + PC_TILE - 1) / PC_TILE, loc_blocks = (pc + PC_TILE - 1) / PC_TILE;
+    const int64_t units = ent_blocks * loc_blocks;
+    const int grid = static_cast<int>(std::min<int64_t>(units, 3ll * ctx->num_sms));
+    if (d_miss)
+        pack_codes_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_src, lds, n, pc, d_codes, ldc, d_colsum, d_miss, d_flags,
+                                                               ent_blocks, units);
+    else
+        pack_codes_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_src, lds, n, pc, d_codes, ldc, d_colsum, nullptr,
+                                                                d_flags, ent_blocks, units);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_locus_keep(grm_cuda_ctx *ctx, int32_t *d_colsum, const int32_t *d_miss, int64_t n, int64_t p,
+                                       int32_t m, double maf, double max_locus_sparsity, int32_t error_on_missing,
+                                       uint8_t *d_keep, uint64_t *d_kept, uint32_t *d_flags) {
+    if (!ctx || !d_colsum || !d_miss || !d_keep || !d_kept || !d_flags || n < 1 || p < 1 || m < 1) {
+        grm_set_error("locus_keep: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    locus_keep_kernel<<<static_cast<unsigned>((p + 255) / 256), 256, 0, ctx->stream>>>(
+        d_colsum, d_miss, n, p, static_cast<double>(m), maf, max_locus_sparsity, error_on_missing, d_keep,
+        reinterpret_cast<unsigned long long *>(d_kept), d_flags);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_mask_codes(grm_cuda_ctx *ctx, int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                       const uint8_t *d_keep) {
+    if (!ctx || !d_codes || !d_keep || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p) {
+        grm_set_error("mask_codes: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t groups = (p + 15) / 16;
+    dim3 grid(static_cast<unsigned>((groups + 31) / 32), static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, 64)));
+    mask_codes_kernel<<<grid, 256, 0, ctx->stream>>>(d_codes, n, p, ldc, d_keep);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;

@@ -245,10 +245,6 @@ static int32_t repair_setup(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx
     r.d_diag = reinterpret_cast<double *>(r.ipiv + int_slots);
     r.h_diag.resize(n);
     r.h_ipiv.resize(n);
-    {
-        const char *e = getenv("GRM_CUDA_GETRF");
-        if (e && e[0] == 'x') r.xalg = (e[1] == '1') ? 1 : 0;
-    }
     if (r.xalg >= 0) {
         GRM_SOLVER_TRY(cusolverDnCreateParams(&r.params));
         GRM_SOLVER_TRY(cusolverDnSetAdvOptions(r.params, CUSOLVERDN_GETRF, r.xalg == 1 ? CUSOLVER_ALG_1 : CUSOLVER_ALG_0));

@@ -197,9 +197,9 @@ centre_f64_kernel(const double *__restrict__ A, int64_t n, int64_t pc, int64_t l
 
 int32_t get_tile_list_f64(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_tiles, int *count) {
     TileListCache &tc = ctx->tiles_f64;
-    if (tc.n != n || tc.rank != rank || tc.world != world) {
+    if (tc.n != n || tc.rank != rank || tc.world != world || tc.kind != ctx->tune.tile_band) {
         std::vector<int2> order;
-        grm_tile_order(n, order);
+        grm_tile_order(n, ctx->tune.tile_band, order);
         int64_t b, e;
         grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
         std::vector<int2> blk;
@@ -219,6 +219,7 @@ int32_t get_tile_list_f64(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t wo
         tc.n = n;
         tc.rank = rank;
         tc.world = world;
+        tc.kind = ctx->tune.tile_band;
         tc.count = static_cast<int32_t>(blk.size());
     }
     *d_tiles = tc.buf.as<int2>();
@@ -240,12 +241,7 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_
     int count;
     GRM_TRY(get_tile_list_f64(ctx, n, rank, world, &d_tiles, &count));
     if (count == 0) return GRM_CUDA_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(F64_SMEM)));
-        attr_set = true;
-    }
+    GRM_TRY(grm_func_smem(ctx, reinterpret_cast<const void *>(syrk_f64_kernel), F64_SMEM));
     syrk_f64_kernel<<<count, 256, F64_SMEM, ctx->stream>>>(dZ, n, p, ldz, d_tiles, d_G, ldg, accumulate);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;

@@ -10,9 +10,10 @@
 //   warp 1      MMA issuer:   one thread issues tcgen05.mma.kind::i8, accumulators (int32) in TMEM
 //   warps 2..5  epilogue:     tcgen05.ld TMEM -> registers -> (int32 | FP64 formula) -> global, overlapped with the
 //                             next tile's main loop through two TMEM accumulator stages (2 x 256 columns)
-// Two variants of the same pipeline:
+// Three variants of the same pipeline (chosen by launch(); grm_cuda_ctx_set_tuning("syrk_i8", ...) forces one):
 //   syrk_i8_2cta_kernel (default)  CTA pairs, cta_group::2, UMMA 256 x 256 x 32, 256 x 256 tiles, 6 x 32 KB stages
-//   syrk_i8_kernel (GRM_CUDA_SYRK_I8=1cta)  single CTA, UMMA 128 x 256 x 32, 128 x 256 tiles, 4 x 48 KB stages
+//   syrk_i8_wide_kernel (long K)   CTA pairs on two tiles that share their column panel, 4 x 48 KB stages
+//   syrk_i8_kernel                 single CTA, UMMA 128 x 256 x 32, 128 x 256 tiles, 4 x 48 KB stages
 // Work items come from a host-built list that covers only the upper triangle.
 #include <math.h>
 #include <stdlib.h>
@@ -34,8 +35,6 @@ constexpr int NUM_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 2 * BN;              // two accumulator stages of 256 int32 columns
 constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-constexpr int GRM_MAX_PEERS = 8;
-
 struct EpiParams {
     int64_t n;
     int32_t *C;      // mode 0
@@ -48,13 +47,6 @@ struct EpiParams {
     const int32_t *slots;  // mode 3: slot of tile t in the packed int32 tile buffer C ([slot][256 cols][256 rows])
     double *Gt;            // modes 1, 2 (2-CTA kernel): if set, tile t is stored packed at Gt + t*65536 ([col][row],
                            // zeros outside n) instead of into the dense matrix G: the sharded-output form
-    const int32_t *prev;   // 2-CTA kernel, modes 1-3: if set, packed int32 tiles ([slot][col][row]) holding the partial
-                           // sums of earlier loci chunks; added to the accumulator before the mode's own epilogue
-    // mode 3, peer-store form (tiles_max > 0): the tile in slot (o, s) = (slot / tiles_max, slot % tiles_max) is stored
-    // straight into GPU o's receive buffer over NVLink, at part `src_rank`: peers[o] + (src_rank*tiles_max + s)*65536
-    int32_t *peers[GRM_MAX_PEERS];
-    int32_t tiles_max;
-    int32_t src_rank;
 };
 
 // Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
@@ -252,14 +244,14 @@ constexpr size_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 // 10 GB operand of C3 (L2 hit rate 51 %, HBM at 69 % of peak while the tensor pipe waits for power).  The leader's
 // producer publishes its global K step every SYNC_PUBLISH blocks; a watcher warp (warp 6 of the leader) keeps
 // min(progress of all pairs) + SYNC_WINDOW in shared memory, and the producer does not issue a load beyond it.  The
-// slowest pair never waits (no deadlock; all CTAs of the grid are co-resident: one per SM), and with a static tile
-// assignment the fast pairs would only have idled at the end anyway.  Measured on C3: 102 ms -> 66 ms.
+// slowest pair never waits, and with a static tile assignment the fast pairs would only have idled at the end anyway.
+// The launch only enables it when the whole grid fits the idle device (cudaOccupancyMaxActiveClusters) and launches
+// cooperatively so that every pair is co-resident; the wait itself is bounded and degrades to "no throttle"
+// (k_window_wait), so a foreign kernel holding SMs can cost bandwidth but never hangs or traps.
+// Measured on C3: 102 ms -> 66 ms.
 constexpr uint32_t SYNC_PUBLISH = 8, SYNC_WINDOW_DEFAULT = 64;
 constexpr bool SYRK_WIDE_DEFAULT = true;  // two tiles per CTA pair sharing the column panel (long contractions)
 constexpr int SYRK_WIDE_MIN_KB = 2048;
-constexpr bool SYRK_WIDE_PACKED_DEFAULT = false;
-constexpr int SYRK_WIDE_PACKED_MIN_KB = 1900;
-constexpr bool SYRK_QUAD_DEFAULT = false;  // clusters of 4 with multicast of the shared column panel
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
     uint32_t v;
@@ -281,32 +273,13 @@ __device__ __forceinline__ void drain_tile(const EpiParams &ep, int t, int2 tc, 
     if (EPI == 2 && row_ok) ui = ep.u[row];
     const int64_t slot = ep.slots ? static_cast<int64_t>(ep.slots[t]) : static_cast<int64_t>(t);
     int32_t *packed = nullptr;
-    if (EPI == 3) {
-        if (ep.tiles_max > 0) {
-            const int64_t o = slot / ep.tiles_max, sl = slot - o * ep.tiles_max;
-            packed = ep.peers[o] + (static_cast<int64_t>(ep.src_rank) * ep.tiles_max + sl) * 65536;
-        } else {
-            packed = ep.C + slot * 65536;
-        }
-    }
+    if (EPI == 3) packed = ep.C + slot * 65536;
     const int row_local = 128 * static_cast<int>(cta) + quarter * 32 + lane;
-    const int32_t *prev = (EPI != 0 && ep.prev) ? ep.prev + slot * 65536 + row_local : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < 256; c0 += 32) {
         uint32_t r[32];
-        if (prev) {
-            // partial sums of the earlier loci chunks: issue the (coalesced) loads before waiting on TMEM
-            int32_t pv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pv[j] = prev[(c0 + j) * 256];
-            tmem_ld_32x32(tmem_acc + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] += static_cast<uint32_t>(pv[j]);
-        } else {
-            tmem_ld_32x32(tmem_acc + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
-            tmem_wait_ld();
-        }
+        tmem_ld_32x32(tmem_acc + c0 + (static_cast<uint32_t>(quarter * 32) << 16), r);
+        tmem_wait_ld();
         if (EPI == 3) {
             epilogue_store_packed(r, packed, row_local, c0);
         } else if ((EPI == 1 || EPI == 2) && ep.Gt != nullptr) {
@@ -321,19 +294,28 @@ __device__ __forceinline__ void drain_tile(const EpiParams &ep, int t, int2 tc, 
     }
 }
 
-// QUAD = false: clusters of 2 (one CTA pair per cluster), one 256 x 256 tile per pair at a time.
-// QUAD = true : clusters of 4 = two CTA pairs working on two consecutive tiles of the list.  Consecutive tiles
-//   share their column panel (tile.y) almost always; then each CTA loads only HALF of its 128-row B block (64 rows,
-//   tmap64) and multicasts it to the CTA of the same parity in the other pair, so that a B row crosses the L2 -> SM
-//   fabric once for both pairs: 24 KB instead of 32 KB per CTA and K block.  The int8 SYRK is fed at the chip's
-//   L2 -> SM limit (pairs: 64 B/clk/SM needed, ~52 sustained; profiles/README.md), so fewer bytes per MAC is what buys
-//   tensor-pipe time.  A shared-memory stage of a CTA is then written by two CTAs, so a stage is released by the
-//   commits of BOTH pairs (empty barriers count 2, commit multicast to all four CTAs): the pairs advance in lock-step.
-template <int EPI, bool QUAD>
-__device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensorMap &tmap, const CUtensorMap &tmap64,
-                                               const int2 *__restrict__ tiles, int num_tiles, int num_kb, int kb_per_slab,
-                                               const EpiParams &ep, uint32_t *__restrict__ progress, uint32_t sync_params) {
-    const uint32_t sync_window = sync_params;  // K window of the pair synchronisation
+// K-window throttle of a producer: publish the K step, then hold back while more than the window ahead of the slowest
+// pair.  The wait is bounded: a pair that is not running (the grid is not fully co-resident because some other kernel of
+// the host application holds SMs) must not stall the others for ever, let alone trap — after the bound this producer
+// simply stops throttling for the rest of the kernel (the window is a bandwidth optimisation, never a correctness
+// requirement).
+__device__ __forceinline__ void k_window_wait(uint32_t *progress, int pair, uint32_t step, volatile uint32_t *sync_allowed,
+                                              bool &throttle) {
+    if ((step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
+    uint32_t spins = 0;
+    while (step > *sync_allowed) {
+        if (++spins > (1u << 22)) {  // ~10 ms: far beyond any drift between co-resident pairs
+            throttle = false;
+            break;
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
+                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_window) {
+    extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
     uint64_t *empty_bar = full_bar + STAGES2;
@@ -345,38 +327,15 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t crank = cluster_ctarank();
-    const uint32_t cta = crank & 1u;          // rank inside the CTA pair (0 = leader: issues the MMAs)
-    const uint32_t pbase = crank & ~1u;       // cluster rank of the pair's leader
-    const uint32_t pidx = crank >> 1;         // pair inside the cluster (0 unless QUAD)
+    const uint32_t cta = cluster_ctarank();  // rank inside the CTA pair (0 = leader: issues the MMAs)
     const bool leader = cta == 0;
-    // `pair` = work-group index: a CTA pair (clusters of 2) or a quad (clusters of 4, two tiles at a time)
-    const int pair = QUAD ? (blockIdx.x >> 2) : (blockIdx.x >> 1);
-    const int num_pairs = QUAD ? (gridDim.x >> 2) : (gridDim.x >> 1);
-    const int tiles_per_group = QUAD ? 2 : 1;
-    const int num_units = (num_tiles + tiles_per_group - 1) / tiles_per_group;
-    // tile of this CTA's pair in unit u; QUAD: an odd tail leaves pair 1 without a tile — it then shadows pair 0's tile
-    // (keeps the lock-step barriers balanced) and stores nothing
-    auto unit_tile = [&](int u, int &t, bool &active, bool &shared) {
-        if (!QUAD) {
-            t = u;
-            active = true;
-            shared = false;
-            return;
-        }
-        const int t0 = 2 * u, t1 = 2 * u + 1;
-        const bool has1 = t1 < num_tiles;
-        t = (pidx == 0 || !has1) ? t0 : t1;
-        active = pidx == 0 || has1;
-        shared = !has1 || tiles[t0].y == tiles[t1].y;
-    };
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
-        if (QUAD) tma_prefetch_desc(&tmap64);
         for (int s = 0; s < STAGES2; ++s) {
             mbar_init(&full_bar[s], 1);   // the leader's arrive.expect_tx covers the bytes of BOTH CTAs (leader only)
-            mbar_init(&empty_bar[s], QUAD ? 2 : 1);  // one multicast tcgen05.commit per pair and use, in each CTA
+            mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit per use, in each CTA
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);   // multicast commit, in each CTA
@@ -399,21 +358,14 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, step = 0;
-            const bool throttle = progress != nullptr && crank == 0;
-            for (int u = pair; u < num_units; u += num_pairs) {
-                int t;
-                bool active, shared;
-                unit_tile(u, t, active, shared);
+            const bool publish = progress != nullptr && leader;
+            bool throttle = publish;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
                 const int2 tc = tiles[t];
                 int slab = 0, kin = 0;
                 for (int kb = 0; kb < num_kb; ++kb, ++step) {
-                    if (throttle) {
-                        if ((step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
-                        uint32_t spins = 0;
-                        while (step > *sync_allowed) {  // more than the window ahead of the slowest pair
-                            if (++spins > (1u << 28)) __trap();  // a pair that never starts: fail, do not hang
-                        }
-                    }
+                    if (throttle) k_window_wait(progress, pair, step, sync_allowed, throttle);
+                    else if (publish && (step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *sA = smem + stage * STAGE2_BYTES;
                     uint8_t *sB = sA + A_BYTES;
@@ -421,14 +373,7 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
                     // negative, the phase cannot complete before the leader's (only) arrival.
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
                     tma_load_3d_2cta(sA, &tmap, &full_bar[stage], kin * BK, tc.x + 128 * static_cast<int>(cta), slab);
-                    if (QUAD && shared) {
-                        // rows [64 pidx, 64 pidx + 64) of this parity's B block, to both CTAs of this parity
-                        tma_load_3d_2cta_mc(sB + 64 * BK * pidx, &tmap64, &full_bar[stage], kin * BK,
-                                            tc.y + 128 * static_cast<int>(cta) + 64 * static_cast<int>(pidx), slab,
-                                            static_cast<uint16_t>(0b0101u << cta));
-                    } else {
-                        tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, tc.y + 128 * static_cast<int>(cta), slab);
-                    }
+                    tma_load_3d_2cta(sB, &tmap, &full_bar[stage], kin * BK, tc.y + 128 * static_cast<int>(cta), slab);
                     if (++kin == kb_per_slab) {
                         kin = 0;
                         ++slab;
@@ -439,14 +384,14 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
                     }
                 }
             }
-            if (throttle) {
+            if (publish) {
                 st_relaxed_u32(&progress[pair], 0xffffffffu);  // done: nobody waits for this pair
                 *sync_done = 1;
             }
         }
     } else if (warp == 6) {
         // ===================== K-window watcher (leader CTA) =====================
-        if (progress != nullptr && crank == 0) {
+        if (progress != nullptr && leader) {
             while (*sync_done == 0) {
                 uint32_t mn = 0xffffffffu;
                 for (int i = lane; i < num_pairs; i += 32) mn = min(mn, ld_relaxed_u32(&progress[i]));
@@ -462,9 +407,7 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            const uint16_t stage_mask = QUAD ? 0b1111 : 0b11;                     // every CTA that fills this stage
-            const uint16_t pair_mask = static_cast<uint16_t>(0b11u << pbase);     // the two CTAs of this pair
-            for (int u = pair; u < num_units; u += num_pairs, ++local) {
+            for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -479,38 +422,29 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_i8_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_2cta(&empty_bar[stage], stage_mask);
+                    umma_commit_2cta(&empty_bar[stage], 0b11);
                     if (++stage == STAGES2) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit_2cta(&tmem_full[acc], pair_mask);
+                umma_commit_2cta(&tmem_full[acc], 0b11);
             }
         }
     } else {
         // ===================== epilogue (warps 2..5 of both CTAs; CTA r owns rows 128 r .. 128 r + 127) ===========
         const int quarter = warp & 3;
         int local = 0;
-        for (int u = pair; u < num_units; u += num_pairs, ++local) {
+        for (int t = pair; t < num_tiles; t += num_pairs, ++local) {
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            int t;
-            bool active, shared;
-            unit_tile(u, t, active, shared);
             const int2 tc = tiles[t];
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            if (!active) {  // shadow tile of an odd tail: nothing to store
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], pbase);
-                continue;
-            }
             drain_tile<EPI>(ep, t, tc, tmem_base + acc * 256, cta, quarter, lane);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], pbase);
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
         }
     }
 
@@ -520,23 +454,6 @@ __device__ __forceinline__ void syrk_pair_body(uint8_t *smem_raw, const CUtensor
         __syncwarp();
         tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
     }
-}
-
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
-syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int num_tiles, int num_kb,
-                    int kb_per_slab, EpiParams ep, uint32_t *__restrict__ progress, uint32_t sync_params) {
-    extern __shared__ uint8_t smem_raw[];
-    syrk_pair_body<EPI, false>(smem_raw, tmap, tmap, tiles, num_tiles, num_kb, kb_per_slab, ep, progress, sync_params);
-}
-
-template <int EPI>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
-syrk_i8_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
-                    const int2 *__restrict__ tiles, int num_tiles, int num_kb, int kb_per_slab, EpiParams ep,
-                    uint32_t *__restrict__ progress, uint32_t sync_params) {
-    extern __shared__ uint8_t smem_raw[];
-    syrk_pair_body<EPI, true>(smem_raw, tmap, tmap64, tiles, num_tiles, num_kb, kb_per_slab, ep, progress, sync_params);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -598,7 +515,8 @@ syrk_i8_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, step = 0;
-            const bool throttle = progress != nullptr && leader;
+            const bool publish = progress != nullptr && leader;
+            bool throttle = publish;
             for (int u = pair; u < num_units; u += num_pairs) {
                 const int2 un = units[u];
                 const bool two = un.y >= 0;
@@ -607,13 +525,8 @@ syrk_i8_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                 const uint32_t bytes = 2 * (two ? STAGEW_BYTES : 2 * A_BYTES);
                 int slab = 0, kin = 0;
                 for (int kb = 0; kb < num_kb; ++kb, ++step) {
-                    if (throttle) {
-                        if ((step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
-                        uint32_t spins = 0;
-                        while (step > *sync_allowed) {
-                            if (++spins > (1u << 28)) __trap();
-                        }
-                    }
+                    if (throttle) k_window_wait(progress, pair, step, sync_allowed, throttle);
+                    else if (publish && (step % SYNC_PUBLISH) == 0) st_relaxed_u32(&progress[pair], step);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *sA0 = smem + stage * STAGEW_BYTES;
                     uint8_t *sA1 = sA0 + A_BYTES;
@@ -632,7 +545,7 @@ syrk_i8_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
                     }
                 }
             }
-            if (throttle) {
+            if (publish) {
                 st_relaxed_u32(&progress[pair], 0xffffffffu);
                 *sync_done = 1;
             }
@@ -704,8 +617,7 @@ syrk_i8_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
     }
 }
 
-int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out,
-                        uint32_t box_rows = 128u) {
+int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs, CUtensorMap *out) {
     GrmEncodeTiledFn encode = nullptr;
     GRM_TRY(grm_tmap_encoder(&encode));
     // dim0 = loci of one slab (bytes, contiguous), dim1 = entries, dim2 = slab.  Out-of-range rows/loci are
@@ -713,7 +625,7 @@ int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc
     // to the integer sums.
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(nslabs)};
     cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ldc), static_cast<cuuint64_t>(ldc) * static_cast<cuuint64_t>(n)};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), box_rows, 1u};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), 128u, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(d_codes), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -726,12 +638,33 @@ int32_t make_codes_tmap(const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc
     return GRM_CUDA_OK;
 }
 
+int32_t upload_list(grm_cuda_ctx *ctx, TileListCache &tc, const void *data, size_t bytes) {
+    GRM_TRY(tc.buf.reserve(std::max<size_t>(bytes, 16)));
+    if (bytes) {
+        // pageable -> device copy is synchronous with respect to the host buffer, safe to free afterwards
+        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return GRM_CUDA_OK;
+}
+
+bool list_cached(const grm_cuda_ctx *ctx, TileListCache &tc, int64_t n, int32_t rank, int32_t world) {
+    return tc.n == n && tc.rank == rank && tc.world == world && tc.kind == ctx->tune.tile_band;
+}
+void list_stamp(const grm_cuda_ctx *ctx, TileListCache &tc, int64_t n, int32_t rank, int32_t world, size_t count) {
+    tc.n = n;
+    tc.rank = rank;
+    tc.world = world;
+    tc.kind = ctx->tune.tile_band;
+    tc.count = static_cast<int32_t>(count);
+}
+
 // 128 x 256 CTA tiles of the owned 256 x 256 sharding tiles, in the L2-friendly order of grm_tile_order().
 int32_t get_tile_list(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_tiles, int *count) {
     TileListCache &tc = ctx->tiles_i8;
-    if (tc.n != n || tc.rank != rank || tc.world != world) {
+    if (!list_cached(ctx, tc, n, rank, world)) {
         std::vector<int2> order;
-        grm_tile_order(n, order);
+        grm_tile_order(n, ctx->tune.tile_band, order);
         int64_t b, e;
         grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
         std::vector<int2> cta;
@@ -741,15 +674,8 @@ int32_t get_tile_list(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world,
             cta.push_back(make_int2(row0, col0));
             if (row0 + BM < n) cta.push_back(make_int2(row0 + BM, col0));
         }
-        GRM_TRY(tc.buf.reserve(std::max<size_t>(cta.size(), 1) * sizeof(int2)));
-        // pageable -> device copy is synchronous with respect to the host buffer, safe to free afterwards
-        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, cta.data(), cta.size() * sizeof(int2), cudaMemcpyHostToDevice,
-                                     ctx->stream));
-        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        tc.n = n;
-        tc.rank = rank;
-        tc.world = world;
-        tc.count = static_cast<int32_t>(cta.size());
+        GRM_TRY(upload_list(ctx, tc, cta.data(), cta.size() * sizeof(int2)));
+        list_stamp(ctx, tc, n, rank, world, cta.size());
     }
     *d_tiles = tc.buf.as<int2>();
     *count = tc.count;
@@ -759,108 +685,146 @@ int32_t get_tile_list(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world,
 // 256 x 256 tiles (one per CTA pair) of the owned sharding tiles
 int32_t get_tile_list_2cta(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_tiles, int *count) {
     TileListCache &tc = ctx->tiles_i8_2cta;
-    if (tc.n != n || tc.rank != rank || tc.world != world) {
+    if (!list_cached(ctx, tc, n, rank, world)) {
         std::vector<int2> order;
-        grm_tile_order(n, order);
+        grm_tile_order(n, ctx->tune.tile_band, order);
         int64_t b, e;
         grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
         std::vector<int2> tl;
         for (int64_t t = b; t < e; ++t) tl.push_back(make_int2(order[t].x * GRM_TILE, order[t].y * GRM_TILE));
-        GRM_TRY(tc.buf.reserve(std::max<size_t>(tl.size(), 1) * sizeof(int2)));
-        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, tl.data(), tl.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        tc.n = n;
-        tc.rank = rank;
-        tc.world = world;
-        tc.count = static_cast<int32_t>(tl.size());
+        GRM_TRY(upload_list(ctx, tc, tl.data(), tl.size() * sizeof(int2)));
+        list_stamp(ctx, tc, n, rank, world, tl.size());
     }
     *d_tiles = tc.buf.as<int2>();
     *count = tc.count;
     return GRM_CUDA_OK;
 }
 
-// zeroed progress words for the K-window synchronisation (GRM_CUDA_SYRK_SYNC=0 switches it off, =1 forces it).
-// It pays when drift can build up AND the operand is far larger than L2: many tiles per pair and a multi-GB operand
-// (C3 on one GPU: 10 GB, 43 tiles per pair: 73 -> 54 ms).  Measured neutral at 5 GB (C3 on 2 GPUs) and a loss for
-// short launches (C2: +5 %; C3 on 4 / 8 GPUs, 2.5 / 1.25 GB per GPU: +11 %), so it is enabled from 6 GB up.
-int32_t sync_buffer(grm_cuda_ctx *ctx, int pairs, int tiles, int64_t operand_bytes, uint32_t **out) {
-    const char *e = getenv("GRM_CUDA_SYRK_SYNC");
-    const bool forced = e && e[0] == '1';
-    if ((e && e[0] == '0') || (!forced && (tiles < 6 * pairs || operand_bytes < (6ll << 30)))) {
-        *out = nullptr;
-        return GRM_CUDA_OK;
+// units of the wide kernel: two consecutive tiles of a list that share their column panel, or one leftover tile
+void make_wide_units(const std::vector<int2> &tiles, size_t t0, size_t t1, std::vector<int2> &units) {
+    for (size_t t = t0; t < t1;) {
+        if (t + 1 < t1 && tiles[t].y == tiles[t + 1].y) {
+            units.push_back(make_int2(static_cast<int>(t), static_cast<int>(t + 1)));
+            t += 2;
+        } else {
+            units.push_back(make_int2(static_cast<int>(t), -1));
+            t += 1;
+        }
     }
-    GRM_TRY(ctx->progress.reserve(static_cast<size_t>(pairs) * sizeof(uint32_t) + 64));
-    GRM_CUDA_TRY(cudaMemsetAsync(ctx->progress.ptr, 0, static_cast<size_t>(pairs) * sizeof(uint32_t), ctx->stream));
-    *out = ctx->progress.as<uint32_t>();
-    return GRM_CUDA_OK;
 }
 
-uint32_t sync_window() {
-    const char *e = getenv("GRM_CUDA_SYRK_WINDOW");
-    const long v = e ? atol(e) : 0;
-    const uint32_t window = (v > 0 && v < 65536) ? static_cast<uint32_t>(v) : SYNC_WINDOW_DEFAULT;
-    return window;
-}
-
-// units of the wide kernel: two consecutive tiles of the list that share their column panel, or one leftover tile
 int32_t get_wide_units(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t world, const int2 **d_units, int *num_units) {
     TileListCache &tc = ctx->tiles_wide;
-    if (tc.n != n || tc.rank != rank || tc.world != world) {
+    if (!list_cached(ctx, tc, n, rank, world)) {
         std::vector<int2> order;
-        grm_tile_order(n, order);
+        grm_tile_order(n, ctx->tune.tile_band, order);
         int64_t b, e;
         grm_tile_range(static_cast<int64_t>(order.size()), rank, world, &b, &e);
-        std::vector<int2> units;
-        for (int64_t t = b; t < e;) {
-            if (t + 1 < e && order[t].y == order[t + 1].y) {
-                units.push_back(make_int2(static_cast<int>(t - b), static_cast<int>(t + 1 - b)));
-                t += 2;
-            } else {
-                units.push_back(make_int2(static_cast<int>(t - b), -1));
-                t += 1;
-            }
-        }
-        GRM_TRY(tc.buf.reserve(std::max<size_t>(units.size(), 1) * sizeof(int2)));
-        if (!units.empty())
-            GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, units.data(), units.size() * sizeof(int2), cudaMemcpyHostToDevice,
-                                         ctx->stream));
-        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        tc.n = n;
-        tc.rank = rank;
-        tc.world = world;
-        tc.count = static_cast<int32_t>(units.size());
+        std::vector<int2> own(order.begin() + b, order.begin() + e), units;
+        make_wide_units(own, 0, own.size(), units);
+        GRM_TRY(upload_list(ctx, tc, units.data(), units.size() * sizeof(int2)));
+        list_stamp(ctx, tc, n, rank, world, units.size());
     }
     *d_units = tc.buf.as<int2>();
     *num_units = tc.count;
     return GRM_CUDA_OK;
 }
 
-// wide kernel: "wide" forces it, "2cta"/"quad"/"1cta" exclude it; by default it is used when a unit's main loop is
-// long enough to dwarf its un-overlapped epilogue (>= SYRK_WIDE_MIN_KB K blocks) and there are enough tiles to keep
-// every pair busy with two-tile units.  Measured: C3 (3907 K blocks, 3160 tiles) SYRK 56.5 -> 51.7 ms; C2 (781 K
-// blocks, 210 tiles) 0.76 -> 0.97 ms, hence the thresholds.
-bool use_wide(int num_kb, int num_tiles, int num_sms) {
-    const char *e = getenv("GRM_CUDA_SYRK_I8");
-    if (e) return !strcmp(e, "wide");
-    return SYRK_WIDE_DEFAULT && num_kb >= SYRK_WIDE_MIN_KB && num_tiles >= 4 * (num_sms / 2);
+// ---------------------------------------------------------------------------------------------------------------
+// Launch of a persistent CTA-pair kernel, with or without the K-window synchronisation.
+//
+// The window pays when drift can build up AND the operand is far larger than L2: many tiles per pair and a multi-GB
+// operand (C3 on one GPU: 10 GB, 43 tiles per pair: 73 -> 54 ms).  Measured neutral at 5 GB (C3 on 2 GPUs) and a loss
+// for short launches (C2: +5 %; C3 on 4 / 8 GPUs: +11 %), so it is enabled from 6 GB up (tune.syrk_sync forces it
+// on / off).  It is only used when every pair of the grid can be co-resident: the capacity of the idle device is
+// checked (cudaOccupancyMaxActiveClusters) and the launch is made cooperative, so the driver starts the grid only
+// once all of it fits next to whatever else the host application is running.  If the cooperative launch is refused
+// the kernel is launched without the window.
+// ---------------------------------------------------------------------------------------------------------------
+bool want_window(const grm_cuda_ctx *ctx, int pairs, int units, int64_t operand_bytes) {
+    if (ctx->tune.syrk_sync == 0) return false;
+    if (ctx->tune.syrk_sync == 1) return true;
+    return units >= 6 * pairs && operand_bytes >= (6ll << 30);
 }
 
-// K-split multi-GPU path (grm_cuda_syrk_i8_packed / _scatter): GRM_CUDA_SYRK_PACKED=wide|2cta forces a kernel
-bool use_wide_packed(int num_kb, int num_tiles, int num_sms) {
-    const char *e = getenv("GRM_CUDA_SYRK_PACKED");
-    if (e) return !strcmp(e, "wide");
-    return SYRK_WIDE_PACKED_DEFAULT && num_kb >= SYRK_WIDE_PACKED_MIN_KB && num_tiles >= 4 * (num_sms / 2);
+uint32_t window_blocks(const grm_cuda_ctx *ctx) {
+    const int v = ctx->tune.syrk_window;
+    return (v > 0 && v < 65536) ? static_cast<uint32_t>(v) : SYNC_WINDOW_DEFAULT;
 }
 
-bool use_quad() {
-    const char *e = getenv("GRM_CUDA_SYRK_I8");
-    return e ? !strcmp(e, "quad") : SYRK_QUAD_DEFAULT;
+int32_t max_coresident_pairs(grm_cuda_ctx *ctx, const void *kernel, size_t smem, int *out) {
+    for (auto &e : ctx->max_clusters)
+        if (e.first == kernel) {
+            *out = e.second;
+            return GRM_CUDA_OK;
+        }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / 2 * 2));
+    cfg.blockDim = dim3(NUM_THREADS2);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int mc = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&mc, kernel, &cfg);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        mc = 0;  // unknown: never enable the window
+    }
+    ctx->max_clusters.emplace_back(kernel, mc);
+    *out = mc;
+    return GRM_CUDA_OK;
 }
 
-bool use_2cta() {
-    const char *e = getenv("GRM_CUDA_SYRK_I8");  // read per call so that both variants can be timed in one process
-    return !(e && (!strcmp(e, "1cta") || !strcmp(e, "1")));  // default: CTA pairs (measured +18 % on C3)
+// go(cfg, progress) launches the kernel with cudaLaunchKernelEx(cfg, kernel, ..., progress, window)
+template <class Go>
+int32_t launch_pairs(grm_cuda_ctx *ctx, const void *kernel, size_t smem, int pairs, int units, int64_t operand_bytes,
+                     Go &&go) {
+    GRM_TRY(grm_func_smem(ctx, kernel, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+    cfg.blockDim = dim3(NUM_THREADS2);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    bool window = want_window(ctx, pairs, units, operand_bytes);
+    if (window) {
+        int cap = 0;
+        GRM_TRY(max_coresident_pairs(ctx, kernel, smem, &cap));
+        if (cap < pairs) window = false;
+    }
+    if (window) {
+        GRM_TRY(ctx->progress.reserve(static_cast<size_t>(pairs) * sizeof(uint32_t) + 64));
+        GRM_CUDA_TRY(cudaMemsetAsync(ctx->progress.ptr, 0, static_cast<size_t>(pairs) * sizeof(uint32_t), ctx->stream));
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (go(&cfg, ctx->progress.as<uint32_t>()) == cudaSuccess) {
+            ctx->launches++;
+            ctx->last_syrk_window = 1;
+            return GRM_CUDA_OK;
+        }
+        cudaGetLastError();  // refused (not co-schedulable / unsupported combination): run without the window
+    }
+    ctx->last_syrk_window = 0;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+    GRM_CUDA_TRY(go(&cfg, nullptr));
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+// wide kernel: used when a unit's main loop is long enough to dwarf its un-overlapped epilogue (>= SYRK_WIDE_MIN_KB K
+// blocks) and there are enough tiles to keep every pair busy with two-tile units.  Measured: C3 (3907 K blocks, 3160
+// tiles) SYRK 56.5 -> 51.7 ms; C2 (781 K blocks, 210 tiles) 0.76 -> 0.97 ms, hence the thresholds.
+bool use_wide(const grm_cuda_ctx *ctx, int num_kb, int num_tiles) {
+    if (ctx->tune.syrk_i8 != 0) return ctx->tune.syrk_i8 == 3;
+    return SYRK_WIDE_DEFAULT && num_kb >= SYRK_WIDE_MIN_KB && num_tiles >= 4 * (ctx->num_sms / 2);
 }
 
 template <int EPI>
@@ -876,108 +840,50 @@ int32_t launch(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, i
     CUtensorMap tmap;
     GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
     const int kbs = static_cast<int>((p + BK - 1) / BK);
-    if (use_wide(kbs * static_cast<int>(nslabs), static_cast<int>(grm_cuda_tile_count(n, rank, world)), ctx->num_sms)) {
-        const int2 *d_tiles, *d_units;
-        int count, nunits;
-        GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
-        if (count == 0) return GRM_CUDA_OK;
-        GRM_TRY(get_wide_units(ctx, n, rank, world, &d_units, &nunits));
-        static bool attrw_set[3] = {false, false, false};
-        if (!attrw_set[EPI]) {
-            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_wide_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(SMEMW_BYTES)));
-            attrw_set[EPI] = true;
-        }
-        const int pairs = std::min(nunits, ctx->num_sms / 2);
-        uint32_t *prog = nullptr;
-        GRM_TRY(sync_buffer(ctx, pairs, nunits, n * ldc * nslabs, &prog));
-        syrk_i8_wide_kernel<EPI><<<2 * pairs, NUM_THREADS2, SMEMW_BYTES, ctx->stream>>>(
-            tmap, d_tiles, d_units, nunits, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
-        GRM_CUDA_TRY(cudaGetLastError());
-        ctx->launches++;
-        return GRM_CUDA_OK;
-    }
-    if (use_quad()) {
-        // clusters of 4: two CTA pairs on two consecutive tiles, shared column panel multicast (see syrk_pair_body)
+    const int num_kb = kbs * static_cast<int>(nslabs);
+    const int64_t operand = n * ldc * nslabs;
+    if (ctx->tune.syrk_i8 == 1) {  // single-CTA variant (kept as the reference point of the pair kernels)
         const int2 *d_tiles;
         int count;
-        GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+        GRM_TRY(get_tile_list(ctx, n, rank, world, &d_tiles, &count));
         if (count == 0) return GRM_CUDA_OK;
-        CUtensorMap tmap64;
-        GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap64, 64u));
-        static bool attrq_set[3] = {false, false, false};
-        static int max_quads[3] = {0, 0, 0};
-        if (!attrq_set[EPI]) {
-            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_quad_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(SMEM2_BYTES)));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / 4 * 4));
-            cfg.blockDim = dim3(NUM_THREADS2);
-            cfg.dynamicSmemBytes = SMEM2_BYTES;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 4;
-            at[0].val.clusterDim.y = 1;
-            at[0].val.clusterDim.z = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            int mc = 0;
-            GRM_CUDA_TRY(cudaOccupancyMaxActiveClusters(&mc, syrk_i8_quad_kernel<EPI>, &cfg));
-            max_quads[EPI] = mc;
-            if (getenv("GRM_CUDA_DEBUG")) fprintf(stderr, "[grm_cuda] quad clusters co-resident: %d (SMs %d)\n", mc, ctx->num_sms);
-            attrq_set[EPI] = true;
-        }
-        if (max_quads[EPI] < 1) {
-            grm_set_error("syrk_i8: no 4-CTA cluster of the quad kernel fits this device");
-            return GRM_CUDA_ERR_CUDA;
-        }
-        const int units = (count + 1) / 2;
-        const int quads = std::min(units, std::min(max_quads[EPI], ctx->num_sms / 4));
-        uint32_t *prog = nullptr;
-        GRM_TRY(sync_buffer(ctx, quads, units, n * ldc * nslabs, &prog));
-        syrk_i8_quad_kernel<EPI><<<4 * quads, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, tmap64, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
-        GRM_CUDA_TRY(cudaGetLastError());
-        ctx->launches++;
-        return GRM_CUDA_OK;
-    }
-    if (use_2cta()) {
-        const int2 *d_tiles;
-        int count;
-        GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
-        if (count == 0) return GRM_CUDA_OK;
-        static bool attr2_set[3] = {false, false, false};
-        if (!attr2_set[EPI]) {
-            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(SMEM2_BYTES)));
-            attr2_set[EPI] = true;
-        }
-        const int pairs = std::min(count, ctx->num_sms / 2);
-        uint32_t *prog = nullptr;
-        GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc * nslabs, &prog));
-        syrk_i8_2cta_kernel<EPI><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tiles, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
+        GRM_TRY(grm_func_smem(ctx, reinterpret_cast<const void *>(syrk_i8_kernel<EPI>), SMEM_BYTES));
+        const int grid = std::min(count, ctx->num_sms);
+        syrk_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmap, d_tiles, count, num_kb, kbs, ep);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         return GRM_CUDA_OK;
     }
     const int2 *d_tiles;
     int count;
-    GRM_TRY(get_tile_list(ctx, n, rank, world, &d_tiles, &count));
+    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
     if (count == 0) return GRM_CUDA_OK;
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[EPI]) {
-        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(SMEM_BYTES)));
-        attr_set[EPI] = true;
+    const uint32_t win = window_blocks(ctx);
+    if (use_wide(ctx, num_kb, count)) {
+        const int2 *d_units;
+        int nunits;
+        GRM_TRY(get_wide_units(ctx, n, rank, world, &d_units, &nunits));
+        const int pairs = std::min(nunits, ctx->num_sms / 2);
+        return launch_pairs(ctx, reinterpret_cast<const void *>(syrk_i8_wide_kernel<EPI>), SMEMW_BYTES, pairs, nunits,
+                            operand, [&](const cudaLaunchConfig_t *cfg, uint32_t *prog) {
+                                return cudaLaunchKernelEx(cfg, syrk_i8_wide_kernel<EPI>, tmap, d_tiles, d_units, nunits,
+                                                          num_kb, kbs, ep, prog, win);
+                            });
     }
-    const int kb_per_slab = static_cast<int>((p + BK - 1) / BK);
-    const int num_kb = kb_per_slab * static_cast<int>(nslabs);
-    const int grid = std::min(count, ctx->num_sms);
-    syrk_i8_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(tmap, d_tiles, count, num_kb, kb_per_slab, ep);
-    GRM_CUDA_TRY(cudaGetLastError());
-    ctx->launches++;
-    return GRM_CUDA_OK;
+    const int pairs = std::min(count, ctx->num_sms / 2);
+    return launch_pairs(ctx, reinterpret_cast<const void *>(syrk_i8_2cta_kernel<EPI>), SMEM2_BYTES, pairs, count, operand,
+                        [&](const cudaLaunchConfig_t *cfg, uint32_t *prog) {
+                            return cudaLaunchKernelEx(cfg, syrk_i8_2cta_kernel<EPI>, tmap, d_tiles, count, num_kb, kbs,
+                                                      ep, prog, win);
+                        });
+}
+
+void set_division(const grm_cuda_ctx *ctx, EpiParams &ep, double denom) {
+    // fast exact division only for ordinary divisors; d = 0 (all loci fixed -> NaN GRM, calc.jl:52-54), Inf, NaN
+    // or extreme magnitudes take the IEEE divide so that the special values come out exactly as in the reference
+    const double a = fabs(denom);
+    ep.denom = denom;
+    ep.rcp = (a > 1e-200 && a < 1e200 && !(ctx && ctx->tune.ieee_div)) ? 1.0 / denom : 0.0;
 }
 
 }  // namespace
@@ -995,13 +901,10 @@ extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, in
     return launch<0>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
 }
 
-bool grm_syrk_i8_pairs() { return use_2cta(); }
-
-// d_prev: packed int32 tiles of earlier loci chunks (grm_syrk_i8_partial), added before the FP64 epilogue; or null
-int32_t grm_syrk_i8_f64_prev(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int64_t nslabs,
-                             double alpha, double beta, double gamma, double denom, const double *d_u, double *d_G,
-                             int64_t ldg, int32_t rank, int32_t world, const int32_t *d_prev) {
-    if (!d_G || ldg < n || (beta != 0.0 && !d_u) || (d_prev && !(use_2cta() && world == 1))) {
+extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                        int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
+                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+    if (!d_G || ldg < n || (beta != 0.0 && !d_u)) {
         grm_set_error("syrk_i8_f64: bad output or missing u (ldg=%lld n=%lld)", (long long)ldg, (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
@@ -1012,284 +915,10 @@ int32_t grm_syrk_i8_f64_prev(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n
     ep.alpha = alpha;
     ep.beta = beta;
     ep.gamma = gamma;
-    ep.denom = denom;
-    {
-        // fast exact division only for ordinary divisors; d = 0 (all loci fixed -> NaN GRM, calc.jl:52-54), Inf, NaN
-        // or extreme magnitudes take the IEEE divide so that the special values come out exactly as in the reference
-        const double a = fabs(denom);
-        const char *no_fast = getenv("GRM_CUDA_IEEE_DIV");
-        ep.rcp = (a > 1e-200 && a < 1e200 && !(no_fast && no_fast[0] == '1')) ? 1.0 / denom : 0.0;
-    }
+    set_division(ctx, ep, denom);
     ep.u = d_u;
-    ep.prev = d_prev;
     if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
     return launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
-}
-
-extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                        int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
-                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) {
-    return grm_syrk_i8_f64_prev(ctx, d_codes, n, p, ldc, nslabs, alpha, beta, gamma, denom, d_u, d_G, ldg, rank, world,
-                                nullptr);
-}
-
-// One loci chunk of the pipelined single-GPU flow (api.cu): raw int32 partial sums of ALL upper-triangular tiles, packed
-// [tile t of the (rank 0, world 1) tile list][col][row]; `accumulate` adds to what d_acc already holds.
-int64_t grm_syrk_i8_partial_bytes(int64_t n) {
-    const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
-    return T * (T + 1) / 2 * 65536 * static_cast<int64_t>(sizeof(int32_t));
-}
-
-int32_t grm_syrk_i8_partial(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t *d_acc,
-                            int accumulate) {
-    if (!ctx || !d_codes || !d_acc || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0) {
-        grm_set_error("syrk_i8_partial: bad argument");
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
-    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
-    CUtensorMap tmap;
-    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, 1, &tmap));
-    const int2 *d_tiles;
-    int count;
-    GRM_TRY(get_tile_list_2cta(ctx, n, 0, 1, &d_tiles, &count));
-    EpiParams ep{};
-    ep.n = n;
-    ep.C = d_acc;
-    ep.prev = accumulate ? d_acc : nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(SMEM2_BYTES)));
-        attr_set = true;
-    }
-    const int kbs = static_cast<int>((p + BK - 1) / BK);
-    const int pairs = std::min(count, ctx->num_sms / 2);
-    uint32_t *prog = nullptr;
-    GRM_TRY(sync_buffer(ctx, pairs, count, n * p, &prog));
-    syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(tmap, d_tiles, count, kbs, kbs, ep, prog,
-                                                                                  sync_window());
-    GRM_CUDA_TRY(cudaGetLastError());
-    ctx->launches++;
-    return GRM_CUDA_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// loci-split (K-split) multi-GPU support: every GPU contracts ITS loci over ALL upper-triangular tiles and writes raw
-// int32 tiles into a buffer laid out for a reduce-scatter ([destination rank][slot][256 x 256]); after the exchange
-// each GPU finalises the tiles it owns.  Exchange volume 4 n^2 / 2 bytes per GPU instead of n p for the all-gather of
-// the codes — the better choice whenever p > 4 n (BASELINE C2, C3).
-// ---------------------------------------------------------------------------------------------------------------
-namespace {
-
-struct PackedPlan {
-    std::vector<int2> tiles;     // all upper-triangular tiles, global order
-    std::vector<int32_t> slots;  // slot in [world][tiles_max] of each tile
-    int64_t tiles_max = 0;
-};
-
-void make_packed_plan(int64_t n, int32_t world, PackedPlan &pl) {
-    std::vector<int2> order;
-    grm_tile_order(n, order);
-    const int64_t total = static_cast<int64_t>(order.size());
-    pl.tiles_max = (total + world - 1) / world;
-    pl.tiles.clear();
-    pl.slots.clear();
-    for (int32_t r = 0; r < world; ++r) {
-        int64_t b, e;
-        grm_tile_range(total, r, world, &b, &e);
-        for (int64_t t = b; t < e; ++t) {
-            pl.tiles.push_back(make_int2(order[t].x * GRM_TILE, order[t].y * GRM_TILE));
-            pl.slots.push_back(static_cast<int32_t>(r * pl.tiles_max + (t - b)));
-        }
-    }
-}
-
-// G tile <- formula(reduced int32 tile): block = one owned tile, same arithmetic as the fused SYRK epilogue
-template <int EPI>
-__global__ void __launch_bounds__(256)
-finalize_tiles_kernel(const int32_t *__restrict__ packed, const int2 *__restrict__ tiles, EpiParams ep, int nparts,
-                      int64_t part_stride) {
-    const int2 tc = tiles[blockIdx.x];
-    const int32_t *tile = packed + static_cast<int64_t>(blockIdx.x) * 65536;
-    for (int idx = threadIdx.x; idx < 65536; idx += 256) {
-        const int cl = idx >> 8, rl = idx & 255;
-        const int64_t row = tc.x + rl, col = tc.y + cl;
-        if (row < ep.n && col < ep.n) {
-            int32_t c = tile[idx];
-            for (int q = 1; q < nparts; ++q) c += tile[q * part_stride + idx];  // peer-store form: one part per GPU
-            double v = static_cast<double>(c) * ep.alpha;
-            if (EPI == 2) v = (v - ep.beta * (__ldg(ep.u + row) + __ldg(ep.u + col))) + ep.gamma;
-            ep.G[row + col * ep.ldg] = (ep.rcp != 0.0) ? div_const(v, ep.denom, ep.rcp) : v / ep.denom;
-        }
-    }
-}
-
-}  // namespace
-
-extern "C" int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world) {
-    if (n < 1 || world < 1) return -1;
-    const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
-    return (T * (T + 1) / 2 + world - 1) / world;
-}
-
-static int32_t syrk_i8_packed_impl(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                   int32_t world, int32_t *d_packed, int32_t src_rank, void *const *peer_recv) {
-    if (!ctx || !d_codes || (!d_packed && !peer_recv) || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1 ||
-        (peer_recv && (world > GRM_MAX_PEERS || src_rank < 0 || src_rank >= world))) {
-        grm_set_error("syrk_i8_packed: bad argument");
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
-    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
-    CUtensorMap tmap;
-    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, 1, &tmap));
-    TileListCache &tc = ctx->tiles_packed;
-    if (tc.n != n || tc.world != world) {
-        PackedPlan pl;
-        make_packed_plan(n, world, pl);
-        const size_t nt = pl.tiles.size();
-        // units of the wide kernel over the same list: consecutive tiles that share their column panel
-        std::vector<int2> units;
-        for (size_t t = 0; t < nt;) {
-            if (t + 1 < nt && pl.tiles[t].y == pl.tiles[t + 1].y) {
-                units.push_back(make_int2(static_cast<int>(t), static_cast<int>(t + 1)));
-                t += 2;
-            } else {
-                units.push_back(make_int2(static_cast<int>(t), -1));
-                t += 1;
-            }
-        }
-        // layout: [tiles: nt int2][slots: nt int32, padded to a multiple of 2][units: nu int2]
-        const size_t slots_padded = (nt + 1) / 2 * 2;
-        GRM_TRY(tc.buf.reserve(nt * sizeof(int2) + slots_padded * sizeof(int32_t) + units.size() * sizeof(int2)));
-        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.ptr, pl.tiles.data(), nt * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        GRM_CUDA_TRY(cudaMemcpyAsync(tc.buf.as<int2>() + nt, pl.slots.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                     ctx->stream));
-        GRM_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int32_t *>(tc.buf.as<int2>() + nt) + slots_padded, units.data(),
-                                     units.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        tc.n = n;
-        tc.world = world;
-        tc.rank = 0;
-        tc.count = static_cast<int32_t>(nt);
-        tc.kind = static_cast<int32_t>(units.size());
-    }
-    const int count = tc.count;
-    EpiParams ep{};
-    ep.n = n;
-    ep.C = d_packed;
-    ep.slots = reinterpret_cast<const int32_t *>(tc.buf.as<int2>() + count);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(SMEM2_BYTES)));
-        attr_set = true;
-    }
-    const int64_t tiles_max = grm_cuda_packed_tiles_max(n, world);
-    if (peer_recv) {
-        for (int r = 0; r < world; ++r) {
-            if (!peer_recv[r]) {
-                grm_set_error("syrk_i8_scatter: receive buffer of rank %d is null", r);
-                return GRM_CUDA_ERR_BAD_ARGUMENT;
-            }
-            ep.peers[r] = static_cast<int32_t *>(peer_recv[r]);
-        }
-        ep.tiles_max = static_cast<int32_t>(tiles_max);
-        ep.src_rank = src_rank;
-    } else if (static_cast<int64_t>(count) != tiles_max * world) {
-        // unused slots of the reduce-scatter layout must be defined (they are summed too)
-        GRM_CUDA_TRY(cudaMemsetAsync(d_packed, 0, static_cast<size_t>(tiles_max) * world * 65536 * sizeof(int32_t),
-                                     ctx->stream));
-    }
-    const int kbs = static_cast<int>((p + BK - 1) / BK);
-    if (use_wide_packed(kbs, count, ctx->num_sms)) {
-        // every GPU contracts ALL tiles over its loci, so there are always enough two-tile units; the K threshold is
-        // lower than in launch() (use_wide_packed)
-        static bool attrw_set = false;
-        if (!attrw_set) {
-            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(SMEMW_BYTES)));
-            attrw_set = true;
-        }
-        const int nunits = tc.kind;
-        const int2 *d_units = reinterpret_cast<const int2 *>(reinterpret_cast<const int32_t *>(tc.buf.as<int2>() + count) +
-                                                             (count + 1) / 2 * 2);
-        const int wpairs = std::min(nunits, ctx->num_sms / 2);
-        uint32_t *wprog = nullptr;
-        GRM_TRY(sync_buffer(ctx, wpairs, nunits, n * ldc, &wprog));
-        syrk_i8_wide_kernel<3><<<2 * wpairs, NUM_THREADS2, SMEMW_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), d_units, nunits,
-                                                                                       kbs, kbs, ep, wprog, sync_window());
-        GRM_CUDA_TRY(cudaGetLastError());
-        ctx->launches++;
-        return GRM_CUDA_OK;
-    }
-    const int pairs = std::min(count, ctx->num_sms / 2);
-    uint32_t *prog = nullptr;
-    GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc, &prog));
-    syrk_i8_2cta_kernel<3><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(tmap, tc.buf.as<int2>(), count, kbs, kbs,
-                                                                                  ep, prog, sync_window());
-    GRM_CUDA_TRY(cudaGetLastError());
-    ctx->launches++;
-    return GRM_CUDA_OK;
-}
-
-extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                           int32_t world, int32_t *d_packed) {
-    return syrk_i8_packed_impl(ctx, d_codes, n, p, ldc, world, d_packed, 0, nullptr);
-}
-
-extern "C" int32_t grm_cuda_syrk_i8_scatter(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                            int32_t rank, int32_t world, void *const *peer_recv) {
-    if (!peer_recv) {
-        grm_set_error("syrk_i8_scatter: peer_recv is null");
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
-    return syrk_i8_packed_impl(ctx, d_codes, n, p, ldc, world, nullptr, rank, peer_recv);
-}
-
-static int32_t finalize_tiles_impl(grm_cuda_ctx *ctx, const int32_t *d_reduced, int nparts, int64_t n, double alpha,
-                                   double beta, double gamma, double denom, const double *d_u, double *d_G,
-                                   int64_t ldg, int32_t rank, int32_t world) {
-    if (!ctx || !d_reduced || !d_G || n < 1 || ldg < n || world < 1 || rank < 0 || rank >= world || nparts < 1 ||
-        (beta != 0.0 && !d_u)) {
-        grm_set_error("finalize_tiles: bad argument");
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
-    const int64_t part_stride = grm_cuda_packed_tiles_max(n, world) * 65536;
-    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
-    const int2 *d_tiles;
-    int count;
-    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
-    if (count == 0) return GRM_CUDA_OK;
-    EpiParams ep{};
-    ep.n = n;
-    ep.G = d_G;
-    ep.ldg = ldg;
-    ep.alpha = alpha;
-    ep.beta = beta;
-    ep.gamma = gamma;
-    ep.denom = denom;
-    const double a = fabs(denom);
-    ep.rcp = (a > 1e-200 && a < 1e200) ? 1.0 / denom : 0.0;
-    ep.u = d_u;
-    if (beta == 0.0 && gamma == 0.0)
-        finalize_tiles_kernel<1><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep, nparts, part_stride);
-    else
-        finalize_tiles_kernel<2><<<count, 256, 0, ctx->stream>>>(d_reduced, d_tiles, ep, nparts, part_stride);
-    GRM_CUDA_TRY(cudaGetLastError());
-    ctx->launches++;
-    return GRM_CUDA_OK;
-}
-
-extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha,
-                                           double beta, double gamma, double denom, const double *d_u, double *d_G,
-                                           int64_t ldg, int32_t rank, int32_t world) {
-    return finalize_tiles_impl(ctx, d_reduced, 1, n, alpha, beta, gamma, denom, d_u, d_G, ldg, rank, world);
-}
-
-extern "C" int32_t grm_cuda_finalize_tiles_parts(grm_cuda_ctx *ctx, const int32_t *d_recv, int64_t n, double alpha,
-                                                 double beta, double gamma, double denom, const double *d_u,
-                                                 double *d_G, int64_t ldg, int32_t rank, int32_t world) {
-    return finalize_tiles_impl(ctx, d_recv, world, n, alpha, beta, gamma, denom, d_u, d_G, ldg, rank, world);
 }
 
 // Sharded-output form of grm_cuda_syrk_i8_f64: the tiles owned by (rank, world) are written as packed 256 x 256 FP64
@@ -1298,17 +927,12 @@ extern "C" int32_t grm_cuda_finalize_tiles_parts(grm_cuda_ctx *ctx, const int32_
 extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                               int64_t nslabs, double alpha, double beta, double gamma, double denom,
                                               const double *d_u, double *d_tiles, int32_t rank, int32_t world) {
-    if (!ctx || !d_codes || !d_tiles || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || nslabs < 1 || world < 1 ||
-        rank < 0 || rank >= world || (beta != 0.0 && !d_u)) {
+    if (!ctx || !d_tiles || (beta != 0.0 && !d_u) || n < 1 || world < 1 || rank < 0 || rank >= world) {
         grm_set_error("syrk_i8_f64_tiles: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
-    CUtensorMap tmap;
-    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, nslabs, &tmap));
-    const int2 *d_tl;
-    int count;
-    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tl, &count));
+    const int64_t count = grm_cuda_tile_count(n, rank, world);
     if (count == 0) return GRM_CUDA_OK;
     // tiles at the ragged edge are only partly written by the epilogue: define the rest as zeros
     GRM_CUDA_TRY(cudaMemsetAsync(d_tiles, 0, static_cast<size_t>(count) * 65536 * sizeof(double), ctx->stream));
@@ -1318,32 +942,225 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
     ep.alpha = alpha;
     ep.beta = beta;
     ep.gamma = gamma;
-    ep.denom = denom;
-    const double a = fabs(denom);
-    ep.rcp = (a > 1e-200 && a < 1e200) ? 1.0 / denom : 0.0;
+    set_division(ctx, ep, denom);
     ep.u = d_u;
-    const int kbs = static_cast<int>((p + BK - 1) / BK);
-    const int pairs = std::min(count, ctx->num_sms / 2);
-    const bool simple = beta == 0.0 && gamma == 0.0;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[simple ? 0 : 1]) {
-        if (simple)
-            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(SMEM2_BYTES)));
-        else
-            GRM_CUDA_TRY(cudaFuncSetAttribute(syrk_i8_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(SMEM2_BYTES)));
-        attr_set[simple ? 0 : 1] = true;
+    // the packed-tile addressing lives in the pair kernels' epilogue (drain_tile): never the single-CTA variant
+    const int saved = ctx->tune.syrk_i8;
+    if (saved == 1) ctx->tune.syrk_i8 = 2;
+    const int32_t st = (beta == 0.0 && gamma == 0.0) ? launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world)
+                                                     : launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
+    ctx->tune.syrk_i8 = saved;
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// loci-split (K-split) multi-GPU support: every GPU contracts ITS loci over ALL upper-triangular tiles and writes raw
+// int32 tiles into a buffer laid out for a reduce-scatter; after the exchange each GPU finalises the tiles it owns.
+// Exchange volume 4 n^2 / 2 bytes per GPU instead of n p for the all-gather of the codes — the better choice whenever
+// p > 4 n (BASELINE C2, C3).
+//
+// Waves: the slots 0 .. tiles_max-1 every rank owns are cut into `waves` ranges [s_w, s_{w+1}); wave w of the packed
+// buffer is the contiguous block [world][s_{w+1} - s_w][256 x 256] starting at element world * s_w * 65536, so the
+// reduce-scatter of wave w is one plain call that can run on a second stream while the tensor cores contract wave
+// w + 1 (run.cu).  waves = 1 is the layout [world][tiles_max][256 x 256] of the single-exchange form.
+// ---------------------------------------------------------------------------------------------------------------
+void grm_packed_wave_range(int64_t n, int32_t world, int32_t waves, int32_t w, int64_t *s0, int64_t *s1) {
+    const int64_t tmax = grm_cuda_packed_tiles_max(n, world);
+    *s0 = tmax * w / waves;
+    *s1 = tmax * (w + 1) / waves;
+}
+
+namespace {
+
+int32_t get_packed_plan_impl(grm_cuda_ctx *ctx, int64_t n, int32_t world, int32_t waves, PackedPlanCache **out) {
+    PackedPlanCache &pc = ctx->packed_plan[waves == 1 ? 1 : 0];
+    if (pc.n != n || pc.world != world || pc.waves != waves || pc.band != ctx->tune.tile_band) {
+        std::vector<int2> order;
+        grm_tile_order(n, ctx->tune.tile_band, order);
+        const int64_t total = static_cast<int64_t>(order.size());
+        std::vector<int2> tiles, units;
+        std::vector<int32_t> slots;
+        pc.tile_off.assign(waves, 0);
+        pc.tile_cnt.assign(waves, 0);
+        pc.unit_off.assign(waves, 0);
+        pc.unit_cnt.assign(waves, 0);
+        for (int32_t w = 0; w < waves; ++w) {
+            int64_t s0, s1;
+            grm_packed_wave_range(n, world, waves, w, &s0, &s1);
+            const int64_t len = s1 - s0;
+            pc.tile_off[w] = static_cast<int32_t>(tiles.size());
+            for (int32_t r = 0; r < world; ++r) {
+                int64_t b, e;
+                grm_tile_range(total, r, world, &b, &e);
+                for (int64_t j = s0; j < s1 && b + j < e; ++j) {
+                    tiles.push_back(make_int2(order[b + j].x * GRM_TILE, order[b + j].y * GRM_TILE));
+                    slots.push_back(static_cast<int32_t>(world * s0 + r * len + (j - s0)));
+                }
+            }
+            pc.tile_cnt[w] = static_cast<int32_t>(tiles.size()) - pc.tile_off[w];
+            // units of the wide kernel: index the wave's own tile sub-list
+            std::vector<int2> sub(tiles.begin() + pc.tile_off[w], tiles.end()), u;
+            make_wide_units(sub, 0, sub.size(), u);
+            pc.unit_off[w] = static_cast<int32_t>(units.size());
+            pc.unit_cnt[w] = static_cast<int32_t>(u.size());
+            units.insert(units.end(), u.begin(), u.end());
+        }
+        const size_t nt = tiles.size(), slots_padded = (nt + 1) / 2 * 2;
+        pc.total_tiles = static_cast<int32_t>(nt);
+        pc.slots_padded = static_cast<int32_t>(slots_padded);
+        // layout: [tiles: nt int2][slots: nt int32, padded to a multiple of 2][units: nu int2]
+        GRM_TRY(pc.buf.reserve(std::max<size_t>(16, nt * sizeof(int2) + slots_padded * sizeof(int32_t) + units.size() * sizeof(int2))));
+        if (nt) {
+            GRM_CUDA_TRY(cudaMemcpyAsync(pc.buf.ptr, tiles.data(), nt * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+            GRM_CUDA_TRY(cudaMemcpyAsync(pc.buf.as<int2>() + nt, slots.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                         ctx->stream));
+            GRM_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<int32_t *>(pc.buf.as<int2>() + nt) + slots_padded, units.data(),
+                                         units.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+            GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        pc.n = n;
+        pc.world = world;
+        pc.waves = waves;
+        pc.band = ctx->tune.tile_band;
     }
-    uint32_t *prog = nullptr;
-    GRM_TRY(sync_buffer(ctx, pairs, count, n * ldc * nslabs, &prog));
-    if (simple)
-        syrk_i8_2cta_kernel<1><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
+    *out = &pc;
+    return GRM_CUDA_OK;
+}
+
+// G tile <- formula(reduced int32 tile): block = one owned tile, same arithmetic as the fused SYRK epilogue.
+// Gt != nullptr: the tile is written packed ([col][row], zeros outside n) at Gt + (t0 + blockIdx.x) * 65536 instead
+// of into the dense matrix (the form the all-gather of the finished tiles moves).
+template <int EPI>
+__global__ void __launch_bounds__(256)
+finalize_tiles_kernel(const int32_t *__restrict__ packed, const int2 *__restrict__ tiles, EpiParams ep, int t0) {
+    const int t = t0 + blockIdx.x;
+    const int2 tc = tiles[t];
+    const int32_t *tile = packed + static_cast<int64_t>(t) * 65536;
+    double *gt = ep.Gt ? ep.Gt + static_cast<int64_t>(t) * 65536 : nullptr;
+    for (int idx = threadIdx.x; idx < 65536; idx += 256) {
+        const int cl = idx >> 8, rl = idx & 255;
+        const int64_t row = tc.x + rl, col = tc.y + cl;
+        double out = 0.0;
+        const bool inside = row < ep.n && col < ep.n;
+        if (inside) {
+            const int32_t c = tile[idx];
+            double v = static_cast<double>(c) * ep.alpha;
+            if (EPI == 2) v = (v - ep.beta * (__ldg(ep.u + row) + __ldg(ep.u + col))) + ep.gamma;
+            out = (ep.rcp != 0.0) ? div_const(v, ep.denom, ep.rcp) : v / ep.denom;
+        }
+        if (gt) gt[idx] = out;
+        else if (inside) ep.G[row + col * ep.ldg] = out;
+    }
+}
+
+}  // namespace
+
+int32_t grm_packed_plan(grm_cuda_ctx *ctx, int64_t n, int32_t world, int32_t waves, PackedPlanCache **out) {
+    return get_packed_plan_impl(ctx, n, world, waves, out);
+}
+
+extern "C" int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world) {
+    if (n < 1 || world < 1) return -1;
+    const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
+    return (T * (T + 1) / 2 + world - 1) / world;
+}
+
+// one wave of the K-split contraction (waves = 1, wave = 0: everything)
+int32_t grm_syrk_i8_packed_wave(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t world,
+                                int32_t waves, int32_t wave, int32_t *d_packed) {
+    if (!ctx || !d_codes || !d_packed || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1 || waves < 1 ||
+        wave < 0 || wave >= waves) {
+        grm_set_error("syrk_i8_packed: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    CUtensorMap tmap;
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, 1, &tmap));
+    PackedPlanCache *pc;
+    GRM_TRY(grm_packed_plan(ctx, n, world, waves, &pc));
+    const int64_t tiles_max = grm_cuda_packed_tiles_max(n, world);
+    if (wave == 0 && static_cast<int64_t>(pc->total_tiles) != tiles_max * world) {
+        // unused slots of the reduce-scatter layout must be defined (they are summed too)
+        GRM_CUDA_TRY(cudaMemsetAsync(d_packed, 0, static_cast<size_t>(tiles_max) * world * 65536 * sizeof(int32_t),
+                                     ctx->stream));
+    }
+    const int count = pc->tile_cnt[wave];
+    if (count == 0) return GRM_CUDA_OK;
+    const int2 *d_tiles = pc->buf.as<int2>() + pc->tile_off[wave];
+    EpiParams ep{};
+    ep.n = n;
+    ep.C = d_packed;
+    ep.slots = reinterpret_cast<const int32_t *>(pc->buf.as<int2>() + pc->total_tiles) + pc->tile_off[wave];
+    const int kbs = static_cast<int>((p + BK - 1) / BK);
+    const uint32_t win = window_blocks(ctx);
+    if (ctx->tune.syrk_packed == 3) {
+        // wide form on the packed path: measured no gain at 2 GPUs (profiles/README.md), kept selectable for the tests
+        const int nunits = pc->unit_cnt[wave];
+        const int2 *d_units = reinterpret_cast<const int2 *>(reinterpret_cast<const int32_t *>(pc->buf.as<int2>() + pc->total_tiles) +
+                                                             pc->slots_padded) + pc->unit_off[wave];
+        const int wpairs = std::min(nunits, ctx->num_sms / 2);
+        return launch_pairs(ctx, reinterpret_cast<const void *>(syrk_i8_wide_kernel<3>), SMEMW_BYTES, wpairs, nunits, n * ldc,
+                            [&](const cudaLaunchConfig_t *cfg, uint32_t *prog) {
+                                return cudaLaunchKernelEx(cfg, syrk_i8_wide_kernel<3>, tmap, d_tiles, d_units, nunits, kbs,
+                                                          kbs, ep, prog, win);
+                            });
+    }
+    const int pairs = std::min(count, ctx->num_sms / 2);
+    return launch_pairs(ctx, reinterpret_cast<const void *>(syrk_i8_2cta_kernel<3>), SMEM2_BYTES, pairs, count, n * ldc,
+                        [&](const cudaLaunchConfig_t *cfg, uint32_t *prog) {
+                            return cudaLaunchKernelEx(cfg, syrk_i8_2cta_kernel<3>, tmap, d_tiles, count, kbs, kbs, ep, prog,
+                                                      win);
+                        });
+}
+
+extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                                           int32_t world, int32_t *d_packed) {
+    return grm_syrk_i8_packed_wave(ctx, d_codes, n, p, ldc, world, 1, 0, d_packed);
+}
+
+// finalise owned tiles [t0, t0 + cnt) of the reduced buffer ([tiles_max][256 x 256] int32, slot = position in the
+// rank's tile list) into the dense matrix d_G, or (d_Gt) into packed FP64 tiles at the same slots
+int32_t grm_finalize_tiles_range(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha, double beta,
+                                 double gamma, double denom, const double *d_u, double *d_G, int64_t ldg, double *d_Gt,
+                                 int32_t rank, int32_t world, int64_t t0, int64_t cnt, cudaStream_t stream) {
+    if (!ctx || !d_reduced || (!d_G && !d_Gt) || n < 1 || (d_G && ldg < n) || world < 1 || rank < 0 || rank >= world ||
+        (beta != 0.0 && !d_u)) {
+        grm_set_error("finalize_tiles: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int2 *d_tiles;
+    int count;
+    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+    if (t0 < 0) t0 = 0;
+    cnt = std::min<int64_t>(cnt, count - t0);
+    if (cnt <= 0) return GRM_CUDA_OK;
+    EpiParams ep{};
+    ep.n = n;
+    ep.G = d_G;
+    ep.ldg = ldg;
+    ep.Gt = d_Gt;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.gamma = gamma;
+    set_division(ctx, ep, denom);
+    ep.u = d_u;
+    if (beta == 0.0 && gamma == 0.0)
+        finalize_tiles_kernel<1><<<static_cast<unsigned>(cnt), 256, 0, stream>>>(d_reduced, d_tiles, ep, static_cast<int>(t0));
     else
-        syrk_i8_2cta_kernel<2><<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, ctx->stream>>>(
-            tmap, d_tl, count, kbs * static_cast<int>(nslabs), kbs, ep, prog, sync_window());
+        finalize_tiles_kernel<2><<<static_cast<unsigned>(cnt), 256, 0, stream>>>(d_reduced, d_tiles, ep, static_cast<int>(t0));
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha,
+                                           double beta, double gamma, double denom, const double *d_u, double *d_G,
+                                           int64_t ldg, int32_t rank, int32_t world) {
+    if (!ctx) {
+        grm_set_error("finalize_tiles: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    return grm_finalize_tiles_range(ctx, d_reduced, n, alpha, beta, gamma, denom, d_u, d_G, ldg, nullptr, rank, world, 0,
+                                    INT32_MAX, ctx->stream);
 }

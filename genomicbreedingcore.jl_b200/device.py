@@ -30,10 +30,13 @@ def on_ctx_stream(ctx: _lib.Context):
     outer = torch.cuda.current_stream(dev)
     if outer.cuda_stream != ext.cuda_stream:
         ext.wait_stream(outer)
-    with torch.cuda.stream(ext):
-        yield ext
-    if outer.cuda_stream != ext.cuda_stream:
-        outer.wait_stream(ext)
+    try:
+        with torch.cuda.stream(ext):
+            yield ext
+    finally:
+        # also on an exception: library work may still be queued, the caller's stream must stay ordered after it
+        if outer.cuda_stream != ext.cuda_stream:
+            outer.wait_stream(ext)
 
 
 def _ptr(t):
@@ -71,9 +74,10 @@ def locus_qc(ctx, A_pn, maf: float, max_locus_sparsity: float, error_on_missing:
     return q, keep, kept, stats, flags
 
 
-def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int = 0, keep=None):
+def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int = 0, miss=None):
     """Quantise + transpose A (loci k0..k0+pc of the full problem) into codes[:, k0:k0+pc]; returns
-    (codes[n, ldc] int8, colsum[ldc] int32, flags[16] uint32-as-int32)."""
+    (codes[n, ldc] int8, colsum[ldc] int32, flags[16] uint32-as-int32).  `miss` (int32 [ldc], zeroed) switches to QC
+    mode: NaN cells are packed as 0 and counted per locus instead of raising flag 1."""
     torch = _torch()
     pc, n = A_pn.shape
     dev = A_pn.device
@@ -88,9 +92,57 @@ def pack_dosage(ctx, A_pn, m: int, codes=None, colsum=None, flags=None, k0: int 
     _lib.check(ctx.lib.grm_cuda_pack_dosage(ctx.handle, _ptr(A_pn), n, pc, n, m,
                                             C.c_void_p(codes.data_ptr() + k0), ldc,
                                             C.c_void_p(colsum.data_ptr() + 4 * k0), _ptr(flags),
-                                            _ptr(keep) if keep is not None else None))
+                                            C.c_void_p(miss.data_ptr() + 4 * k0) if miss is not None else None))
     ctx.order_torch_after()
     return codes, colsum, flags
+
+
+def pack_codes(ctx, src_pn, codes=None, colsum=None, flags=None, k0: int = 0, miss=None):
+    """Host-quantised codes (int8 [pc, lds], locus-major like the caller's matrix; lds % 4 == 0, entries beyond n
+    ignored via `n = codes.shape[0]` when `codes` is given, else n = lds) -> K-major codes + column sums + flags."""
+    torch = _torch()
+    pc, lds = src_pn.shape
+    dev = src_pn.device
+    n = lds if codes is None else codes.shape[0]
+    if codes is None:
+        codes = torch.zeros((n, padded_loci(k0 + pc)), dtype=torch.int8, device=dev)
+    ldc = codes.shape[1]
+    if colsum is None:
+        colsum = torch.zeros((ldc,), dtype=torch.int32, device=dev)
+    if flags is None:
+        flags = torch.zeros((16,), dtype=torch.int32, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_pack_codes(ctx.handle, _ptr(src_pn), n, pc, lds, C.c_void_p(codes.data_ptr() + k0), ldc,
+                                           C.c_void_p(colsum.data_ptr() + 4 * k0), _ptr(flags),
+                                           C.c_void_p(miss.data_ptr() + 4 * k0) if miss is not None else None))
+    ctx.order_torch_after()
+    return codes, colsum, flags
+
+
+def locus_keep(ctx, colsum, miss, n: int, p: int, m: int, maf: float, max_locus_sparsity: float,
+               error_on_missing: bool = True, flags=None):
+    """QC mask from the integers of a QC-mode pack -> (keep uint8 [p], kept count tensor, flags); colsum of dropped
+    loci is zeroed in place."""
+    torch = _torch()
+    dev = colsum.device
+    keep = torch.zeros((p,), dtype=torch.uint8, device=dev)
+    kept = torch.zeros((1,), dtype=torch.int64, device=dev)
+    if flags is None:
+        flags = torch.zeros((16,), dtype=torch.int32, device=dev)
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_locus_keep(ctx.handle, _ptr(colsum), _ptr(miss), n, p, m, float(maf),
+                                           float(max_locus_sparsity), 1 if error_on_missing else 0, _ptr(keep), _ptr(kept),
+                                           _ptr(flags)))
+    ctx.order_torch_after()
+    return keep, kept, flags
+
+
+def mask_codes(ctx, codes, p: int, keep):
+    n, ldc = codes.shape
+    ctx.synchronize_with_torch()
+    _lib.check(ctx.lib.grm_cuda_mask_codes(ctx.handle, _ptr(codes), n, p, ldc, _ptr(keep)))
+    ctx.order_torch_after()
+    return codes
 
 
 def _slabs(codes):
@@ -160,63 +212,6 @@ def finalize_tiles(ctx, reduced, n: int, alpha: float, beta: float, gamma: float
                                                _ptr(u) if u is not None else None, _ptr(G), n, rank, world))
     ctx.order_torch_after()
     return G
-
-
-def syrk_i8_scatter(ctx, codes, p: int, rank: int, world: int, peer_ptrs):
-    """K-split contraction with the exchange fused into the epilogue: every finished int32 tile is stored straight into
-    its owner's receive buffer (peer memory), part `rank`.  peer_ptrs: `world` raw device pointers (ints)."""
-    n, ldc = codes.shape
-    arr = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in peer_ptrs])
-    ctx.synchronize_with_torch()
-    _lib.check(ctx.lib.grm_cuda_syrk_i8_scatter(ctx.handle, _ptr(codes), n, p, ldc, rank, world, arr))
-    ctx.order_torch_after()
-
-
-def finalize_tiles_parts(ctx, recv_ptr: int, n: int, alpha: float, beta: float, gamma: float, denom: float, u, G,
-                         rank: int, world: int):
-    """Sum the `world` parts of each owned tile in the receive buffer and apply the epilogue formula."""
-    ctx.synchronize_with_torch()
-    _lib.check(ctx.lib.grm_cuda_finalize_tiles_parts(ctx.handle, C.c_void_p(int(recv_ptr)), n, alpha, beta, gamma, denom,
-                                                     _ptr(u) if u is not None else None, _ptr(G), n, rank, world))
-    ctx.order_torch_after()
-    return G
-
-
-class PeerBuffer:
-    """A cudaMalloc'ed buffer of this rank plus the mappings of the same buffer of every peer (CUDA IPC)."""
-
-    def __init__(self, ctx, nbytes: int):
-        self.ctx = ctx
-        self.nbytes = int(nbytes)
-        ptr = C.c_void_p()
-        handle = (C.c_uint8 * 64)()
-        _lib.check(ctx.lib.grm_cuda_ipc_alloc(ctx.handle, self.nbytes, C.byref(ptr), handle))
-        self.ptr = int(ptr.value)
-        self.handle = bytes(handle)
-        self.peers = None     # raw pointers, index = rank
-        self._opened = []
-
-    def open_peers(self, handles, rank: int):
-        """handles: list of 64-byte handles, index = rank (own entry ignored)."""
-        self.peers = []
-        for r, h in enumerate(handles):
-            if r == rank:
-                self.peers.append(self.ptr)
-                continue
-            buf = (C.c_uint8 * 64).from_buffer_copy(bytes(h))
-            p = C.c_void_p()
-            _lib.check(self.ctx.lib.grm_cuda_ipc_open(self.ctx.handle, buf, C.byref(p)))
-            self.peers.append(int(p.value))
-            self._opened.append(int(p.value))
-        return self.peers
-
-    def close(self):
-        for p in self._opened:
-            self.ctx.lib.grm_cuda_ipc_close(self.ctx.handle, C.c_void_p(p))
-        self._opened = []
-        if self.ptr:
-            self.ctx.lib.grm_cuda_ipc_free(self.ctx.handle, C.c_void_p(self.ptr))
-            self.ptr = 0
 
 
 def locus_stats_i8(ctx, colsum, p: int, n: int, m: int, ploidy: int):
@@ -326,26 +321,43 @@ def scale_mirror(ctx, G, denom: float = 1.0):
 
 
 def grm_device(ctx, A_pn, ploidy=None, *, path=_lib.PATH_AUTO, denominator=0, skip_repair=False, max_iter=1000,
-               rank=0, world=1, out=None):
+               rank=0, world=1, out=None, distributed=False, p_total=None, tiles=False, missing="error", maf=0.0,
+               max_locus_sparsity=1.0):
     """One-call device-resident GRM (inputs and output already in HBM): grmsimple if `ploidy` is None, else
-    grmploidyaware.  Returns (G, info dict)."""
+    grmploidyaware.  Returns (G, info dict).  distributed=True: the context carries a communicator, A_pn is THIS
+    rank's loci slab ((pc, n), may be empty) of p_total loci and every rank makes the same call; tiles=True returns
+    the rank's packed [tiles_owned, 256, 256] tiles instead of the dense matrix."""
     torch = _torch()
     p, n = A_pn.shape
-    if out is None:
-        out = torch.empty((n, n), dtype=torch.float64, device=A_pn.device)
-        if world > 1:
-            out.zero_()
     o = _lib.default_options()
     o.path, o.denominator, o.max_iter = path, denominator, max_iter
     o.skip_repair = 1 if skip_repair else 0
     o.input_location = o.output_location = _lib.LOC_DEVICE
     o.rank, o.world = rank, world
+    o.missing_policy = {"error": _lib.MISSING_ERROR, "meanfill": _lib.MISSING_MEANFILL}[missing]
+    o.maf, o.max_locus_sparsity = float(maf), float(max_locus_sparsity)
+    trank, tworld = rank, world
+    if distributed:
+        o.distributed, o.input_slab = 1, 1
+        p = int(p_total)
+        trank, tworld, _ = ctx.comm_info()
+    if tiles:
+        o.output_mode = _lib.OUT_TILES
+    if out is None:
+        if tiles:
+            out = torch.empty((max(ctx.lib.grm_cuda_tile_count(n, trank, tworld), 1), 256, 256), dtype=torch.float64,
+                              device=A_pn.device)
+        else:
+            out = torch.empty((n, n), dtype=torch.float64, device=A_pn.device)
+            if world > 1:
+                out.zero_()
     info = _lib.new_info()
     ctx.synchronize_with_torch()
+    a_ptr = _ptr(A_pn) if A_pn.numel() > 0 else C.c_void_p(out.data_ptr())  # an empty slab is never dereferenced
     if ploidy is None:
-        st = ctx.lib.grm_cuda_simple(ctx.handle, _ptr(A_pn), n, p, n, _ptr(out), n, C.byref(o), C.byref(info))
+        st = ctx.lib.grm_cuda_simple(ctx.handle, a_ptr, n, p, n, _ptr(out), n, C.byref(o), C.byref(info))
     else:
-        st = ctx.lib.grm_cuda_ploidyaware(ctx.handle, _ptr(A_pn), n, p, n, int(ploidy), _ptr(out), n, C.byref(o),
+        st = ctx.lib.grm_cuda_ploidyaware(ctx.handle, a_ptr, n, p, n, int(ploidy), _ptr(out), n, C.byref(o),
                                           C.byref(info))
     _lib.check(st)
     ctx.order_torch_after()

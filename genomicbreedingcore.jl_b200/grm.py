@@ -34,10 +34,16 @@ def _raise_for(err: _lib.GrmCudaError):
 def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.Context] = None,
              path: int = _lib.PATH_AUTO, denominator: int = 0, max_iter: int = 1_000, skip_repair: bool = False,
              chunk_loci: int = 0, rank: int = 0, world: int = 1, out: Optional[np.ndarray] = None,
-             missing: str = "error", maf: float = 0.0, max_locus_sparsity: float = 1.0):
+             missing: str = "error", maf: float = 0.0, max_locus_sparsity: float = 1.0, distributed: bool = False,
+             input_slab: bool = False, p_total: Optional[int] = None, tiles: bool = False):
     """The C-ABI call a Julia `ccall` shim makes, on host buffers: grm_cuda_simple (ploidy is None) or
     grm_cuda_ploidyaware.  `A` is n x p (NaN = missing); a strided view of a larger Fortran array is passed with its
-    leading dimension, no copy.  Returns (G, info dict).  Raises GrmCudaError with the library status."""
+    leading dimension, no copy.  Returns (G, info dict).  Raises GrmCudaError with the library status.
+
+    distributed=True (the context carries a communicator, every rank makes the same call): `A` is the whole matrix
+    (the library reads only this rank's loci range of it) or, with input_slab=True, the rank's own loci range of a
+    matrix of p_total loci; every rank receives the complete, repaired GRM.  tiles=True returns this rank's packed
+    [tiles_owned, 256, 256] tiles instead (tile t is [col][row])."""
     ctx = ctx or _lib.default_context()
     A = np.asarray(A)
     if A.dtype != np.float64 or A.ndim != 2 or A.strides[0] != 8 or (A.shape[1] > 1 and A.strides[1] % 8) \
@@ -45,12 +51,23 @@ def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.
         A = np.asfortranarray(A, dtype=np.float64)
     n, p = A.shape
     lda = A.strides[1] // 8 if p > 1 else n
-    if out is None:
-        out = np.empty((n, n), dtype=np.float64, order="F")  # calc.jl:123
-        if world > 1:
-            out[...] = 0.0
-    ldg = out.strides[1] // 8 if n > 1 else n
     o = _lib.default_options()
+    trank, tworld = rank, world
+    if distributed:
+        o.distributed, o.input_slab = 1, 1 if input_slab else 0
+        if input_slab:
+            p = int(p_total)
+        trank, tworld, _ = ctx.comm_info()
+    if tiles:
+        o.output_mode = _lib.OUT_TILES
+    if out is None:
+        if tiles:
+            out = np.empty((max(ctx.lib.grm_cuda_tile_count(n, trank, tworld), 1), 256, 256), dtype=np.float64)
+        else:
+            out = np.empty((n, n), dtype=np.float64, order="F")  # calc.jl:123
+            if world > 1:
+                out[...] = 0.0
+    ldg = n if tiles else (out.strides[1] // 8 if n > 1 else n)
     o.path, o.denominator, o.max_iter = path, denominator, int(max_iter)
     o.skip_repair = 1 if skip_repair else 0
     o.chunk_loci = int(chunk_loci)
@@ -66,6 +83,78 @@ def grm_call(A: np.ndarray, ploidy: Optional[int] = None, *, ctx: Optional[_lib.
                                           C.byref(o), C.byref(info))
     _lib.check(st)
     return out, info.as_dict()
+
+
+def _finish_call(ctx, fn, args, o, info):
+    st = fn(ctx.handle, *args, C.byref(o), C.byref(info))
+    _lib.check(st)
+    return info.as_dict()
+
+
+def _options(path, denominator, max_iter, skip_repair, chunk_loci, missing, maf, max_locus_sparsity):
+    o = _lib.default_options()
+    o.path, o.denominator, o.max_iter = path, denominator, int(max_iter)
+    o.skip_repair = 1 if skip_repair else 0
+    o.chunk_loci = int(chunk_loci)
+    o.missing_policy = {"error": _lib.MISSING_ERROR, "meanfill": _lib.MISSING_MEANFILL}[missing]
+    o.maf, o.max_locus_sparsity = float(maf), float(max_locus_sparsity)
+    return o
+
+
+def grm_call_union(payload: np.ndarray, selectors: Optional[np.ndarray], float_tag: int, ploidy: Optional[int] = None, *,
+                   ctx: Optional[_lib.Context] = None, path: int = _lib.PATH_AUTO, denominator: int = 0,
+                   max_iter: int = 1_000, skip_repair: bool = False, chunk_loci: int = 0, missing: str = "error",
+                   maf: float = 0.0, max_locus_sparsity: float = 1.0):
+    """grm_cuda_simple_union / grm_cuda_ploidyaware_union: the call julia/GRMCuda.jl makes on
+    genomes.allele_frequencies as Julia stores it (Matrix{Union{Float64,Missing}}: payloads + selector bytes, pageable
+    memory, nothing converted on the caller's side).  `payload` (n, p) Fortran-ordered float64, `selectors` (n, p)
+    Fortran-ordered uint8 or None (plain Matrix{Float64})."""
+    ctx = ctx or _lib.default_context()
+    n, p = payload.shape
+    if payload.dtype != np.float64 or not payload.flags.f_contiguous:
+        raise TypeError("payload must be a Fortran-ordered float64 matrix")
+    if selectors is not None and (selectors.dtype != np.uint8 or selectors.shape != payload.shape
+                                  or not selectors.flags.f_contiguous):
+        raise TypeError("selectors must be a Fortran-ordered uint8 matrix of the payload's shape")
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    o = _options(path, denominator, max_iter, skip_repair, chunk_loci, missing, maf, max_locus_sparsity)
+    info = _lib.new_info()
+    sel_ptr = selectors.ctypes.data if selectors is not None else None
+    if ploidy is None:
+        d = _finish_call(ctx, ctx.lib.grm_cuda_simple_union, (payload.ctypes.data, sel_ptr, int(float_tag), n, p, n,
+                                                              out.ctypes.data, n), o, info)
+    else:
+        d = _finish_call(ctx, ctx.lib.grm_cuda_ploidyaware_union, (payload.ctypes.data, sel_ptr, int(float_tag), n, p, n,
+                                                                   int(ploidy), out.ctypes.data, n), o, info)
+    return out, d
+
+
+def grm_call_codes(codes: np.ndarray, m: int, ploidy: Optional[int] = None, *, ctx: Optional[_lib.Context] = None,
+                   max_iter: int = 1_000, skip_repair: bool = False, chunk_loci: int = 0, maf: float = 0.0,
+                   max_locus_sparsity: float = 1.0):
+    """grm_cuda_from_codes: the GRM of pre-packed int8 dosage codes (io.read_genomes of an int8 wire file), codes[i, k] =
+    m * x_ik, -128 = missing.  ploidy None -> grmsimple."""
+    ctx = ctx or _lib.default_context()
+    if codes.dtype != np.int8 or codes.ndim != 2 or not codes.flags.f_contiguous:
+        codes = np.asfortranarray(codes, dtype=np.int8)
+    n, p = codes.shape
+    out = np.empty((n, n), dtype=np.float64, order="F")
+    o = _options(_lib.PATH_I8, int(m), max_iter, skip_repair, chunk_loci, "error", maf, max_locus_sparsity)
+    info = _lib.new_info()
+    d = _finish_call(ctx, ctx.lib.grm_cuda_from_codes, (codes.ctypes.data, n, p, n, int(m), -1 if ploidy is None else int(ploidy),
+                                                        out.ctypes.data, n), o, info)
+    return out, d
+
+
+def grm_from_wire(path: str, ploidy: Optional[int] = None, **kw):
+    """GRM straight from a wire-format file (io.write_genomes): int8 payloads go through grm_cuda_from_codes, Float64
+    payloads through the plain entry points."""
+    from . import io
+
+    w = io.read_genomes(path)
+    if w.dtype == io.DTYPE_I8:
+        return grm_call_codes(w.data, w.m, ploidy, **kw)
+    return grm_call(w.data, ploidy, **kw)
 
 
 def _run(genomes: Genomes, centred: bool, ploidy: int, max_iter: int, verbose: bool, ctx, path, denominator,

@@ -13,7 +13,9 @@
  * Conventions (mirroring the Julia side):
  *   - All matrices are COLUMN-MAJOR, exactly as Julia stores them.  The input is
  *     genomes.allele_frequencies, n entries x p loci, element (i,k) at A[i + k*lda];
- *     a missing value is passed as NaN.  The output is the n x n Float64 GRM,
+ *     a missing value is passed as NaN (plain double* entry points) or through the
+ *     selector bytes of Julia's Matrix{Union{Float64,Missing}} (the *_union entry
+ *     points).  The output is the n x n Float64 GRM,
  *     element (i,j) at G[i + j*ldg]; both triangles are written and are
  *     bit-identical mirrors of each other (the reference asserts issymmetric,
  *     calc.jl:43).  Row/column order is the input order of genomes.entries
@@ -35,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GRM_CUDA_VERSION 100 /* 0.1.0 */
+#define GRM_CUDA_VERSION 200 /* 0.2.0 */
 
 typedef enum grm_cuda_status {
     GRM_CUDA_OK = 0,
@@ -50,8 +52,9 @@ typedef enum grm_cuda_status {
     GRM_CUDA_ERR_NOT_DOSAGE = 9,     /* int8 path forced but the frequencies are not k/m with m a power of two <= 64 */
     GRM_CUDA_ERR_OVERFLOW = 10,      /* m*m*p would overflow the int32 accumulators                                  */
     GRM_CUDA_ERR_ALL_FILTERED = 11,  /* QC mask: "All loci filtered out ..." (src/genomes/filter.jl:363-365, :644-646) */
-    GRM_CUDA_ERR_NOT_POSDEF = 12     /* grm_cuda_cholesky: Julia's PosDefException (what MvNormal(mu, Sigma) throws,
+    GRM_CUDA_ERR_NOT_POSDEF = 12,    /* grm_cuda_cholesky: Julia's PosDefException (what MvNormal(mu, Sigma) throws,
                                         src/simulations/simulate_effects.jl:480) */
+    GRM_CUDA_ERR_COMM = 13           /* NCCL not loadable / communicator missing / collective failed                  */
 } grm_cuda_status;
 
 /* Which contraction ran (grm_cuda_info.path) / may run (grm_cuda_options.path). */
@@ -72,6 +75,17 @@ typedef enum grm_cuda_status {
 
 typedef struct grm_cuda_ctx grm_cuda_ctx; /* opaque: device, streams, workspaces, cuSOLVER handle */
 
+/* grm_cuda_options.output_mode */
+#define GRM_CUDA_OUT_DENSE 0 /* the whole n x n matrix, both triangles (distributed calls: on every rank)            */
+#define GRM_CUDA_OUT_TILES 1 /* only the upper-triangular 256 x 256 tiles this rank owns, packed [t][col][row] FP64,
+                                t in grm_cuda_tile_at order, zeros outside the matrix; implies skip_repair.  For GRMs
+                                larger than one device (BASELINE config 5) and for hosts that keep the GRM sharded.   */
+
+/* grm_cuda_info.ingest / tuning key "ingest": how HOST input reaches the GPU */
+#define GRM_CUDA_INGEST_AUTO   0 /* dosage input: quantise on the host; continuous input: stream FP64                 */
+#define GRM_CUDA_INGEST_STREAM 1 /* FP64 cells cross PCIe (8 bytes per cell), quantised / centred on the device        */
+#define GRM_CUDA_INGEST_HOSTQ  2 /* host threads quantise to int8 into a pinned ring: 1 byte per cell crosses PCIe      */
+
 typedef struct grm_cuda_options {
     int32_t struct_size;     /* = sizeof(grm_cuda_options); lets the struct grow compatibly                    */
     int32_t path;            /* GRM_CUDA_PATH_*                                                                */
@@ -80,8 +94,9 @@ typedef struct grm_cuda_options {
     int32_t skip_repair;     /* 1 = return the raw GRM, i.e. stop before calc.jl:133 / :211                    */
     int32_t input_location;  /* GRM_CUDA_LOC_*: where A lives                                                  */
     int32_t output_location; /* GRM_CUDA_LOC_*: where G lives                                                  */
-    int32_t rank;            /* tile sharding: this process computes tiles t with owner(t) == rank ...         */
-    int32_t world;           /* ... out of `world` ranks (1 = everything).  Sharded calls imply skip_repair.   */
+    int32_t rank;            /* tile sharding WITHOUT a communicator (input replicated on every GPU): this call   */
+    int32_t world;           /* computes only the tiles owned by `rank` of `world`, written into their place of a
+                                dense G (other elements untouched); implies skip_repair.  1 = everything.        */
     int32_t missing_policy;  /* GRM_CUDA_MISSING_*                                                             */
     int64_t chunk_loci;      /* loci per host->device streaming chunk; 0 = automatic                           */
     /* Fused QC locus mask (extension; the step before the GRM in the reference's documented workflow).  A locus is
@@ -91,6 +106,19 @@ typedef struct grm_cuda_options {
      * max_locus_sparsity = 1 (the defaults) switch the mask off = the bare reference functions. */
     double maf;
     double max_locus_sparsity;
+    /* ---- since 0.2.0 ---- */
+    /* distributed = 1: ONE grmsimple / grmploidyaware call spread over the GPUs of the context's communicator
+     * (grm_cuda_comm_init; one process per GPU, the same call on every rank).  Rank r ingests only the loci range
+     * [L r, min(p, L (r+1))), L = ceil(p / world), of the n x p matrix: with input_slab = 0, A is the whole matrix and
+     * the library reads those columns of it; with input_slab = 1, A points at the rank's own range (its first column is
+     * locus L r).  p is always the total number of loci.  The exchange steps (integer statistics all-reduce, partial-tile
+     * reduce-scatter or code all-gather, tile all-gather, parallel inflatediagonals! probes) run inside the call over
+     * NCCL; with output_mode DENSE every rank receives the same, complete, repaired matrix (G may be NULL on ranks
+     * that do not want a copy). */
+    int32_t distributed;
+    int32_t input_slab;
+    int32_t output_mode;     /* GRM_CUDA_OUT_*                                                                   */
+    int32_t reserved0;
 } grm_cuda_options;
 
 typedef struct grm_cuda_info {
@@ -102,16 +130,26 @@ typedef struct grm_cuda_info {
     double scale;          /* divisor applied: p for grmsimple (calc.jl:127), d for grmploidyaware (calc.jl:201)*/
     int64_t tiles;         /* upper-triangular output tiles this call computed                                 */
     /* device timings, CUDA events on the library stream, milliseconds */
-    float ms_h2d;
+    float ms_h2d;          /* host input: first chunk issued -> last chunk packed (host work, PCIe and pack overlap) */
     float ms_pack;         /* column statistics + quantise/pack kernel                                         */
-    float ms_rowdot;       /* u = c.w row dot products for the rank-1 correction                               */
-    float ms_syrk;         /* int8 tcgen05 or FP64 SYRK kernel                                                 */
-    float ms_finalize;     /* mirror kernel                                                                    */
+    float ms_rowdot;       /* integer row statistics for the rank-1 correction (+ their all-reduce)            */
+    float ms_syrk;         /* int8 tcgen05 or FP64 SYRK kernel (+ the exchange waves overlapped with it)       */
+    float ms_finalize;     /* mirror kernel / tile finalisation                                                */
     float ms_repair;       /* inflatediagonals! (cuSOLVER LU/Cholesky + host pivot product)                    */
     float ms_d2h;
     float ms_total;        /* wall time of the whole call, host clock                                          */
     int32_t kernel_launches; /* kernels of this library launched by the call                                   */
     int32_t loci_kept;       /* loci that entered the GRM (= p without the QC mask)                            */
+    /* ---- since 0.2.0 ---- */
+    float ms_exchange;     /* distributed: exchange time NOT hidden under the SYRK (tail of the last wave)     */
+    float ms_gather;       /* distributed: all-gather of the finished tiles + unpack into the dense matrix      */
+    float ms_host_busy;    /* host input: summed wall time the worker pool spent quantising / copying           */
+    int32_t ingest;        /* GRM_CUDA_INGEST_* actually used (0 for device input)                              */
+    int32_t host_threads;  /* worker threads of the host ingest                                                 */
+    int32_t world;         /* ranks that took part (1 unless distributed)                                       */
+    int32_t exchange_waves;/* K-split: reduce-scatter waves overlapped with the SYRK                            */
+    int32_t syrk_window;   /* 1 if the SYRK ran with the K-window synchronisation                               */
+    int32_t reserved0;
 } grm_cuda_info;
 
 /* ---- library / context ------------------------------------------------------------------------------------ */
@@ -126,6 +164,24 @@ int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx);
 void *grm_cuda_ctx_stream(grm_cuda_ctx *ctx);
 int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx);
 
+/* Per-context tuning knobs; the library never reads the environment.  Keys (value 0 / -1 = automatic, the measured
+ * best): "syrk_i8" (1 single-CTA, 2 CTA pair, 3 wide), "syrk_packed" (2, 3), "syrk_sync" (-1 auto, 0 off, 1 on),
+ * "syrk_window", "pack" (1 = register-staged), "ieee_div", "tile_band", "host_threads", "ingest" (GRM_CUDA_INGEST_*),
+ * "ksplit_waves", "f64_kernel" (1 = register-staged operands), "ring_mb".  Unknown key -> GRM_CUDA_ERR_BAD_ARGUMENT. */
+int32_t grm_cuda_ctx_set_tuning(grm_cuda_ctx *ctx, const char *key, int64_t value);
+int32_t grm_cuda_ctx_get_tuning(grm_cuda_ctx *ctx, const char *key, int64_t *value);
+
+/* ---- communicator: one process per GPU, NCCL over NVLink / NVSwitch ------------------------------------------
+ * The reference's functions are single calls (grmsimple(genomes), calc.jl:115); to spread one call over several GPUs
+ * the exchange lives inside the library.  grm_cuda_comm_unique_id fills 128 opaque bytes on ONE rank; the host
+ * application hands them to the others (MPI, Distributed.jl, torch.distributed, a file ...) and every rank calls
+ * grm_cuda_comm_init (collective).  NCCL is dlopen'ed on first use: single-GPU users need no NCCL, and a process that
+ * already carries one (PyTorch) shares it. */
+int32_t grm_cuda_comm_unique_id(uint8_t *id128);
+int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world);
+int32_t grm_cuda_comm_destroy(grm_cuda_ctx *ctx);
+int32_t grm_cuda_comm_info(grm_cuda_ctx *ctx, int32_t *rank, int32_t *world, int32_t *nccl_version);
+
 /* ---- the three reference entry points ---------------------------------------------------------------------- */
 /* grmsimple, calc.jl:115-142:  G = A*A'/p, then inflatediagonals!. */
 int32_t grm_cuda_simple(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
@@ -136,6 +192,40 @@ int32_t grm_cuda_simple(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p
 int32_t grm_cuda_ploidyaware(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
                              int32_t ploidy, double *G, int64_t ldg, const grm_cuda_options *opts,
                              grm_cuda_info *info);
+
+/* The same two functions on genomes.allele_frequencies AS JULIA STORES IT: Matrix{Union{Float64,Missing}}
+ * (src/all_structs.jl:66) is an isbits-Union array = n*p Float64 payloads (column-major) followed by n*p selector
+ * bytes, in ordinary pageable memory.  payload / selectors are those two HOST pointers (selectors == NULL: a plain
+ * Matrix{Float64}, NaN then means missing as above); float_tag is the selector value of a Float64 cell (the shim
+ * computes it, julia/GRMCuda.jl), every other value is `missing`.  Nothing is converted or copied on the caller's side:
+ * worker threads read the caller's memory in place and feed a pinned ring (int8 codes for dosage input, FP64
+ * otherwise).  A Float64 cell holding NaN behaves as in the reference: it propagates into G and inflatediagonals!
+ * reports "The input matrix is not symmetric." (calc.jl:43) -> GRM_CUDA_ERR_NOT_SYMMETRIC (GRM_CUDA_ERR_NAN_MATRIX
+ * with skip_repair).  opts->input_location is ignored (always host). */
+int32_t grm_cuda_simple_union(grm_cuda_ctx *ctx, const double *payload, const uint8_t *selectors, int32_t float_tag,
+                              int64_t n, int64_t p, int64_t lda, double *G, int64_t ldg, const grm_cuda_options *opts,
+                              grm_cuda_info *info);
+int32_t grm_cuda_ploidyaware_union(grm_cuda_ctx *ctx, const double *payload, const uint8_t *selectors,
+                                   int32_t float_tag, int64_t n, int64_t p, int64_t lda, int32_t ploidy, double *G,
+                                   int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info);
+
+/* ... and on PRE-PACKED dosage codes (the wire format's int8 payload): codes[i + k*ldc] = m * x_ik in
+ * 0..m, column-major like A (entry fastest), HOST memory; m = denominator (power of two <= 64).  A negative byte is a
+ * missing cell (GRM_CUDA_ERR_MISSING unless the QC mask drops the locus).  ploidy < 0 selects grmsimple. */
+int32_t grm_cuda_from_codes(grm_cuda_ctx *ctx, const int8_t *codes, int64_t n, int64_t p, int64_t ldc, int32_t m,
+                            int32_t ploidy, double *G, int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info);
+
+/* Host utilities — no GPU involved.  The quantiser of the host ingest on its own: codes[i + k*ldo] = m * x_ik for
+ * the cells that are dosages, else a sentinel (-128 missing, -127 NaN payload, -126 +-Inf, -125 not k/m); *flags = OR of
+ * 1 missing | 2 Inf | 4 not a dosage | 16 NaN payload.  `threads` <= 0: one per available core.  This is the int8
+ * payload of the wire format (genomicbreedingcore.jl_b200/io.py) and the input of grm_cuda_from_codes.
+ * grm_cuda_host_detect: smallest power-of-two m <= 64 with m*x integral in [0, m] over the first max_cells cells
+ * (<= 0: all), 0 if none.  grm_cuda_host_simd: "avx512" / "avx2" / "scalar", the level picked at run time. */
+int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
+                               int64_t lda, int32_t m, int8_t *codes, int64_t ldo, int32_t threads, uint32_t *flags);
+int32_t grm_cuda_host_detect(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
+                             int64_t lda, int64_t max_cells, int32_t ignore_missing, int32_t *m_out);
+const char *grm_cuda_host_simd(void);
 
 /* inflatediagonals!, calc.jl:41-70.  `location` says where X lives (GRM_CUDA_LOC_*). */
 int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
@@ -203,11 +293,29 @@ int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *dA, int64_t
  *                                                 when ldc covers them up to the next multiple of 128)
  *   colsum[k]        = sum_i codes[i,k]           (int32, exact)
  *   flags[0]        |= 1 if a cell is NaN, 2 if +-Inf, 4 if m*x is not an integer in [0,m]
- * ldc (bytes per packed row) must be a multiple of 128.  d_keep (optional, pc bytes): loci with keep == 0 are packed
- * as zeros and not validated (QC mask). */
+ * ldc (bytes per packed row) must be a multiple of 128.  d_miss (optional, pc int32, zeroed by the caller) switches
+ * to QC mode: a NaN cell is packed as 0 and counted in miss[k] instead of raising flag 1 — grm_cuda_locus_keep then
+ * decides the mask from colsum / miss, so the QC mask costs no second pass over A. */
 int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda, int32_t m,
-                             int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
-                             const uint8_t *d_keep);
+                             int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags, int32_t *d_miss);
+
+/* The same products from int8 codes quantised on the HOST (grm_cuda_*_union, grm_cuda_from_codes): d_src is
+ * [locus][entry] with row stride lds (multiple of 4; the caller's column-major layout, 1 byte per cell); the kernel
+ * transposes to the K-major operand layout, sums the columns and decodes the sentinels of cells that are not codes
+ * (-128 missing -> flag 1 or miss[k], -127 NaN payload -> flag 16, -126 Inf -> flag 2, other negative -> flag 4).
+ * 2 bytes of HBM traffic per cell. */
+int32_t grm_cuda_pack_codes(grm_cuda_ctx *ctx, const int8_t *d_src, int64_t n, int64_t pc, int64_t lds,
+                            int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags, int32_t *d_miss);
+
+/* QC mask from the integers of a QC-mode pack: cnt = n - miss[k]; keep[k] = (n - cnt)/n <= max_locus_sparsity &&
+ * maf <= (colsum[k]/m)/cnt <= 1 - maf (filter.jl:361-368, :632-635 — for dosages the skipmissing mean is exact in any
+ * order).  Dropped loci get colsum 0; *d_kept += kept; error_on_missing raises flag 1 for a KEPT locus with missing
+ * cells.  grm_cuda_mask_codes then zeroes the dropped columns of the packed codes. */
+int32_t grm_cuda_locus_keep(grm_cuda_ctx *ctx, int32_t *d_colsum, const int32_t *d_miss, int64_t n, int64_t p, int32_t m,
+                            double maf, double max_locus_sparsity, int32_t error_on_missing, uint8_t *d_keep,
+                            uint64_t *d_kept, uint32_t *d_flags);
+int32_t grm_cuda_mask_codes(grm_cuda_ctx *ctx, int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
+                            const uint8_t *d_keep);
 
 /* QC locus mask in one pass over A: q[k] = mean(skipmissing(column k)); keep[k] = 1 iff the locus passes the
  * sparsity and MAF rules above; *d_kept += number of kept loci; d_stats (optional) (+)= {sum q(1-q), 0, sum q} over
@@ -243,26 +351,6 @@ int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_
 int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha, double beta,
                                 double gamma, double denom, const double *d_u, double *d_G, int64_t ldg,
                                 int32_t rank, int32_t world);
-
-/* The same exchange WITHOUT a collective, fused into the SYRK epilogue (one process per GPU, NVLink / NVSwitch peer
- * memory): every GPU owns a receive buffer of [world parts][tiles_max][256][256] int32 that its peers can address
- * (grm_cuda_ipc_alloc / _open).  grm_cuda_syrk_i8_scatter stores each finished int32 tile straight into its OWNER's
- * receive buffer, at part `rank`, while the tensor cores work on the next tile (plain coalesced stores to peer memory,
- * no atomics, every part written by exactly one GPU); after a barrier across the GPUs,
- * grm_cuda_finalize_tiles_parts sums the `world` parts of each owned tile (int32, exact, fixed order) and applies the
- * epilogue formula.  peer_recv: host array of `world` device pointers (entry r = rank r's receive buffer as mapped
- * in THIS process; entry `rank` = the own buffer).  The caller orders the steps: a peer may only be written after it
- * has finalised the previous step (dist.py uses the statistics all-reduce / a one-element all-reduce as barriers). */
-int32_t grm_cuda_syrk_i8_scatter(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                 int32_t rank, int32_t world, void *const *peer_recv);
-int32_t grm_cuda_finalize_tiles_parts(grm_cuda_ctx *ctx, const int32_t *d_recv, int64_t n, double alpha, double beta,
-                                      double gamma, double denom, const double *d_u, double *d_G, int64_t ldg,
-                                      int32_t rank, int32_t world);
-/* cudaMalloc'ed buffer + its 64-byte CUDA IPC handle; open / close a peer's handle; free an own buffer. */
-int32_t grm_cuda_ipc_alloc(grm_cuda_ctx *ctx, int64_t bytes, void **dptr, uint8_t *handle64);
-int32_t grm_cuda_ipc_open(grm_cuda_ctx *ctx, const uint8_t *handle64, void **dptr);
-int32_t grm_cuda_ipc_close(grm_cuda_ctx *ctx, void *dptr);
-int32_t grm_cuda_ipc_free(grm_cuda_ctx *ctx, void *dptr);
 
 /* Exact integer statistics of the codes for the rank-1 centring of grmploidyaware:
  *   r[i] = sum_k codes[i,k]      T[i] = sum_k codes[i,k]*colsum[k]      sums = { sum_k colsum[k], sum_k colsum[k]^2 }

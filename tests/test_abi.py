@@ -28,16 +28,16 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert C.sizeof(_lib.Options) == 64
-    assert C.sizeof(_lib.Info) == 80
+    assert C.sizeof(_lib.Options) == 80
+    assert C.sizeof(_lib.Info) == 120
     o = _lib.default_options()
-    assert (o.struct_size, o.path, o.max_iter, o.world, o.rank, o.skip_repair) == (64, 0, 1000, 1, 0, 0)
+    assert (o.struct_size, o.path, o.max_iter, o.world, o.rank, o.skip_repair) == (80, 0, 1000, 1, 0, 0)
     assert (o.maf, o.max_locus_sparsity, o.missing_policy) == (0.0, 1.0, 0)
 
 
 def test_version_and_status_strings():
     lib = _lib.load()
-    assert lib.grm_cuda_version() == 100
+    assert lib.grm_cuda_version() == 200
     assert lib.grm_cuda_status_string(4) == b"The input matrix is not symmetric."  # calc.jl:44
     assert lib.grm_cuda_status_string(5) == b"The input matrix contains NaN values."  # calc.jl:53
     assert lib.grm_cuda_status_string(6) == b"The input matrix contains Inf values."  # calc.jl:56

@@ -488,22 +488,22 @@ def test_sharded_tiles_union_is_bit_identical(world):
         part, _ = grm_call(Ac, None, skip_repair=True, rank=r, world=world)
         accc += part
     iu = np.triu_indices(600)
-    assert relerr(accc[iu] / 500.0, fullc[iu]) <= 1e-13  # sharded FP64 calls return raw sums
+    assert relerr(accc[iu], fullc[iu]) <= 1e-13  # sharded FP64 calls return their tiles already divided, like the int8 path
 
 
 @pytest.mark.parametrize("kernel", ["2cta", "wide"])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("ploidy", [None, 4])
-def test_loci_split_packed_tiles_emulated_ranks(ctx, monkeypatch, world, ploidy, kernel):
+def test_loci_split_packed_tiles_emulated_ranks(ctx, world, ploidy, kernel):
     """The "ksplit" multi-GPU decomposition with the ranks emulated on one GPU: every rank contracts its own loci
     over all tiles (raw int32 tiles in reduce-scatter layout), the tile buffers are summed (what the NCCL
     reduce-scatter does), every rank finalises the tiles it owns; the union must be bit-identical to one call.
-    `kernel`: the CTA-pair kernel or the two-tiles-per-pair kernel on the packed path (GRM_CUDA_SYRK_PACKED)."""
+    `kernel`: the CTA-pair kernel or the two-tiles-per-pair kernel on the packed path (tuning key "syrk_packed")."""
     import torch
 
-    monkeypatch.setenv("GRM_CUDA_SYRK_PACKED", kernel)
-
     from grm_b200 import device as D, dist as GD
+
+    ctx.set_tuning("syrk_packed", {"2cta": 2, "wide": 3}[kernel])
 
     n, p, m = 1100, 3001, 4
     A = synth.dosage(n, p, m, seed=61)
@@ -527,50 +527,8 @@ def test_loci_split_packed_tiles_emulated_ranks(ctx, monkeypatch, world, ploidy,
         D.finalize_tiles(ctx, total[rk * tmax:(rk + 1) * tmax].contiguous(), n, alpha, beta, gamma, denom, u, G, rk, world)
     D.scale_mirror(ctx, G, 1.0)
     ctx.synchronize()
+    ctx.set_tuning("syrk_packed", 0)
     assert np.array_equal(G.cpu().numpy(), full)
-
-
-@pytest.mark.parametrize("world", [2, 3, 8])
-@pytest.mark.parametrize("ploidy", [None, 4])
-def test_loci_split_peer_store_exchange_emulated_ranks(ctx, world, ploidy):
-    """The collective-free exchange of the "ksplit" decomposition with the ranks emulated on one GPU: every rank's SYRK
-    epilogue stores its int32 tiles straight into the owner's receive buffer (part = source rank), every owner sums
-    its `world` parts and finalises; the union must be bit-identical to one call.  (Across processes the receive
-    buffers are CUDA IPC mappings; here they are `world` buffers of one process.)"""
-    import torch
-
-    from grm_b200 import device as D, dist as GD
-
-    n, p, m = 1100, 3001, 4
-    A = synth.dosage(n, p, m, seed=62)
-    full, info = grm_call(A, ploidy, skip_repair=True)
-    At = to_dev(A)
-    tmax = ctx.lib.grm_cuda_packed_tiles_max(n, world)
-    bufs = [D.PeerBuffer(ctx, world * tmax * 65536 * 4) for _ in range(world)]
-    try:
-        assert all(len(b.handle) == 64 for b in bufs)
-        ptrs = [b.ptr for b in bufs]
-        sums = r = T = None
-        for rk in range(world):
-            k0, k1 = GD.loci_range(p, rk, world)
-            codes, colsum, flags = D.pack_dosage(ctx, At[k0:k1].contiguous(), m)
-            D.syrk_i8_scatter(ctx, codes, k1 - k0, rk, world, ptrs)
-            sums, r, T = D.dosage_stats(ctx, codes, k1 - k0, colsum, sums, r, T, accumulate=sums is not None)
-            ctx.synchronize()
-        if ploidy is None:
-            u, (alpha, beta, gamma, denom) = None, (1.0 / (m * m), 0.0, 0.0, float(p))
-        else:
-            u, (alpha, beta, gamma, denom) = D.dosage_centre(ctx, sums, r, T, p, m, ploidy)
-        G = torch.zeros((n, n), dtype=torch.float64, device=dev())
-        for rk in range(world):
-            D.finalize_tiles_parts(ctx, ptrs[rk], n, alpha, beta, gamma, denom, u, G, rk, world)
-        D.scale_mirror(ctx, G, 1.0)
-        ctx.synchronize()
-        assert np.array_equal(G.cpu().numpy(), full)
-    finally:
-        ctx.synchronize()
-        for b in bufs:
-            b.close()
 
 
 @pytest.mark.parametrize("world", [1, 3])
@@ -673,47 +631,6 @@ def test_full_size_c2_integer_properties(ctx):
     assert torch.equal(G, G.T)
     sub = Cfull[:64, :64].cpu().numpy().astype(np.float64)
     assert np.array_equal(G[:64, :64].cpu().numpy(), (sub / (m * m)) / p)
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# pipelined flow (pack of chunk c+1 and the integer statistics overlap the SYRK of chunk c): bit-identical to the
-# serial flow for any number of chunks, ragged sizes included
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,p,m,ploidy", [(300, 4000, 2, None), (257, 3001, 4, 4), (1000, 20_000, 2, 2),
-                                          (513, 1024, 4, None)])
-@pytest.mark.parametrize("chunks", [2, 3, 8])
-def test_pipelined_flow_is_bit_identical_to_serial(ctx, monkeypatch, n, p, m, ploidy, chunks):
-    import torch
-
-    from grm_b200 import device as D
-
-    At = synth.dosage_device(n, p, m, 11 + chunks, dev())
-    torch.cuda.synchronize()
-    monkeypatch.setenv("GRM_CUDA_PIPELINE", "1")
-    G0, i0 = D.grm_device(ctx, At, ploidy, skip_repair=True)
-    G0 = G0.clone()
-    monkeypatch.setenv("GRM_CUDA_PIPELINE", str(chunks))
-    G1, i1 = D.grm_device(ctx, At, ploidy, skip_repair=True)
-    ctx.synchronize()
-    assert i0["path"] == _lib.PATH_I8 and i1["path"] == _lib.PATH_I8
-    assert i1["kernel_launches"] > i0["kernel_launches"]  # the chunked SYRK launches really ran
-    assert torch.equal(G0, G1)
-    assert i0["scale"] == i1["scale"]
-    # errors surface the same way: a NaN in the last chunk
-    Ab = At.clone()
-    Ab[p - 1, n - 1] = float("nan")
-    with pytest.raises(_lib.GrmCudaError) as ei:
-        D.grm_device(ctx, Ab, ploidy, skip_repair=True)
-    assert ei.value.status == _lib.ERR_MISSING
-    # a non-dosage value in a late chunk: the sample-based guess is retried / falls back exactly as in the serial flow
-    Ac = At.clone()
-    Ac[p - 1, 0] = 0.3
-    G2, i2 = D.grm_device(ctx, Ac, ploidy, skip_repair=True)
-    G2 = G2.clone()
-    monkeypatch.setenv("GRM_CUDA_PIPELINE", "1")
-    G3, i3 = D.grm_device(ctx, Ac, ploidy, skip_repair=True)
-    assert i2["path"] == i3["path"] == _lib.PATH_F64
-    assert torch.equal(G2, G3)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -915,22 +832,39 @@ def test_estimateld_per_chromosome_correlation_matrices():
     assert chroms2 == sorted(set(labels)) and [x.shape[0] for x in LDs2] == [labels.count(c) for c in chroms2]
 
 
-@pytest.mark.parametrize("mode", ["wide", "quad"])
+@pytest.mark.parametrize("mode", ["wide", "single", "window"])
 @pytest.mark.parametrize("n,p,m,ploidy", [(300, 1000, 2, None), (700, 3001, 4, 4), (1100, 777, 2, None), (2049, 5001, 4, 2)])
-def test_syrk_kernel_variants_are_bit_identical_to_the_pair_kernel(ctx, monkeypatch, mode, n, p, m, ploidy):
-    """GRM_CUDA_SYRK_I8=wide: a CTA pair works on two tiles that share their column panel (the default for long
-    contractions with many tiles, i.e. C3; forced here on small ragged shapes incl. leftover single-tile units).
-    GRM_CUDA_SYRK_I8=quad: clusters of 4 with TMA multicast of the shared panel (opt-in; odd tile counts leave a shadow
-    tile).  Both must reproduce the pair kernel bit for bit."""
+def test_syrk_kernel_variants_are_bit_identical_to_the_pair_kernel(mode, n, p, m, ploidy):
+    """Tuning key "syrk_i8" = 3: a CTA pair works on two tiles that share their column panel (the default for long
+    contractions with many tiles, i.e. C3; forced here on small ragged shapes incl. leftover single-tile units);
+    = 1: the single-CTA kernel; "syrk_sync" = 1: the pair kernel with the K-window synchronisation (cooperative launch).
+    All must reproduce the plain pair kernel bit for bit.  A fresh context per run: the knobs are per context."""
     import torch
 
     from grm_b200 import device as D
 
     At = synth.dosage_device(n, p, m, 31, dev())
     torch.cuda.synchronize()
-    monkeypatch.setenv("GRM_CUDA_SYRK_I8", "2cta")
-    G0 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0].clone()
-    monkeypatch.setenv("GRM_CUDA_SYRK_I8", mode)
-    G1 = D.grm_device(ctx, At, ploidy, denominator=m, skip_repair=True)[0]
-    ctx.synchronize()
-    assert torch.equal(G0, G1)
+    c0, c1 = grm_b200.Context(0), grm_b200.Context(0)
+    try:
+        c0.set_tuning("syrk_i8", 2)
+        c0.set_tuning("syrk_sync", 0)
+        G0, i0 = D.grm_device(c0, At, ploidy, denominator=m, skip_repair=True)
+        if mode == "window":
+            c1.set_tuning("syrk_i8", 2)
+            c1.set_tuning("syrk_sync", 1)
+        else:
+            c1.set_tuning("syrk_i8", {"wide": 3, "single": 1}[mode])
+        assert c1.get_tuning("syrk_i8") in (1, 2, 3)
+        G1, i1 = D.grm_device(c1, At, ploidy, denominator=m, skip_repair=True)
+        c0.synchronize()
+        c1.synchronize()
+        assert i0["syrk_window"] == 0
+        if mode == "window":
+            assert i1["syrk_window"] == 1, "the cooperative launch of the K-window kernel was refused on an idle device"
+        assert torch.equal(G0, G1)
+    finally:
+        c0.close()
+        c1.close()
+    with pytest.raises(_lib.GrmCudaError):
+        grm_b200.default_context(0).set_tuning("no_such_knob", 1)
