@@ -7,11 +7,15 @@
 One "step" = one pass of the hot path over the workload: FP64 allele frequencies already resident in HBM ->
 column statistics + int8 pack -> locus stats / row dots -> tcgen05 int8 SYRK with the FP64 epilogue -> mirror
 (= the raw GRM, src/grm/calc.jl:189-209).  `value` times exactly that.  `e2e` times the reference-facing call
-(grm_cuda_ploidyaware through the C ABI) on HOST buffers: pinned H2D of the FP64 matrix, the same device pipeline,
-the inflatediagonals! repair (calc.jl:211) and the D2H of the n x n result are all inside the timed region.
+(ONE grm_cuda_ploidyaware_union call per rank through the C ABI) on HOST buffers laid out as Julia holds
+genomes.allele_frequencies — Matrix{Union{Float64,Missing}}: payloads + selector bytes in PAGEABLE memory: host threads
+quantise into a pinned ring, H2D, the same device pipeline (with the NCCL exchange inside the library at N > 1), the
+inflatediagonals! repair (calc.jl:211) and the D2H of the n x n result into pageable memory are all inside the timed
+region.  After the timed loops (outside them) the timed outputs are verified (`verified`).
 
 Workloads (BASELINE.json configs): c3 = 20,000 x 500,000 tetraploid grmploidyaware (default: the configuration the
-north_star target is quoted on; it fits one GPU), c2 = 5,000 x 100,000 diploid grmsimple, c1 = 100 x 10,000.
+north_star target is quoted on; it fits one GPU), c2 = 5,000 x 100,000 diploid grmsimple, c1 = 100 x 10,000,
+c4 = 10,000 x 1,000,000 continuous with 1 % missing (FP64 path), c5 = 100,000 x 50,000 (output kept as sharded tiles).
 """
 import argparse
 import json
@@ -31,6 +35,12 @@ WORKLOADS = {
                name="C2 5,000 x 100,000 diploid grmsimple (int8 dosage path)"),
     "c3": dict(n=20_000, p=500_000, ploidy=4, fn="grmploidyaware", gen_chunk=2500,
                name="C3 20,000 x 500,000 tetraploid grmploidyaware (int8 dosage path)"),
+    "c4": dict(n=10_000, p=1_000_000, ploidy=2, fn="grmploidyaware", gen_chunk=5000, kind="continuous", missing="meanfill",
+               missing_rate=0.01, name="C4 10,000 pools x 1,000,000 loci continuous pool-seq, 1 % missing mean-filled (FP64 SYRK path)"),
+    "c5": dict(n=100_000, p=50_000, ploidy=2, fn="grmsimple", gen_chunk=1250, tiles=True,
+               name="C5 100,000 x 50,000 diploid grmsimple, 80 GB GRM kept as sharded tiles (int8 path, code all-gather)"),
+    "small": dict(n=1_100, p=6_000, ploidy=4, fn="grmploidyaware", gen_chunk=2500,
+                  name="smoke-size 1,100 x 6,000 tetraploid grmploidyaware (bench self-test)"),
 }
 METRIC = "grm_mac_per_s"
 UNIT = "n^2*p/2 MAC/s"
@@ -175,13 +185,45 @@ def ncu_traffic():
     return {}
 
 
+def fill_host_parallel(dst_rows, src_dev, threads=8, block=1024):
+    """dst_rows[k] = src_dev[k] for a (rows, n) pageable numpy array: the device chunk goes through a pinned bounce
+    buffer, the copies into the (first-touched) pageable pages run on several threads (numpy releases the GIL)."""
+    import concurrent.futures as cf
+
+    import torch
+
+    rows = dst_rows.shape[0]
+    if rows == 0:
+        return
+    bounce = [torch.empty((min(block, rows), dst_rows.shape[1]), dtype=src_dev.dtype).pin_memory() for _ in range(2)]
+    def put(r0, bn, a, c):
+        dst_rows[r0 + a:r0 + c] = bn[a:c]
+
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+        pending = []
+        for i, r0 in enumerate(range(0, rows, block)):
+            r1 = min(rows, r0 + block)
+            b = bounce[i & 1][:r1 - r0]
+            b.copy_(src_dev[r0:r1])      # the other bounce buffer is still being drained by the threads
+            torch.cuda.synchronize()
+            for f in pending:
+                f.result()
+            bn = b.numpy()
+            step = max(1, (r1 - r0 + threads - 1) // threads)
+            pending = [ex.submit(put, r0, bn, a, min(a + step, r1 - r0)) for a in range(0, r1 - r0, step)]
+        for f in pending:
+            f.result()
+
+
 def run_b200(args, wl):
+    import ctypes as C
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import grm_b200
-    from grm_b200 import _lib, device as D, dist as GD, grm_call, synth
+    from grm_b200 import _lib, device as D, dist as GD, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,21 +235,35 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = grm_b200.Context(local)
+    if world > 1:
+        GD.init_comm(ctx)  # the library's own communicator: every exchange step of the path runs inside the C call
+    lib = ctx.lib
     peaks = load_peaks()
     n, p, ploidy = wl["n"], wl["p"], wl["ploidy"]
-    m = ploidy  # generator emits c/ploidy; ploidy 2 and 4 are power-of-two denominators
+    kind = wl.get("kind", "dosage")
+    m = ploidy if kind == "dosage" else 0  # generator emits c/ploidy; ploidy 2 and 4 are power-of-two denominators
     centred = wl["fn"] == "grmploidyaware"
+    pl = ploidy if centred else None
+    tiles_out = bool(wl.get("tiles")) or world > 1
+    missing = wl.get("missing", "error")
     k0, k1 = GD.loci_range(p, rank, world)
     pc = k1 - k0
 
-    # ---- synthetic input, generated on the device in fixed 2500-locus chunks (same data for every world size) ----
+    # ---- synthetic input, generated on the device in fixed chunks (same data for every world size) -------------
     gc = wl["gen_chunk"]
     A_dev = torch.empty((pc, n), dtype=torch.float64, device=dev)
     for c0 in range(0, p, gc):
         lo, hi = max(c0, k0), min(c0 + gc, k1)
         if lo >= hi:
             continue
-        blk = synth.dosage_device(n, min(gc, p - c0), ploidy, 1000 + c0 // gc, dev, chunk=gc)
+        if kind == "dosage":
+            blk = synth.dosage_device(n, min(gc, p - c0), ploidy, 1000 + c0 // gc, dev, chunk=gc)
+        else:
+            blk = synth.continuous_device(n, min(gc, p - c0), 1000 + c0 // gc, dev, chunk=gc)
+            if wl.get("missing_rate"):
+                g = torch.Generator(device=dev)
+                g.manual_seed(5000 + c0 // gc)
+                blk[torch.rand(blk.shape, generator=g, device=dev) < wl["missing_rate"]] = float("nan")
         A_dev[lo - k0:hi - k0] = blk[lo - c0:hi - c0]
         del blk
     torch.cuda.synchronize()
@@ -217,25 +273,31 @@ def run_b200(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident step --------------------------------------------------------------------------------
-    G_dev = None
-    sharded = None
-    stage_ms = {}
-    if world == 1:
-        G_dev = torch.empty((n, n), dtype=torch.float64, device=dev)
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- device-resident step: ONE library call per rank -------------------------------------------------------
+    path = _lib.PATH_I8 if kind == "dosage" else _lib.PATH_F64
+    if world == 1 and not tiles_out:
+        out_dev = torch.empty((n, n), dtype=torch.float64, device=dev)
 
         def step():
-            _, info = D.grm_device(ctx, A_dev, ploidy if centred else None, denominator=m, skip_repair=True, out=G_dev)
+            _, info = D.grm_device(ctx, A_dev, pl, path=path, denominator=m, skip_repair=True, out=out_dev, missing=missing)
             return info
     else:
-        sharded = GD.ShardedGRM(n, p, ploidy if centred else None, m, ctx)
+        if world == 1:
+            ctx.comm_init(_lib.comm_unique_id(), 0, 1)
+        sharded = GD.ShardedGRM(n, p, pl, m, ctx, output="tiles", path=path)
+        out_dev = sharded.out
 
         def step():
-            t = {}
-            sharded.step(A_dev, timings=t)
-            return t
+            sharded.step(A_dev)
+            return sharded.info
 
-    launches = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # sampled from the warm-up on: short multi-GPU timed regions would otherwise see no sample
@@ -250,87 +312,77 @@ def run_b200(args, wl):
         e1.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-    ms_step = ms / args.steps
+    ms_step = allmax(e0.elapsed_time(e1)) / args.steps
     value = macs(n, p) / (ms_step * 1e-3)
-    for key in ("ms_pack", "ms_exchange", "ms_rowdot", "ms_syrk", "ms_finalize"):
-        vals = [i[key] for i in infos if key in i]
-        if vals:
-            stage_ms[key] = sum(vals) / len(vals)
-    if world == 1:
-        launches = sum(i["kernel_launches"] for i in infos)
-    else:
-        launches = sharded.launches * args.steps // (args.steps + args.warmup)
+    stage_ms = {}
+    for key in ("ms_pack", "ms_rowdot", "ms_syrk", "ms_exchange", "ms_gather", "ms_finalize"):
+        stage_ms[key] = allmax(sum(i[key] for i in infos) / len(infos))  # max over ranks of the per-rank mean
+    launches = sum(i["kernel_launches"] for i in infos)
+    waves = infos[-1]["exchange_waves"]
+    window = infos[-1]["syrk_window"]
 
-    # ---- roofline of the dominant kernel (int8 tcgen05 SYRK) and of the HBM-bound pack kernel --------------------
+    # ---- what was timed is what is verified (outside the timed region) -------------------------------------------
+    verified = None
+    if not args.no_verify and kind == "dosage":
+        verified = verify_int8(ctx, A_dev, out_dev, infos[-1], n, p, pc, k0, m, pl, rank, world, tiles_out, dev)
+
+    # ---- library peaks measured in the same run (burst: best of a few back-to-back calls) ------------------------
+    lib_peaks = {}
+    if rank == 0 and not args.no_libpeaks:
+        lib_peaks = library_peaks(dev)
+
+    # ---- roofline of the dominant kernel and of the HBM-bound pack kernel ----------------------------------------
     T = (n + 255) // 256
-    tiles_rank = _lib.load().grm_cuda_tile_count(n, rank, world)
-    syrk_ms = stage_ms.get("ms_syrk", float("nan"))
-    if world > 1:
-        t = torch.tensor([syrk_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        syrk_ms = float(t[0])
-    alg_ops = 2.0 * macs(n, p) / world  # algorithmic int8 ops per launch per GPU: n^2 p / 2 MACs dealt over the ranks
-    achieved = alg_ops / (syrk_ms * 1e-3) / 1e12
-    # sustained peak for a kernel that keeps the tensor pipe busy for most of a long run (power-capped regime),
-    # burst peak for short launches (B200_PROFILING.md)
-    busy_ms = syrk_ms * (args.steps + args.warmup)
-    regime = "sustained" if busy_ms >= 400.0 else "burst"
-    int8_peak = 2.0 * (peaks["bf16_sustained"] if regime == "sustained" else peaks["bf16_burst"])
+    tiles_rank = lib.grm_cuda_tile_count(n, rank, world)
+    syrk_ms = stage_ms["ms_syrk"]
     tr = ncu_traffic() if world == 1 else {}
     wk = args.workload
-    roofline = {
-        "bound": "tensor", "kernel": ("syrk_i8_wide_kernel" if (world == 1 and (p + 127) // 128 >= 2048 and T * (T + 1) // 2 >= 296)
-                                     else "syrk_i8_2cta_kernel") + " (tcgen05.mma cta_group::2 kind::i8, TMA, TMEM)", "achieved": achieved,
-        "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
-        "frac_of_nominal_int8": achieved / 4500.0, "frac_of_burst_derived": achieved / (2.0 * peaks["bf16_burst"]),
-        "traffic": tr.get(f"syrk_i8_dram_bytes_per_launch_{wk}"),
-        "peak_note": f"int8 dense = 2 x measured {regime} bf16 ({peaks['source']}); unit counts int8 ops (1 MAC = 2 ops); "
-                     f"cuBLASLt int8 8192^3 measured on this pool: 3213 burst / 2579 sustained TOP/s (profiles/). "
-                     f"A fraction above 1 means the kernel does more int8 work per joule than cuBLAS does bf16 work "
-                     f"(the denominator is a power-capped library GEMM), not skipped work: results are bit-exact "
-                     f"against cuBLASLt int8 and the CPU oracle (tests/test_gpu_parity.py)",
-        "ms_per_launch": syrk_ms, "algorithmic_ops_per_launch": alg_ops, "tiles_owned": int(tiles_rank),
-    }
-    if world == 1 and infos and infos[0]["kernel_launches"] > 6:
-        roofline["launches_per_step"] = 4
-        roofline["note"] = ("pipelined flow: the loci are contracted in 4 chunk launches (the pack of the next chunk and "
-                            "the integer statistics run underneath on a second stream); ms_per_launch and "
-                            "algorithmic_ops_per_launch are the sums over the 4 launches of one step")
+    if kind == "dosage":
+        alg_ops = 2.0 * macs(n, p) / world  # algorithmic int8 ops per GPU per step: n^2 p / 2 MACs dealt over the ranks
+        achieved = alg_ops / (syrk_ms * 1e-3) / 1e12
+        wide = world == 1 and (p + 127) // 128 >= 2048 and T * (T + 1) // 2 >= 296
+        roofline = {
+            "bound": "tensor", "kernel": ("syrk_i8_wide_kernel" if wide else "syrk_i8_2cta_kernel") +
+            " (tcgen05.mma cta_group::2 kind::i8, TMA, TMEM)" + (f", {waves} launches per step (exchange waves)" if waves > 1 else ""),
+            "achieved": achieved, "peak": 4500.0, "unit": "TFLOP/s", "frac": achieved / 4500.0,
+            "peak_note": "NOMINAL dense int8 of a B200 (4,500 TOP/s; unit counts int8 ops, 1 MAC = 2 ops). "
+                         "MEASURED_PEAKS.json holds no int8 figure; frac_of_cublaslt_int8 is against a cuBLASLt int8 GEMM "
+                         "(torch._int_mm 8192^3) timed in this same run; frac_of_2x_bf16 (2 x the driver-measured bf16 peak: "
+                         "a power-capped library GEMM at ~1.3 GHz) is context only",
+            "frac_of_cublaslt_int8": (achieved / lib_peaks["int8_tops"]) if lib_peaks.get("int8_tops") else None,
+            "cublaslt_int8_tops_same_run": lib_peaks.get("int8_tops"),
+            "frac_of_2x_bf16_sustained": achieved / (2.0 * peaks["bf16_sustained"]),
+            "frac_of_2x_bf16_burst": achieved / (2.0 * peaks["bf16_burst"]), "peaks_source": peaks["source"],
+            "traffic": tr.get(f"syrk_i8_dram_bytes_per_launch_{wk}"),
+            "ms_per_launch": syrk_ms / max(waves, 1), "ms_per_step": syrk_ms, "algorithmic_ops_per_step": alg_ops,
+            "algorithmic_ops_per_launch": alg_ops / max(waves, 1), "tiles_owned": int(tiles_rank), "k_window_sync": int(window),
+        }
+        pack_ms = stage_ms["ms_pack"]
+        pack_bytes = 9.0 * n * pc  # 8 B read + 1 B written per cell
+        roofline_pack = {
+            "bound": "hbm", "kernel": "pack_dosage_tma_kernel", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
+            "peak": peaks["hbm"], "unit": "GB/s", "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / peaks["hbm"],
+            "traffic": tr.get(f"pack_dram_bytes_per_launch_{wk}"), "ms_per_launch": pack_ms, "timing": "timed inside the step",
+        }
+    else:
+        # FP64 path: the chunk loop (column means, centring, DMMA SYRK) is one stage; flop = n^2 p (upper triangle x 2)
+        flop = float(n) * n * pc
+        loop_ms = stage_ms["ms_pack"]
+        achieved = flop / (loop_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "syrk_f64_kernel (DMMA mma.sync.m16n8k8.f64) + centre_f64 + column means",
+                    "achieved": achieved, "peak": lib_peaks.get("dgemm_tflops"), "unit": "TFLOP/s",
+                    "frac": (achieved / lib_peaks["dgemm_tflops"]) if lib_peaks.get("dgemm_tflops") else None,
+                    "peak_note": "cuBLAS dgemm (torch.matmul 8192^3 FP64) timed in this same run", "traffic": None,
+                    "ms_per_step": loop_ms, "algorithmic_flop_per_step": flop}
+        roofline_pack = None
 
-    pack_ms = stage_ms.get("ms_pack", float("nan"))
-    pack_note = "timed inside the step"
-    if world == 1 and infos and infos[0]["kernel_launches"] > 6:
-        # pipelined flow: the step's pack runs on the auxiliary stream underneath the SYRK launches, so its span is not
-        # a kernel time; time the pack kernel alone (same input, CUDA events on the launching stream)
-        codes_b, colsum_b, flags_b = D.pack_dosage(ctx, A_dev, m)
-        with D.on_ctx_stream(ctx):
-            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            pe0.record()
-            for _ in range(3):
-                D.pack_dosage(ctx, A_dev, m, codes=codes_b, colsum=colsum_b, flags=flags_b)
-            pe1.record()
-            pe1.synchronize()
-        pack_ms = pe0.elapsed_time(pe1) / 3
-        pack_note = ("timed alone, 3 launches after the timed region (inside the pipelined step 3/4 of the pack runs "
-                     "underneath the SYRK launches at a lower rate)")
-        del codes_b, colsum_b, flags_b
-    pack_bytes = 9.0 * n * pc  # 8 B read + 1 B written per cell
-    roofline_pack = {
-        "bound": "hbm", "kernel": "pack_dosage_kernel", "achieved": pack_bytes / (pack_ms * 1e-3) / 1e9,
-        "peak": peaks["hbm"], "unit": "GB/s", "frac": pack_bytes / (pack_ms * 1e-3) / 1e9 / peaks["hbm"],
-        "traffic": tr.get(f"pack_dram_bytes_per_launch_{wk}"), "ms_per_launch": pack_ms, "timing": pack_note,
-    }
+    # ---- FP64 mode on the default line: a C4-shaped slice, SYRK kernel against same-run cuBLAS dgemm ---------------
+    roofline_f64 = None
+    if world == 1 and kind == "dosage" and not args.no_f64 and rank == 0:
+        roofline_f64 = f64_slice(ctx, dev, lib_peaks)
 
-    # ---- end to end through the C ABI with host buffers -----------------------------------------------------------
-    e2e = None
-    e2e_detail = {}
-    A_host = None
-    e2e_skip = None
+    # ---- end to end through the reference-facing C call on HOST buffers ------------------------------------------
+    e2e, e2e_skip, A_pay = None, None, None
     if not args.no_e2e:
         try:
             import psutil
@@ -338,85 +390,98 @@ def run_b200(args, wl):
             avail = psutil.virtual_memory().available
         except Exception:
             avail = None
-        need = 8 * n * pc + (8 * n * n if rank == 0 else 0)
-        if avail is not None and avail < 1.15 * need * world + (2 << 30):  # every rank allocates its share of the host
-            e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available, {need / 2**30:.0f} GiB needed for the host buffers"
+        need = 9 * n * pc + (8 * n * n if rank == 0 else 0)
+        if avail is not None and avail < 1.1 * need * world + (4 << 30):  # every rank allocates its share of the host
+            e2e_skip = f"host memory: {avail / 2**30:.0f} GiB available, {need * world / 2**30:.0f} GiB needed for the host buffers"
     if not args.no_e2e and e2e_skip is None:
-        try:
-            A_host = torch.empty((pc, n), dtype=torch.float64, pin_memory=True)
-            pinned = True
-        except Exception:
-            A_host = torch.empty((pc, n), dtype=torch.float64)
-            pinned = False
-        A_host.copy_(A_dev)
-        torch.cuda.synchronize()
-        esteps = args.e2e_steps or args.steps
-        h2d = 8 * n * pc
-        if world == 1:
-            del A_dev
-            torch.cuda.empty_cache()
-            A_np = A_host.numpy().T  # (n, p) column-major view, no copy
-            G_host = torch.empty((n, n), dtype=torch.float64, pin_memory=pinned)
-            G_np = G_host.numpy().T
-            pl = ploidy if centred else None
-            _, info = grm_call(A_np, pl, ctx=ctx, denominator=0, out=G_np)  # warm-up (allocations, cuSOLVER handle)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(esteps):
-                _, info = grm_call(A_np, pl, ctx=ctx, denominator=0, out=G_np)
-                launches_e2e = info["kernel_launches"]
-            barrier()
-            dt = (time.perf_counter() - t0) / esteps
-            d2h = 8 * n * n
-            e2e_detail = {k: info[k] for k in ("ms_h2d", "ms_syrk", "ms_repair", "ms_d2h", "ms_total", "repair_iters",
-                                               "eps_total", "denominator", "path")}
-            e2e_detail["pinned"] = pinned
-            e2e_detail["includes"] = "H2D (chunked, overlapped with pack), detect, pack, stats, rowdot, SYRK, mirror, inflatediagonals!, D2H"
+        # genomes.allele_frequencies as Julia holds it: Matrix{Union{Float64,Missing}} = n*pc Float64 payloads followed by
+        # n*pc selector bytes, in ordinary PAGEABLE memory (src/all_structs.jl:66).  No pinning, no conversion pass.
+        buf = np.empty(9 * n * max(pc, 1), dtype=np.uint8)
+        A_pay = buf[:8 * n * pc].view(np.float64).reshape((pc, n))  # C-order (pc, n) == column-major n x pc
+        A_sel = buf[8 * n * pc:9 * n * pc].reshape((pc, n))
+        fill_host_parallel(A_pay, A_dev)
+        if kind == "dosage" or not wl.get("missing_rate"):
+            for r0 in range(0, pc, 4096):
+                A_sel[r0:r0 + 4096] = 1  # every cell is a Float64
         else:
-            G_host = torch.empty((n, n), dtype=torch.float64, pin_memory=pinned) if rank == 0 else None
-            A_in = torch.empty((pc, n), dtype=torch.float64, device=dev)
-            import ctypes as C
+            for r0 in range(0, pc, 1024):  # missing cells live in the selectors; their payload is left as garbage (0.25)
+                blk = A_pay[r0:r0 + 1024]
+                miss = np.isnan(blk)
+                A_sel[r0:r0 + 1024] = (~miss).astype(np.uint8)
+                blk[miss] = 0.25
+        del A_dev
+        torch.cuda.empty_cache()
+        if tiles_out:
+            G_host = np.empty((max(int(tiles_rank), 1), 256, 256), dtype=np.float64)
+        else:
+            G_host = np.empty((n, n), dtype=np.float64, order="F") if rank == 0 else None  # pageable, like Julia's Matrix{Float64}
+        o = _lib.default_options()
+        o.path = _lib.PATH_AUTO  # the dosage denominator is detected on load, as the Julia shim does
+        o.missing_policy = _lib.MISSING_MEANFILL if missing == "meanfill" else _lib.MISSING_ERROR
+        if world > 1 or tiles_out:
+            o.distributed, o.input_slab = 1, 1
+        if tiles_out:
+            o.output_mode, o.skip_repair = _lib.OUT_TILES, 1
+        info = _lib.new_info()
+        g_ptr = G_host.ctypes.data if G_host is not None else None
 
-            def e2e_step():
-                with D.on_ctx_stream(ctx):
-                    A_in.copy_(A_host, non_blocking=True)
-                sharded.step(A_in)
-                G = sharded.gather()
-                # inflatediagonals! with the rounds probed in parallel, one per rank (every rank holds G after gather)
-                it, tot = GD.inflatediagonals_parallel(ctx, G, 1000)
-                if rank == 0:
-                    with D.on_ctx_stream(ctx):
-                        G_host.copy_(G, non_blocking=True)
-                ctx.synchronize()
-                return it, tot
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(esteps):
-                it, tot = e2e_step()
-            barrier()
-            dt = (time.perf_counter() - t0) / esteps
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
+        def call():
+            if centred:
+                st = lib.grm_cuda_ploidyaware_union(ctx.handle, A_pay.ctypes.data, A_sel.ctypes.data, 1, n, p, n, ploidy, g_ptr, n,
+                                                    C.byref(o), C.byref(info))
+            else:
+                st = lib.grm_cuda_simple_union(ctx.handle, A_pay.ctypes.data, A_sel.ctypes.data, 1, n, p, n, g_ptr, n, C.byref(o),
+                                               C.byref(info))
+            _lib.check(st)
+
+        esteps = args.e2e_steps or args.steps
+        call()  # warm-up (workspaces, pinned ring, cuSOLVER handle, worker threads)
+        barrier()
+        acc = {}
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            call()
+            for k in ("ms_h2d", "ms_host_busy", "ms_rowdot", "ms_syrk", "ms_exchange", "ms_gather", "ms_finalize", "ms_repair", "ms_d2h",
+                      "ms_total"):
+                acc[k] = acc.get(k, 0.0) + getattr(info, k)
+        barrier()
+        dt = allmax((time.perf_counter() - t0) / esteps)
+        launches_e2e = info.kernel_launches
+        detail = {k: allmax(v / esteps) for k, v in acc.items()}  # max over ranks of the per-rank mean
+        if tiles_out:
+            d2h = 8 * 65536 * int(tiles_rank)
+        else:
             d2h = 8 * n * n if rank == 0 else 0
-            e2e_detail = {"repair_iters": it, "eps_total": tot, "pinned": pinned,
-                          "includes": "per-rank H2D of its loci slab, pack, integer statistics + int64 all-reduce, SYRK over own loci, "
-                                      "int32 reduce-scatter onto the tile owners, finalize, all-reduce gather of G, "
-                                      "inflatediagonals! with its rounds probed in parallel (one per rank), D2H on rank 0"}
-        e2e = {"value": macs(n, p) / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt * 1e3, "steps": esteps, **e2e_detail}
+        e2e = {"value": macs(n, p) / dt, "unit": UNIT, "h2d_bytes_per_step": (n * pc if info.ingest == _lib.INGEST_HOSTQ else 8 * n * pc),
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": esteps, **detail,
+               "repair_iters": info.repair_iters, "eps_total": info.eps_total, "denominator": info.denominator, "path": info.path,
+               "ingest": {0: "device", 1: "FP64 stream", 2: "host-quantised int8"}[info.ingest], "host_threads": info.host_threads,
+               "host_bytes_read_per_step": 9 * n * pc, "pinned": False, "calls_per_rank_per_step": 1,
+               "kernel_launches_per_step": launches_e2e,
+               "includes": ("ONE C call per rank (grm_cuda_%s_union) on the PAGEABLE Matrix{Union{Float64,Missing}} layout "
+                            "(payloads + selector bytes) of %s: denominator detection, host threads quantise into a pinned ring, "
+                            "H2D, transpose/pack + column sums, integer statistics%s, tcgen05 SYRK%s, inflatediagonals! (%s), D2H into a "
+                            "pageable n x n matrix%s") % (
+                   "ploidyaware" if centred else "simple", "its own loci slab" if world > 1 else "the whole matrix",
+                   " + int64 all-reduce" if world > 1 else "", " over own loci in waves + int32 reduce-scatter (NCCL inside the library) + "
+                   "all-gather of the finished tiles" if world > 1 else "", "rounds probed in parallel, one per rank" if world > 1 else
+                   "cuSOLVER LU/Cholesky", " on rank 0" if world > 1 else "")}
+        if verified is not None and G_host is not None and not tiles_out and world == 1:
+            verified.update(verify_e2e(G_host, out_dev, info, n))
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------------------
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and kind == "dosage":
         nthreads = os.cpu_count() or 1
         p_sub = cpu_sample_loci(wl)
-        if A_host is not None:
-            A_sub = np.asfortranarray(A_host[:p_sub].numpy().T)
+        # a fresh PAGEABLE copy of the first loci (the pair loop strides through the matrix one element per 8n bytes:
+        # on the 4 KB pages of a pinned buffer it runs ~3x slower than on malloc'ed, huge-page-backed memory, which is
+        # what the 2.9x gap between this number and the --impl reference arm was in round 1)
+        if A_pay is not None:
+            A_sub = np.array(A_pay[:p_sub].T, order="F", copy=True)
         else:
             A_sub = synth.dosage(n, p_sub, ploidy, seed=42)
-        rows = cpu_rows_for(wl, A_sub, 12.0, nthreads)
+        rows = cpu_rows_for(wl, A_sub, 8.0, nthreads)
         rate, dt_cpu, m_cpu = cpu_sample(wl, A_sub, rows, nthreads)
         # not the reference's algorithm, reported so the GPU is not compared with the pair loop only: the same
         # contraction as one OpenBLAS dgemm (NumPy) on all host cores, on a 4096-entry x p_sub sample
@@ -431,36 +496,252 @@ def run_b200(args, wl):
                     f"(n^2 p/2 useful MACs of the n^2 p computed), {nthreads} host threads", "seconds": dtb}
         except Exception as ex:  # pragma: no cover
             blas = {"error": repr(ex)}
-        # the reference README's own setting is `julia --threads 2`: the same port on 2 threads, smaller sample
-        two = None
-        if nthreads > 2:
-            rows2 = max(2, rows * 2 // nthreads // 2)  # about half the wall time of the all-threads sample
-            rate2, dt2, m2 = cpu_sample(wl, A_sub, rows2, 2)
-            two = {"value": rate2, "unit": UNIT, "cores": 2, "seconds": dt2,
-                   "sample": f"pairs (i<{rows2}, j>=i) over the first {p_sub} loci = {m2:.3g} MACs"}
-        cpu = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port", "optimised_blas": blas, "two_threads": two,
+        cpu = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port", "optimised_blas": blas,
                "sample": f"oracle port of the src/grm/calc.jl pair loop ({wl['fn']}): pairs (i<{rows}, j>=i) of n={n} over the "
-                         f"first {p_sub} of {p} loci = {m_cpu:.3g} MACs in {dt_cpu:.1f} s on {nthreads} threads",
+                         f"first {p_sub} of {p} loci = {m_cpu:.3g} MACs in {dt_cpu:.1f} s on {nthreads} threads (pageable copy)",
                "seconds": dt_cpu}
 
+    if kind == "dosage":
+        par = (f"ONE library call per rank: loci-split pack + tcgen05 SYRK over own loci in {waves} waves, int32 reduce-scatter of "
+               f"wave w under the SYRK of wave w+1 (NCCL inside libgrm_cuda), tiles finalised on their owners x{world}") if world > 1 else "single GPU"
+        step_desc = ("FP64 A resident in HBM -> pack/stats -> integer row statistics -> SYRK -> " +
+                     ("finalised tiles stay sharded on their owners" if tiles_out else "mirror (raw GRM)") +
+                     "; the inflatediagonals! repair is in e2e, not in value")
+    else:
+        par = f"FP64 loci-split SYRK + FP64 reduce-scatter of upper-triangle tiles x{world}" if world > 1 else "single GPU"
+        step_desc = "FP64 A resident in HBM -> column means (+ mean-fill) -> centred operand -> DMMA SYRK -> scale/mirror (raw GRM)"
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8",
-        "data": "synthetic",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int8" if kind == "dosage" else "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "n": n, "p": p, "ploidy": ploidy, "function": wl["fn"],
-                   "dosage_denominator": m, "path": "int8 tcgen05 SYRK + FP64 rank-1 epilogue",
-                   "step": "FP64 A resident in HBM -> pack/stats -> rowdot -> SYRK -> mirror (raw GRM); the "
-                           "inflatediagonals! repair is in e2e, not in value",
-                   "l2": "inputs larger than L2 (FP64 input and int8 codes >> 126 MB)",
-                   "parallelism": f"loci-split pack + tcgen05 SYRK over own loci + int32 reduce-scatter onto tile owners x{world} ({sharded.mode})" if world > 1
-                   else "single GPU", "macs_per_step": macs(n, p)},
+                   "dosage_denominator": m, "path": "int8 tcgen05 SYRK + FP64 rank-1 epilogue" if kind == "dosage" else "FP64 DMMA SYRK",
+                   "step": step_desc, "l2": "inputs larger than L2 (FP64 input and int8 codes >> 126 MB)",
+                   "parallelism": par, "macs_per_step": macs(n, p)},
         "clocks": clocks, "e2e": e2e if e2e is not None else ({"unavailable": e2e_skip} if e2e_skip else None),
-        "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack,
-        "cpu_baseline": cpu, "stage_ms": stage_ms,
+        "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack, "roofline_f64": roofline_f64,
+        "verified": verified, "cpu_baseline": cpu, "stage_ms": stage_ms,
     }
     if world > 1:
         dist.destroy_process_group()
     return result
+
+
+def library_peaks(dev):
+    """cuBLASLt int8 GEMM and cuBLAS dgemm, timed in this run (burst figures: best of 5 back-to-back calls)."""
+    import torch
+
+    out = {}
+    try:
+        a = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev).t()  # column-major B, what cuBLASLt int8 wants
+        torch._int_mm(a, b)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out["int8_tops"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    except Exception as ex:  # pragma: no cover
+        out["int8_error"] = repr(ex)
+    try:
+        a = torch.rand((8192, 8192), dtype=torch.float64, device=dev)
+        torch.matmul(a, a.t())
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, a.t())
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out["dgemm_tflops"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a
+    except Exception as ex:  # pragma: no cover
+        out["dgemm_error"] = repr(ex)
+    torch.cuda.empty_cache()
+    return out
+
+
+def f64_slice(ctx, dev, lib_peaks, n=10_000, p=100_000):
+    """FP64 mode (north_star mode 2, BASELINE config 4) on a C4-shaped slice: 10,000 pools x 100,000 loci, continuous
+    frequencies with 1 % missing cells, mean-filled, grmploidyaware.  Times the whole one-call step and the DMMA SYRK
+    kernel alone (CUDA events on the library stream) against the cuBLAS dgemm rate of this run."""
+    import torch
+
+    from grm_b200 import _lib, device as D, synth
+
+    A = synth.continuous_device(n, p, 77, dev, chunk=5000)
+    g = torch.Generator(device=dev)
+    g.manual_seed(78)
+    for r0 in range(0, p, 5000):
+        blk = A[r0:r0 + 5000]
+        blk[torch.rand(blk.shape, generator=g, device=dev) < 0.01] = float("nan")
+    torch.cuda.synchronize()
+    G, info = D.grm_device(ctx, A, 2, skip_repair=True, missing="meanfill")  # warm-up
+    with D.on_ctx_stream(ctx):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        G, info = D.grm_device(ctx, A, 2, skip_repair=True, missing="meanfill", out=G)
+        e1.record()
+        e1.synchronize()
+    step_ms = e0.elapsed_time(e1)
+    # the SYRK kernel alone on an already centred operand
+    q, stats, flags = D.locus_stats_f64(ctx, A[:20_000], skip_missing=True)
+    Z = D.centre_f64(ctx, A[:20_000], True, 2.0, q, fill_missing=True)
+    D.syrk_f64(ctx, Z, out=G)
+    with D.on_ctx_stream(ctx):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            D.syrk_f64(ctx, Z, out=G)
+        e1.record()
+        e1.synchronize()
+    k_ms = e0.elapsed_time(e1) / 3
+    flop_k = float(n) * n * 20_000  # n (n + 1) / 2 pairs x 2 flop x loci ~ n^2 p
+    ach = flop_k / (k_ms * 1e-3) / 1e12
+    out = {"bound": "tensor", "kernel": "syrk_f64_kernel (mma.sync.m16n8k8.f64 DMMA, upper-triangular tiles)",
+           "workload": f"C4-shaped slice {n} x {p}, continuous, 1 % missing, mean-fill, grmploidyaware(ploidy=2)",
+           "achieved": ach, "peak": lib_peaks.get("dgemm_tflops"), "unit": "TFLOP/s",
+           "frac": (ach / lib_peaks["dgemm_tflops"]) if lib_peaks.get("dgemm_tflops") else None,
+           "peak_note": "cuBLAS dgemm (torch.matmul 8192^3 FP64) timed in this same run; tcgen05 has no FP64 kind, DMMA is the FP64 tensor path",
+           "ms_per_launch": k_ms, "algorithmic_flop_per_launch": flop_k, "traffic": None,
+           "step_ms": step_ms, "step_tflops": float(n) * n * p / (step_ms * 1e-3) / 1e12,
+           "step": "one call: column means (skip missing) + centre/mean-fill + SYRK over 100,000 loci + scale/mirror",
+           "path": info["path"], "loci_kept": info["loci_kept"]}
+    del A, Z, G
+    torch.cuda.empty_cache()
+    return out
+
+
+def verify_int8(ctx, A_dev, out_dev, info, n, p, pc, k0, m, pl, rank, world, tiles_out, dev, nrows=64):
+    """Checks on the OUTPUT OF THE TIMED STEP (outside the timed region), all against quantities computed by other code:
+    (1) the integer Gram matrix of the same input satisfies sum_ij C_ij = sum_k S_k^2, row sums = T_i (dp4a statistics
+    kernel) and C_ii = sum_k c_ik^2 (torch); (2) `nrows` random rows of the timed FP64 result against an exact
+    recomputation from the codes (torch FP64 matmul of small integers: every partial sum < 2^53) with the reference's
+    formula (calc.jl:197-209).  With several ranks the integer pieces are summed over the ranks' loci slabs."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from grm_b200 import device as D
+
+    res = {}
+    codes, colsum, flags = D.pack_dosage(ctx, A_dev, m)
+    ctx.synchronize()
+    S = colsum[:pc].long()
+    sums, r_, T_ = D.dosage_stats(ctx, codes, pc, colsum, m=m)
+    ctx.synchronize()
+    sumS2 = (S * S).sum()
+    cc = torch.zeros((n,), dtype=torch.int64, device=dev)
+    for c0 in range(0, pc, 25_000):
+        blk = codes[:, c0:min(pc, c0 + 25_000)].to(torch.int32)
+        cc += (blk * blk).sum(1, dtype=torch.int64)
+        del blk
+    if world == 1:
+        Cm = D.syrk_i8(ctx, codes, pc)  # [j, i] = C_ij for i <= j (upper triangle of the column-major matrix)
+        ctx.synchronize()
+        Cl = torch.triu(Cm.T.long())  # diagonal tiles hold their full square: keep i <= j only
+        full_rows = Cl.sum(0) + Cl.sum(1) - torch.diagonal(Cl)  # row sums of the mirrored matrix
+        res["sum_C_equals_sum_S2"] = bool(int(full_rows.sum()) == int(sumS2) == int(sums[1]))
+        res["row_sums_equal_T"] = bool(torch.equal(full_rows, T_))
+        res["diag_equals_sum_c2"] = bool(torch.equal(torch.diagonal(Cl), cc))
+        del Cm, Cl, full_rows
+        torch.cuda.empty_cache()
+    # rows of the timed result
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(12345)
+    rows = torch.sort(torch.randperm(n, generator=gen)[:nrows])[0].to(dev)
+    part = torch.zeros((nrows, n), dtype=torch.float64, device=dev)
+    for c0 in range(0, pc, 20_000):
+        blk = codes[:, c0:min(pc, c0 + 20_000)].double()
+        part += blk[rows] @ blk.T
+        del blk
+    stats = torch.cat([sums.to(torch.int64), r_, T_]).double() if pl is not None else None
+    if world > 1:
+        dist.all_reduce(part)
+        if stats is not None:
+            st64 = torch.cat([sums.to(torch.int64), r_, T_])
+            dist.all_reduce(st64)
+            sums, r_, T_ = st64[:2], st64[2:2 + n], st64[2 + n:]
+    Cr = part  # exact integers
+    if pl is None:
+        ref = (Cr / float(m * m)) / torch.tensor(float(p), dtype=torch.float64, device=dev)
+    else:
+        mn = float(m) * float(n)
+        h = 0.5 * pl
+        s = float(pl) / float(m)
+        S1, S2 = int(sums[0]), int(sums[1])
+        d = float(pl) * (float(m * n * S1 - S2) / (mn * mn))  # calc.jl:201 from exact integers
+        W2 = (float(p) * h * h + 2.0 * h * (S1 / mn)) + S2 / (mn * mn)
+        u = h * r_.double() + T_.double() / mn
+        v = (Cr * (s * s) - s * (u[rows][:, None] + u[None, :])) + W2
+        ref = v / torch.tensor(d, dtype=torch.float64, device=dev)
+        res["scale_d_rel_err"] = abs(info["scale"] - d) / abs(d)
+    # pick the same rows out of the timed output
+    if not tiles_out:
+        got = out_dev[rows]  # symmetric: row i of the matrix
+        err = float(((got - ref).abs().max() / ref.abs().max()))
+        res["symmetric"] = bool(torch.equal(out_dev, out_dev.T))
+        res["rows_checked"] = nrows
+    else:
+        # sharded output: every owned tile that intersects the chosen rows (as rows or, mirrored, as columns)
+        ti, tj = C.c_int64(), C.c_int64()
+        cnt = ctx.lib.grm_cuda_tile_count(n, rank, world)
+        rows_h = rows.cpu().tolist()
+        pos = {r: i for i, r in enumerate(rows_h)}
+        err, checked = 0.0, 0
+        scale_ref = float(ref.abs().max())
+        for t in range(cnt):
+            ctx.lib.grm_cuda_tile_at(n, rank, world, t, C.byref(ti), C.byref(tj))
+            r0, c0 = ti.value * 256, tj.value * 256
+            tile = out_dev[t]  # [col][row]
+            for r in rows_h:
+                if r0 <= r < min(r0 + 256, n):  # row r of the tile: columns c0 .. (upper triangle only on diagonal tiles)
+                    lo = max(c0, r) if ti.value == tj.value else c0
+                    hi = min(c0 + 256, n)
+                    if lo < hi:
+                        err = max(err, float((tile[lo - c0:hi - c0, r - r0] - ref[pos[r], lo:hi]).abs().max()) / scale_ref)
+                        checked += 1
+                if ti.value != tj.value and c0 <= r < min(c0 + 256, n):  # column r of the tile = row r of the mirror
+                    hi = min(r0 + 256, n)
+                    err = max(err, float((tile[r - c0, :hi - r0] - ref[pos[r], r0:hi]).abs().max()) / scale_ref)
+                    checked += 1
+        if world > 1:
+            t_ = torch.tensor([err], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            err = float(t_[0])
+        res["tile_row_segments_checked_on_rank0"] = checked
+        res["rows_checked"] = nrows
+    res["rows_max_rel_err"] = err
+    res["rows_ok"] = bool(err <= 1e-12)  # north_star: final GRM within 1e-12 relative on the int8 path
+    res["what"] = ("output of the timed device step vs an exact recomputation from the integer codes (torch FP64 matmul, "
+                   "reference formula calc.jl:197-209) on %d random rows; integer identities of the Gram matrix" % nrows)
+    del codes, colsum, part
+    torch.cuda.empty_cache()
+    return res
+
+
+def verify_e2e(G_host, out_dev, info, n):
+    """The end-to-end result (host call, host-quantised ingest, with the repair) against the device step's raw GRM: every
+    off-diagonal element bit-identical, the diagonal larger by exactly the repair's eps_total (calc.jl:62-66)."""
+    import numpy as np
+
+    raw = out_dev.cpu().numpy()  # symmetric: memory order does not matter
+    diff = G_host - raw
+    dg = np.diagonal(diff).copy()
+    np.fill_diagonal(diff, 0.0)
+    want = np.diagonal(raw) + info.eps_total if info.repair_iters == 1 else None
+    ok_diag = bool(np.allclose(dg, info.eps_total, rtol=1e-12, atol=1e-15)) if info.repair_iters > 0 else bool((dg == 0).all())
+    if want is not None:
+        ok_diag = ok_diag and bool(np.array_equal(np.diagonal(G_host), want))
+    return {"e2e_offdiag_bit_identical_to_device_step": bool(not diff.any()), "e2e_diag_inflated_by_eps_total": ok_diag,
+            "e2e_symmetric": bool(np.array_equal(G_host, G_host.T))}
 
 
 def main():
@@ -473,6 +754,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-f64", action="store_true", help="skip the FP64-mode slice (roofline_f64) of the default line")
+    ap.add_argument("--no-libpeaks", action="store_true", help="skip the same-run cuBLASLt int8 / cuBLAS dgemm timings")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -229,6 +229,77 @@ struct Feeder {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Way out for a PAGEABLE result (Julia's Matrix{Float64}): an asynchronous device->host copy into pageable memory
+// blocks the calling thread until it is done, which would put the 8 n^2 bytes in front of the repair instead of under
+// it.  A helper thread drains the matrix through the pinned ring (idle once the ingest is over) — copy engine -> pinned
+// slot, then the worker pool spreads the memcpy into the caller's pages — while the main thread drives the
+// factorisations.  The repair only ever changes the diagonal, which is patched afterwards.
+// ---------------------------------------------------------------------------------------------------------------
+struct OutCopier {
+    std::thread th;
+    int32_t status = GRM_CUDA_OK;
+    char err[256] = "";
+    bool active = false;
+
+    struct CopyJob {
+        const double *src;
+        double *dst;
+        int64_t n, ldg, cols;
+    };
+    static void copy_job(void *arg, int tid, int nt) {
+        const CopyJob *j = static_cast<const CopyJob *>(arg);
+        const int64_t a = j->cols * tid / nt, b = j->cols * (tid + 1) / nt;
+        for (int64_t c = a; c < b; ++c) memcpy(j->dst + c * j->ldg, j->src + c * j->n, static_cast<size_t>(j->n) * sizeof(double));
+    }
+
+    void fail(const char *what, cudaError_t e) {
+        status = GRM_CUDA_ERR_CUDA;
+        snprintf(err, sizeof(err), "result copy-out: %s failed: %s", what, cudaGetErrorString(e));
+    }
+
+    // ready: event on which dG is complete.  Uses ctx->copy_stream, ctx->copy_done[] and the pinned ring.
+    void start(grm_cuda_ctx *ctx, const double *dG, int64_t ldG, int64_t n, double *G, int64_t ldg, cudaEvent_t ready) {
+        active = true;
+        th = std::thread([=]() {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess) return fail("cudaSetDevice", e);
+            cudaStream_t cs = ctx->copy_stream;
+            if ((e = cudaStreamWaitEvent(cs, ready, 0)) != cudaSuccess) return fail("cudaStreamWaitEvent", e);
+            const int64_t cols = std::max<int64_t>(1, static_cast<int64_t>(ctx->pin_cap / (static_cast<size_t>(n) * sizeof(double))));
+            const int64_t nchunks = (n + cols - 1) / cols;
+            auto issue = [&](int64_t c) -> cudaError_t {
+                const int s = static_cast<int>(c % RING);
+                const int64_t c0 = c * cols, l = std::min(cols, n - c0);
+                cudaError_t r = cudaMemcpy2DAsync(ctx->pin[s], n * sizeof(double), dG + c0 * ldG, ldG * sizeof(double),
+                                                  n * sizeof(double), static_cast<size_t>(l), cudaMemcpyDeviceToHost, cs);
+                if (r != cudaSuccess) return r;
+                return cudaEventRecord(ctx->copy_done[s], cs);
+            };
+            for (int64_t c = 0; c < std::min<int64_t>(RING, nchunks); ++c)
+                if ((e = issue(c)) != cudaSuccess) return fail("cudaMemcpy2DAsync", e);
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int s = static_cast<int>(c % RING);
+                if ((e = cudaEventSynchronize(ctx->copy_done[s])) != cudaSuccess) return fail("cudaEventSynchronize", e);
+                const int64_t c0 = c * cols, l = std::min(cols, n - c0);
+                CopyJob job{static_cast<const double *>(ctx->pin[s]), G + c0 * ldg, n, ldg, l};
+                grm_pool_run(ctx->pool, copy_job, &job);
+                if (c + RING < nchunks && (e = issue(c + RING)) != cudaSuccess) return fail("cudaMemcpy2DAsync", e);
+            }
+        });
+    }
+    int32_t join() {
+        if (!active) return GRM_CUDA_OK;
+        th.join();
+        active = false;
+        if (status != GRM_CUDA_OK) grm_set_error("%s", err);
+        return status;
+    }
+    ~OutCopier() {
+        if (active && th.joinable()) th.join();
+    }
+};
+
 // precedence as in the reference: any `missing` makes grmsimple / grmploidyaware throw (calc.jl:127,205) whatever else
 // the matrix holds; a NaN payload only surfaces later, in inflatediagonals! (calc.jl:43)
 int32_t flags_to_status(uint32_t f, bool skip_repair) {
@@ -909,6 +980,9 @@ int32_t Run::go() {
     // The repair only ever touches the diagonal, so the bulk device->host copy of G runs on the copy stream WHILE the
     // O(n^3) factorisations run; if a round of inflation happened, the n diagonal values are copied again afterwards.
     const bool want_copy = out_host && G != nullptr;
+    // a pageable dense result leaves through the helper thread (OutCopier); pinned memory is copied to directly
+    const bool via_ring = want_copy && !out_tiles && !is_pinned(G);
+    OutCopier drain;
     bool bulk_started = false;
     auto copy_out = [&](cudaStream_t s) -> int32_t {
         if (out_tiles) {
@@ -923,7 +997,14 @@ int32_t Run::go() {
         }
         return GRM_CUDA_OK;
     };
-    if (want_copy && do_repair) {
+    if (via_ring) {
+        GRM_TRY(ensure_pool(ctx, world));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the ring and its events belong to the finished ingest
+        GRM_TRY(ensure_ring(ctx, std::max<size_t>(ctx->pin_cap, std::max<size_t>(32u << 20, static_cast<size_t>(n) * sizeof(double)))));
+        GRM_CUDA_TRY(cudaEventRecord(ev[7], st));
+        drain.start(ctx, dG, ldG, n, G, ldg, ev[4]);
+        bulk_started = true;
+    } else if (want_copy && do_repair) {
         GRM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ev[4], 0));
         GRM_CUDA_TRY(cudaEventRecord(ev[7], ctx->copy_stream));
         GRM_TRY(copy_out(ctx->copy_stream));
@@ -934,12 +1015,26 @@ int32_t Run::go() {
         const int32_t rst = dist ? repair_parallel(dG, ldG)
                                  : grm_repair_device(ctx, dG, n, ldG, o.max_iter, &inf.repair_iters, &inf.eps_total);
         if (rst != GRM_CUDA_OK) {
+            drain.join();
             cudaStreamSynchronize(ctx->copy_stream);  // never leave a copy into the caller's buffer in flight
             return rst;
         }
     }
     GRM_CUDA_TRY(cudaEventRecord(ev[5], st));
-    if (want_copy) {
+    if (via_ring) {
+        Timer td;
+        GRM_TRY(drain.join());
+        GRM_CUDA_TRY(cudaEventRecord(ev[8], st));
+        inf.ms_d2h = td.ms();  // what the copy-out adds after the repair (the rest ran underneath it)
+        if (inf.repair_iters > 0) {
+            // the repaired diagonal: n doubles through a pinned slot, scattered by the host
+            double *pd = static_cast<double *>(ctx->pin[0]);
+            GRM_CUDA_TRY(cudaMemcpy2DAsync(pd, sizeof(double), dG, (ldG + 1) * sizeof(double), sizeof(double),
+                                           static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+            GRM_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int64_t i = 0; i < n; ++i) G[i * (ldg + 1)] = pd[i];
+        }
+    } else if (want_copy) {
         if (bulk_started) {
             if (inf.repair_iters > 0) {
                 // diagonal only: n elements with a pitch of (ld + 1) doubles on both sides
@@ -980,7 +1075,7 @@ int32_t Run::go() {
     cudaEventElapsedTime(&inf.ms_gather, ev[10], ev[11]);
     cudaEventElapsedTime(&inf.ms_finalize, ev[11], ev[4]);
     cudaEventElapsedTime(&inf.ms_repair, ev[4], ev[5]);
-    if (want_copy) cudaEventElapsedTime(&inf.ms_d2h, ev[7], ev[8]);
+    if (want_copy && !via_ring) cudaEventElapsedTime(&inf.ms_d2h, ev[7], ev[8]);
     inf.ms_h2d = src.host ? inf.ms_pack : 0.f;  // host input: the ingest stage is host work, PCIe and pack overlapped
     inf.host_threads = (src.host && ctx->pool) ? grm_pool_threads(ctx->pool) : 0;
     inf.ms_total = wall.ms();
