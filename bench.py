@@ -474,9 +474,10 @@ def run_b200(args, wl):
     if world == 1 and not args.no_cpu and kind == "dosage":
         nthreads = os.cpu_count() or 1
         p_sub = cpu_sample_loci(wl)
-        # a fresh PAGEABLE copy of the first loci (the pair loop strides through the matrix one element per 8n bytes:
-        # on the 4 KB pages of a pinned buffer it runs ~3x slower than on malloc'ed, huge-page-backed memory, which is
-        # what the 2.9x gap between this number and the --impl reference arm was in round 1)
+        # a fresh PAGEABLE copy of the first loci, as the --impl reference arm uses.  Round 1 sampled a VIEW of the
+        # cudaHostAlloc'ed input instead and measured 9.5e8 MAC/s against the arm's 2.76e9 on the same box and threads;
+        # with the copy the two agree (3.1e9 measured).  The pair loop strides through the matrix one element per 8n
+        # bytes, so it is sensitive to how the pages are mapped.
         if A_pay is not None:
             A_sub = np.array(A_pay[:p_sub].T, order="F", copy=True)
         else:

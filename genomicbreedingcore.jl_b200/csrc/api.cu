@@ -150,7 +150,7 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     for (auto &pp : ctx->pin)
         if (pp) cudaFreeHost(pp);
     DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
-                      &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->stage[2], &ctx->stage[3], &ctx->lu,
+                      &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->stage[2], &ctx->stage[3], &ctx->lu, &ctx->lu2,
                       &ctx->lu_work, &ctx->ipiv, &ctx->misc, &ctx->misc2, &ctx->planes, &ctx->rT, &ctx->cnt, &ctx->keep,
                       &ctx->progress, &ctx->packed, &ctx->reduced, &ctx->gtiles, &ctx->gtiles_all, &ctx->codes_all,
                       &ctx->cons, &ctx->tiles_i8.buf, &ctx->tiles_i8_2cta.buf, &ctx->tiles_f64.buf, &ctx->tiles_packed.buf,

@@ -87,7 +87,7 @@ struct grm_cuda_ctx {
     cudaEvent_t copy_done[4] = {}, stage_free[4] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
-    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[4], lu, lu_work, ipiv, misc, misc2, planes, rT, cnt,
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[4], lu, lu2, lu_work, ipiv, misc, misc2, planes, rT, cnt,
         keep, progress, packed, reduced, gtiles, gtiles_all, codes_all, cons;
     TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed, tiles_wide, tiles_f64_all;
     int64_t factor_n = -1;  // >= 0: ctx->lu holds the upper Cholesky factor of the n x n matrix the last repair returned

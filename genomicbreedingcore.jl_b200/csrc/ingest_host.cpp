@@ -75,14 +75,23 @@ void grm_pool_destroy(GrmHostPool *pool) {
 
 int grm_pool_threads(const GrmHostPool *pool) { return pool ? static_cast<int>(pool->workers.size()) : 0; }
 
-void grm_pool_run(GrmHostPool *pool, void (*fn)(void *, int, int), void *arg) {
-    std::unique_lock<std::mutex> lk(pool->mu);
+void grm_pool_start(GrmHostPool *pool, void (*fn)(void *, int, int), void *arg) {
+    std::lock_guard<std::mutex> lk(pool->mu);
     pool->fn = fn;
     pool->arg = arg;
     pool->pending = static_cast<int>(pool->workers.size());
     ++pool->generation;
     pool->cv_job.notify_all();
+}
+
+void grm_pool_wait(GrmHostPool *pool) {
+    std::unique_lock<std::mutex> lk(pool->mu);
     pool->cv_done.wait(lk, [&] { return pool->pending == 0; });
+}
+
+void grm_pool_run(GrmHostPool *pool, void (*fn)(void *, int, int), void *arg) {
+    grm_pool_start(pool, fn, arg);
+    grm_pool_wait(pool);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -113,9 +122,13 @@ static inline int8_t quantise_cell(double x, bool is_float, bool have_sel, doubl
     return GRM_CODE_BAD;
 }
 
-#ifndef GRM_PF_DIST
-#define GRM_PF_DIST 4096  // bytes ahead of the streaming read (measured: 7.8 -> 11.7 GB/s per thread, 56 -> 73 GB/s on 8)
-#endif
+// Software prefetch distance (bytes ahead of the streaming read) of the quantiser.  A single core's demand misses do not
+// fill its share of the memory system; prefetching a few KB ahead does (measured on the build host: 7.8 -> 11.7 GB/s per
+// thread, 56 -> 73 GB/s on 8 threads; on the B200 host, 16 threads: 97 GB/s without, 150 at 4 KB, 157 at 8 KB —
+// profiles/host_ingest_sweep_r2.jsonl).  Run-time adjustable (grm_cuda_host_tune) so that it can be swept on the target.
+static int g_pf_dist = 8192;
+void grm_host_set_prefetch(int bytes) { g_pf_dist = bytes < 0 ? 0 : (bytes > (1 << 20) ? (1 << 20) : bytes); }
+int grm_host_get_prefetch(void) { return g_pf_dist; }
 
 static uint32_t quantise_col_scalar(const double *x, const uint8_t *s, int tag, int64_t n, double mf, int8_t *out) {
     uint32_t flags = 0;
@@ -130,9 +143,12 @@ quantise_col_avx512(const double *x, const uint8_t *s, int tag, int64_t n, doubl
     const __m256i vmax = _mm256_set1_epi32(m);
     const __m128i vtag = _mm_set1_epi8(static_cast<char>(tag));
     int64_t i = 0;
+    const int pf = g_pf_dist;
     for (; i + 16 <= n; i += 16) {
-        _mm_prefetch(reinterpret_cast<const char *>(x + i) + GRM_PF_DIST, _MM_HINT_T0);
-        _mm_prefetch(reinterpret_cast<const char *>(x + i) + GRM_PF_DIST + 64, _MM_HINT_T0);
+        if (pf) {
+            _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf, _MM_HINT_T0);
+            _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf + 64, _MM_HINT_T0);
+        }
         const __m512d t0 = _mm512_mul_pd(_mm512_loadu_pd(x + i), vm);
         const __m512d t1 = _mm512_mul_pd(_mm512_loadu_pd(x + i + 8), vm);
         const __m256i c0 = _mm512_cvtpd_epi32(t0);  // round to nearest even; NaN / out of range -> 0x80000000
@@ -159,7 +175,9 @@ __attribute__((target("avx2"))) static uint32_t quantise_col_avx2(const double *
     const __m256d vm = _mm256_set1_pd(mf);
     const __m128i vmax = _mm_set1_epi32(m);
     int64_t i = 0;
+    const int pf = g_pf_dist;
     for (; i + 8 <= n; i += 8) {
+        if (pf) _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf, _MM_HINT_T0);
         const __m256d t0 = _mm256_mul_pd(_mm256_loadu_pd(x + i), vm);
         const __m256d t1 = _mm256_mul_pd(_mm256_loadu_pd(x + i + 4), vm);
         const __m128i c0 = _mm256_cvtpd_epi32(t0);

@@ -24,6 +24,9 @@ void grm_pool_destroy(GrmHostPool *pool);
 int grm_pool_threads(const GrmHostPool *pool);
 // fn(arg, tid, nthreads) on every worker; returns when all have finished
 void grm_pool_run(GrmHostPool *pool, void (*fn)(void *, int, int), void *arg);
+// the same in two halves: start returns at once, wait blocks until every worker has returned from fn (one job at a time)
+void grm_pool_start(GrmHostPool *pool, void (*fn)(void *, int, int), void *arg);
+void grm_pool_wait(GrmHostPool *pool);
 
 // Columns [k0, k1) of the n x p matrix -> out[(k - k0) * ldo + i] = int8(m * x) or a sentinel.  sel may be null (plain
 // Matrix{Float64}: every cell is a Float64, NaN counts as missing).  Returns the OR of the flags raised.
@@ -40,5 +43,8 @@ uint32_t grm_host_copy(const double *payload, const uint8_t *sel, int float_tag,
 // ignore_missing != 0.  A cell that is not k/64 in [0, 1] raises GRM_HF_NOT_DOSAGE.
 void grm_host_detect(const double *payload, const uint8_t *sel, int float_tag, int64_t n, int64_t p, int64_t lda,
                      int64_t cells, int ignore_missing, uint32_t *bits, uint32_t *flags);
+// software prefetch distance of the quantiser, bytes (0 = off)
+void grm_host_set_prefetch(int bytes);
+int grm_host_get_prefetch(void);
 // name of the SIMD level the passes above dispatch to on this machine ("avx512", "avx2", "scalar")
 const char *grm_host_simd(void);

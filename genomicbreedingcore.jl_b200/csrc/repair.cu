@@ -5,6 +5,13 @@
 // of a running product, so it is reproduced literally: cuSOLVER Dgetrf/Dpotrf factorise on the device, the n pivots
 // come back to the host and are multiplied in pivot order in plain binary64 (gradual underflow, no log-domain
 // shortcut) — SURVEY.md A.4.  This step is O(n^3) FP64 library work and is reported separately from the GRM itself.
+//
+// Order of evaluation: the reference's tests are pure functions of the matrix — early return iff det > eps && isposdef
+// (calc.jl:49), another round iff det < eps || !isposdef (calc.jl:61) — so either factorisation may be skipped once the
+// other has decided.  The LU goes first, as in the reference: for a large GRM it is the determinant test that fails
+// (the product of n pivots under- or overflows: C3's matrix is numerically positive definite, its determinant
+// underflows to 0), and det < eps then makes the Cholesky unnecessary.  Measured at n = 20,000 on a B200
+// (scripts/potrf_probe.cu): Dgetrf 279 ms, Dpotrf 117 ms; Cholesky-first cost 817 ms per C3 repair against 689 ms.
 #include <cusolverDn.h>
 #include <float.h>
 #include <math.h>
@@ -93,7 +100,8 @@ struct Repair {
     cusolverDnHandle_t h;
     double *X;
     int64_t n, ldx;
-    double *work_mat;  // n x n copy that the factorisations destroy
+    double *work_chol;  // n x n copy the Cholesky destroys (ctx->lu: what grm_cuda_last_factor hands out)
+    double *work_lu;    // n x n copy the LU destroys (its own buffer, so the LU never clobbers a cached factor)
     double *lwork;
     int lwork_len;
     int *ipiv, *info;
@@ -102,26 +110,14 @@ struct Repair {
     double shift_eps0 = 0.0;
     std::vector<double> h_diag;
     std::vector<int> h_ipiv;
-    // 64-bit cuSOLVER API (GRM_CUDA_GETRF=x0|x1): same LAPACK-style partial-pivoting LU, int64 pivots, selectable
-    // algorithm; measured against the legacy Dgetrf in profiles/
-    int xalg = -1;  // -1 = legacy cusolverDnDgetrf
-    cusolverDnParams_t params = nullptr;
-    ~Repair() {
-        if (params) cusolverDnDestroyParams(params);
-    }
-    int64_t *ipiv64 = nullptr;
-    void *xwork_d = nullptr;
-    size_t xwork_d_bytes = 0, xwork_h_bytes = 0;
-    std::vector<char> xwork_h;
-    std::vector<int64_t> h_ipiv64;
 
-    int32_t copy_in() {
+    int32_t copy_in(double *dst) {
         const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
-        copy_matrix_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(X, n, ldx, work_mat);
+        copy_matrix_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(X, n, ldx, dst);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         if (shift_rounds > 0) {
-            diag_add_rounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(work_mat, n, n, shift_eps0,
+            diag_add_rounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(dst, n, n, shift_eps0,
                                                                                                 shift_rounds);
             GRM_CUDA_TRY(cudaGetLastError());
             ctx->launches++;
@@ -132,22 +128,15 @@ struct Repair {
     // Julia: det(X) = det(lu(X; check=false)): 0 if the factorisation hit an exact zero pivot, otherwise the
     // sequential product of diag(U) times (-1)^(number of row interchanges).
     int32_t det(double *out) {
-        GRM_TRY(copy_in());
-        if (xalg >= 0)
-            GRM_SOLVER_TRY(cusolverDnXgetrf(h, params, n, n, CUDA_R_64F, work_mat, n, ipiv64, CUDA_R_64F, xwork_d,
-                                            xwork_d_bytes, xwork_h.data(), xwork_h_bytes, info));
-        else
-            GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), work_mat, static_cast<int>(n),
-                                            lwork, ipiv, info));
-        diag_extract_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(work_mat, n, d_diag);
+        GRM_TRY(copy_in(work_lu));
+        GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), work_lu, static_cast<int>(n), lwork, ipiv,
+                                        info));
+        diag_extract_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(work_lu, n, d_diag);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches++;
         int h_info = 0;
         GRM_CUDA_TRY(cudaMemcpyAsync(h_diag.data(), d_diag, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (xalg >= 0)
-            GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv64.data(), ipiv64, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        else
-            GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (h_info < 0) {
@@ -162,8 +151,7 @@ struct Repair {
         int swaps = 0;
         for (int64_t i = 0; i < n; ++i) {
             P = P * h_diag[i];
-            const int64_t pv = xalg >= 0 ? h_ipiv64[i] : static_cast<int64_t>(h_ipiv[i]);
-            if (pv != i + 1) ++swaps;
+            if (static_cast<int64_t>(h_ipiv[i]) != i + 1) ++swaps;
         }
         *out = (swaps & 1) ? -P : P;
         return GRM_CUDA_OK;
@@ -171,9 +159,10 @@ struct Repair {
 
     // Julia: isposdef(X) = ishermitian(X) && LAPACK.potrf!('U', copy(X)) succeeded (symmetry already checked)
     int32_t posdef(bool *out) {
-        GRM_TRY(copy_in());
-        GRM_SOLVER_TRY(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), work_mat, static_cast<int>(n),
-                                        lwork, lwork_len, info));
+        ctx->factor_n = -1;
+        GRM_TRY(copy_in(work_chol));
+        GRM_SOLVER_TRY(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), work_chol, static_cast<int>(n), lwork,
+                                        lwork_len, info));
         int h_info = 0;
         GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -182,6 +171,15 @@ struct Repair {
             return GRM_CUDA_ERR_CUDA;
         }
         *out = (h_info == 0);
+        return GRM_CUDA_OK;
+    }
+
+    // one evaluation of the reference's pair of tests on the current matrix: dt = det(X); pd = isposdef(X) unless
+    // det < eps already decides (then pd = false: not evaluated, the outcome does not depend on it)
+    int32_t evaluate(bool *pd, double *dt) {
+        GRM_TRY(det(dt));
+        *pd = false;
+        if (!(*dt < DBL_EPSILON)) GRM_TRY(posdef(pd));
         return GRM_CUDA_OK;
     }
 };
@@ -228,11 +226,13 @@ static int32_t repair_setup(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx
     r.n = n;
     r.ldx = ldx;
     GRM_TRY(ctx->lu.reserve(static_cast<size_t>(n) * n * sizeof(double)));
-    r.work_mat = ctx->lu.as<double>();
+    GRM_TRY(ctx->lu2.reserve(static_cast<size_t>(n) * n * sizeof(double)));
+    r.work_chol = ctx->lu.as<double>();
+    r.work_lu = ctx->lu2.as<double>();
     int lw1 = 0, lw2 = 0;
-    GRM_SOLVER_TRY(cusolverDnDgetrf_bufferSize(h, static_cast<int>(n), static_cast<int>(n), r.work_mat,
+    GRM_SOLVER_TRY(cusolverDnDgetrf_bufferSize(h, static_cast<int>(n), static_cast<int>(n), r.work_chol,
                                                static_cast<int>(n), &lw1));
-    GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), r.work_mat,
+    GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), r.work_chol,
                                                static_cast<int>(n), &lw2));
     r.lwork_len = std::max(lw1, lw2);
     GRM_TRY(ctx->lu_work.reserve(std::max<size_t>(static_cast<size_t>(r.lwork_len), 1) * sizeof(double)));
@@ -245,19 +245,6 @@ static int32_t repair_setup(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx
     r.d_diag = reinterpret_cast<double *>(r.ipiv + int_slots);
     r.h_diag.resize(n);
     r.h_ipiv.resize(n);
-    if (r.xalg >= 0) {
-        GRM_SOLVER_TRY(cusolverDnCreateParams(&r.params));
-        GRM_SOLVER_TRY(cusolverDnSetAdvOptions(r.params, CUSOLVERDN_GETRF, r.xalg == 1 ? CUSOLVER_ALG_1 : CUSOLVER_ALG_0));
-        GRM_SOLVER_TRY(cusolverDnXgetrf_bufferSize(h, r.params, n, n, CUDA_R_64F, r.work_mat, n, CUDA_R_64F,
-                                                   &r.xwork_d_bytes, &r.xwork_h_bytes));
-        const size_t off = (r.xwork_d_bytes + 255) & ~size_t(255);
-        GRM_TRY(ctx->misc2.reserve(off + static_cast<size_t>(n) * sizeof(int64_t)));
-        r.xwork_d = ctx->misc2.ptr;
-        r.ipiv64 = reinterpret_cast<int64_t *>(static_cast<char *>(ctx->misc2.ptr) + off);
-        r.xwork_h.resize(r.xwork_h_bytes + 1);
-        r.h_ipiv64.resize(n);
-    }
-
     return GRM_CUDA_OK;
 }
 
@@ -275,16 +262,13 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
     }
 
     const double eps = DBL_EPSILON;
-    // calc.jl:49-51 — early return; isposdef is evaluated only if det > eps (&& short-circuit)
-    double det0 = 0.0;
-    GRM_TRY(r.det(&det0));
-    if (det0 > eps) {
-        bool pd = false;
-        GRM_TRY(r.posdef(&pd));
-        if (pd) {
-            ctx->factor_n = n;  // the work matrix now holds chol(X).U (grm_cuda_last_factor)
-            return GRM_CUDA_OK;
-        }
+    // calc.jl:49-51 — early return iff det(X) > eps && isposdef(X)
+    bool pd = false;
+    double det_cur = NAN;
+    GRM_TRY(r.evaluate(&pd, &det_cur));
+    if (pd && det_cur > eps) {
+        ctx->factor_n = n;  // ctx->lu holds chol(X).U (grm_cuda_last_factor)
+        return GRM_CUDA_OK;
     }
     // calc.jl:52-57
     if (h_scan[0] & 2ull) {
@@ -296,7 +280,7 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
         return GRM_CUDA_ERR_INF_MATRIX;
     }
     // calc.jl:58-66.  The first evaluation of the loop condition looks at the SAME matrix as the early test, so its
-    // det is reused (same input, same factorisation, same value).
+    // results are reused (same input, same factorisations, same values).
     double e = 0.0;
     {
         const long long bits = static_cast<long long>(h_scan[1]);
@@ -304,15 +288,10 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
     }
     double total = 0.0;
     int iter = 0;
-    double det_cur = det0;
     for (;;) {
-        bool need = det_cur < eps;  // NaN compares false, negative compares true (calc.jl:61)
-        if (!need) {
-            bool pd = false;
-            GRM_TRY(r.posdef(&pd));
-            need = !pd;
-            if (pd) ctx->factor_n = n;  // last factorisation = Cholesky of the matrix being returned
-        }
+        // calc.jl:61: det < eps || !isposdef  (a NaN det compares false, then isposdef decides)
+        const bool need = det_cur < eps || !pd;
+        if (!need) ctx->factor_n = n;  // the last factorisation into ctx->lu is the Cholesky of the matrix being returned
         if (!need || iter >= max_iter) break;
         ++iter;
         diag_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(X, n, ldx, e);
@@ -320,7 +299,7 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
         ctx->launches++;
         total += e;
         e *= (1.0 + eps);
-        GRM_TRY(r.det(&det_cur));
+        GRM_TRY(r.evaluate(&pd, &det_cur));
     }
     *iters = iter;
     *eps_total = total;
@@ -355,12 +334,9 @@ extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, in
     if (h_scan[0] & 1ull) return GRM_CUDA_OK;  // not symmetric: the caller raises before any factorisation (calc.jl:43)
     r.shift_rounds = rounds;
     r.shift_eps0 = mx;
-    GRM_TRY(r.det(det_out));
-    if (!(*det_out < DBL_EPSILON)) {  // the reference evaluates isposdef only when det passes (&& / || short-circuit)
-        bool pd = false;
-        GRM_TRY(r.posdef(&pd));
-        *posdef_out = pd ? 1 : 0;
-    }
+    bool pd = false;
+    GRM_TRY(r.evaluate(&pd, det_out));
+    *posdef_out = (*det_out < DBL_EPSILON) ? -1 : (pd ? 1 : 0);  // -1: not evaluated, det < eps already decides
     return GRM_CUDA_OK;
 }
 

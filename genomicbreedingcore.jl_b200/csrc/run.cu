@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <chrono>
 #include <thread>
 
@@ -97,30 +98,54 @@ bool is_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-struct IngestJob {
-    const Source *src;
-    int64_t n, k0, k1, ldo;
-    int m, mode;  // mode: 0 quantise FP64 -> int8, 1 copy pre-packed codes, 2 copy FP64
-    void *out;
+// ---------------------------------------------------------------------------------------------------------------
+// The host half of the ingest as ONE continuous job for the whole pass: the loci are cut into ring chunks and every
+// chunk into small units (a few loci, ~1.5 MB of source); the workers pull units from a global counter in chunk order,
+// so there is no barrier between chunks and a slow core simply takes fewer units.  A worker may only write into the
+// ring slot of chunk c once the copy of chunk c - RING out of that slot has finished (`writable`, advanced by the thread
+// that drives the GPU); the workers therefore run up to RING - 1 chunks ahead of the device.
+// ---------------------------------------------------------------------------------------------------------------
+struct StreamJob {
+    const Source *src = nullptr;
+    int64_t n = 0, pc = 0, chunk = 0, nchunks = 0, ldo = 0, grain = 1, total_units = 0;
+    int m = 0, mode = 0;  // mode: 0 quantise FP64 -> int8, 1 copy pre-packed codes, 2 copy FP64
+    size_t elt = 1;
+    void *pin[RING] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<int64_t> unit_base;  // first unit of chunk c; unit_base[nchunks] = total
+    std::atomic<int64_t> next{0};
+    std::unique_ptr<std::atomic<int32_t>[]> done;  // units finished per chunk
+    std::atomic<int64_t> writable{RING};
     std::atomic<uint32_t> flags{0};
+    std::atomic<int> abort{0};
+
+    int64_t chunk_len(int64_t c) const { return std::min(chunk, pc - c * chunk); }
+    int32_t units_of(int64_t c) const { return static_cast<int32_t>(unit_base[c + 1] - unit_base[c]); }
 };
 
-void ingest_job(void *arg, int tid, int nt) {
-    IngestJob *j = static_cast<IngestJob *>(arg);
-    const int64_t len = j->k1 - j->k0;
-    const int64_t a = j->k0 + len * tid / nt, b = j->k0 + len * (tid + 1) / nt;
-    if (a >= b) return;
+void stream_worker(void *arg, int, int) {
+    StreamJob *j = static_cast<StreamJob *>(arg);
     const Source &s = *j->src;
-    uint32_t f = 0;
-    if (j->mode == 0)
-        f = grm_host_quantise(s.A, s.sel, s.float_tag, j->n, s.lda, a, b, j->m, static_cast<int8_t *>(j->out) + (a - j->k0) * j->ldo,
-                              j->ldo);
-    else if (j->mode == 1)
-        f = grm_host_copy_codes(s.codes, j->n, s.lda, a, b, j->m, static_cast<int8_t *>(j->out) + (a - j->k0) * j->ldo, j->ldo);
-    else
-        f = grm_host_copy(s.A, s.sel, s.float_tag, j->n, s.lda, a, b, static_cast<double *>(j->out) + (a - j->k0) * j->ldo,
-                          j->ldo);
-    if (f) j->flags.fetch_or(f);
+    for (;;) {
+        const int64_t u = j->next.fetch_add(1, std::memory_order_relaxed);
+        if (u >= j->total_units || j->abort.load(std::memory_order_relaxed)) return;
+        const int64_t c = std::upper_bound(j->unit_base.begin(), j->unit_base.end(), u) - j->unit_base.begin() - 1;
+        while (c >= j->writable.load(std::memory_order_acquire)) {
+            if (j->abort.load(std::memory_order_relaxed)) return;
+            std::this_thread::yield();
+        }
+        const int64_t c0 = c * j->chunk;
+        const int64_t a = c0 + (u - j->unit_base[c]) * j->grain, b = std::min(a + j->grain, c0 + j->chunk_len(c));
+        char *out = static_cast<char *>(j->pin[c % RING]) + static_cast<size_t>(a - c0) * j->ldo * j->elt;
+        uint32_t f;
+        if (j->mode == 0)
+            f = grm_host_quantise(s.A, s.sel, s.float_tag, j->n, s.lda, a, b, j->m, reinterpret_cast<int8_t *>(out), j->ldo);
+        else if (j->mode == 1)
+            f = grm_host_copy_codes(s.codes, j->n, s.lda, a, b, j->m, reinterpret_cast<int8_t *>(out), j->ldo);
+        else
+            f = grm_host_copy(s.A, s.sel, s.float_tag, j->n, s.lda, a, b, reinterpret_cast<double *>(out), j->ldo);
+        if (f) j->flags.fetch_or(f, std::memory_order_relaxed);
+        j->done[c].fetch_add(1, std::memory_order_release);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -129,8 +154,7 @@ void ingest_job(void *arg, int tid, int nt) {
 //   DIRECT   pinned host FP64 without selectors: asynchronous copies straight from the caller's memory
 //   RING_F64 host FP64 (pageable and / or Union layout): worker threads copy into the pinned ring (missing -> NaN)
 //   RING_I8  host dosages: worker threads quantise (or copy pre-packed codes) into the pinned ring, 1 byte per cell
-// The ring has RING slots (pinned host + device staging); the host only ever blocks on "the copy out of the pinned slot
-// I am about to refill has finished", everything else is stream-ordered.
+// The ring has RING slots (pinned host + device staging); chunks must be fetched in order.
 // ---------------------------------------------------------------------------------------------------------------
 struct Feeder {
     enum Kind { DEVICE, DIRECT, RING_F64, RING_I8 };
@@ -141,10 +165,13 @@ struct Feeder {
     int m = 0;
     size_t elt = 8;
     bool used[RING] = {false, false, false, false};
-    uint64_t seq = 0;
     int cur = 0;
     float host_ms = 0.f;
     uint32_t host_flags = 0;
+    StreamJob job;
+    bool running = false;
+    int64_t fetched = 0;  // chunks handed to the device so far
+    Timer t_job;
 
     int32_t init(grm_cuda_ctx *c, const Source *s, Kind k, int64_t n_, int64_t pc_, int m_, int64_t want_chunk, int world) {
         ctx = c;
@@ -172,22 +199,45 @@ struct Feeder {
         const size_t slot = static_cast<size_t>(ld) * static_cast<size_t>(std::min(chunk, std::max<int64_t>(pc, 1))) * elt;
         const int slots = static_cast<int>(std::min<int64_t>(RING, std::max<int64_t>(nchunks, 1)));
         for (int i = 0; i < slots; ++i) GRM_TRY(ctx->stage[i].reserve(slot));
-        if (kind != DIRECT) {
-            GRM_TRY(ensure_pool(ctx, world));
-            GRM_TRY(ensure_ring(ctx, slot));
-        }
+        if (kind == DIRECT || nchunks == 0) return GRM_CUDA_OK;
+        GRM_TRY(ensure_pool(ctx, world));
+        GRM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // nothing of an earlier pass may still read the ring
+        GRM_TRY(ensure_ring(ctx, slot));
+        // the whole pass as one job
+        job.src = src;
+        job.n = n;
+        job.pc = pc;
+        job.chunk = chunk;
+        job.nchunks = nchunks;
+        job.ldo = ld;
+        job.m = m;
+        job.mode = kind == RING_F64 ? 2 : (src->codes ? 1 : 0);
+        job.elt = elt;
+        for (int i = 0; i < RING; ++i) job.pin[i] = ctx->pin[i];
+        const int64_t src_per_locus = n * (job.mode == 1 ? 1 : 9);
+        job.grain = std::max<int64_t>(1, std::min<int64_t>(chunk, (3ll << 19) / std::max<int64_t>(src_per_locus, 1)));
+        job.unit_base.assign(nchunks + 1, 0);
+        for (int64_t cc = 0; cc < nchunks; ++cc)
+            job.unit_base[cc + 1] = job.unit_base[cc] + (job.chunk_len(cc) + job.grain - 1) / job.grain;
+        job.total_units = job.unit_base[nchunks];
+        job.done.reset(new std::atomic<int32_t>[nchunks]);
+        for (int64_t cc = 0; cc < nchunks; ++cc) job.done[cc].store(0, std::memory_order_relaxed);
+        job.writable.store(RING, std::memory_order_relaxed);
+        t_job = Timer();
+        grm_pool_start(ctx->pool, stream_worker, &job);
+        running = true;
         return GRM_CUDA_OK;
     }
     int64_t k0(int64_t c) const { return c * chunk; }
     int64_t len(int64_t c) const { return std::min(chunk, pc - c * chunk); }
 
-    // device pointer of chunk c, valid on the compute stream
+    // device pointer of chunk c, valid on the compute stream (chunks in order)
     int32_t get(int64_t c, const void **d) {
         if (kind == DEVICE) {
             *d = src->A;
             return GRM_CUDA_OK;
         }
-        const int s = static_cast<int>(seq % RING);
+        const int s = static_cast<int>(c % RING);
         const int64_t a = k0(c), l = len(c);
         void *dst = ctx->stage[s].ptr;
         if (kind == DIRECT) {
@@ -196,20 +246,17 @@ struct Feeder {
                                            n * sizeof(double), static_cast<size_t>(l), cudaMemcpyHostToDevice,
                                            ctx->copy_stream));
         } else {
-            if (used[s]) GRM_CUDA_TRY(cudaEventSynchronize(ctx->copy_done[s]));  // the pinned slot has left the host
-            IngestJob job;
-            job.src = src;
-            job.n = n;
-            job.k0 = a;
-            job.k1 = a + l;
-            job.ldo = ld;
-            job.m = m;
-            job.mode = kind == RING_F64 ? 2 : (src->codes ? 1 : 0);
-            job.out = ctx->pin[s];
-            Timer t;
-            grm_pool_run(ctx->pool, ingest_job, &job);
-            host_ms += t.ms();
-            host_flags |= job.flags.load();
+            if (c >= 1) {
+                // the copy of chunk c - 1 has left its pinned slot: chunk c - 1 + RING may be written
+                GRM_CUDA_TRY(cudaEventSynchronize(ctx->copy_done[(c - 1) % RING]));
+                job.writable.store(c + RING, std::memory_order_release);
+            }
+            const int32_t want = job.units_of(c);
+            for (unsigned spins = 0; job.done[c].load(std::memory_order_acquire) < want; ++spins) {
+                if (spins < 64) std::this_thread::yield();
+                else std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+            host_flags |= job.flags.load(std::memory_order_relaxed);
             if (used[s]) GRM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[s], 0));
             GRM_CUDA_TRY(cudaMemcpyAsync(dst, ctx->pin[s], static_cast<size_t>(l) * ld * elt, cudaMemcpyHostToDevice,
                                          ctx->copy_stream));
@@ -218,7 +265,7 @@ struct Feeder {
         GRM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[s], 0));
         used[s] = true;
         cur = s;
-        ++seq;
+        fetched = c + 1;
         *d = dst;
         return GRM_CUDA_OK;
     }
@@ -227,6 +274,18 @@ struct Feeder {
         GRM_CUDA_TRY(cudaEventRecord(ctx->stage_free[cur], ctx->stream));
         return GRM_CUDA_OK;
     }
+    // end of the pass (also an early end): stop the workers and collect their flags
+    void finish() {
+        if (!running) return;
+        // every fetched chunk was complete; after an early end a worker may still wait for a ring slot that will never be
+        // released, so the decision is taken on the chunks, not on the unit counter
+        if (fetched < nchunks) job.abort.store(1);
+        grm_pool_wait(ctx->pool);
+        running = false;
+        host_ms += t_job.ms();
+        host_flags |= job.flags.load();
+    }
+    ~Feeder() { finish(); }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -504,6 +563,7 @@ int32_t Run::int8_path(int32_t m, double *dG, int64_t ldG, double **d_tiles_out,
         // a cell that breaks the guessed denominator ends the pass early (the whole pass is repeated anyway)
         if (feed.host_flags & (F_NOT_DOSAGE | F_INF | F_NAN_PAYLOAD)) break;
     }
+    feed.finish();
     inf.ms_host_busy += feed.host_ms;
     if (masked && pc > 0) {
         // a KEPT locus that still holds missing cells always raises the flag: under the "error" policy that is the
@@ -699,6 +759,7 @@ int32_t Run::f64_path(double *dG, int64_t ldG, double **d_tiles_out, int64_t *p_
         }
         GRM_TRY(feed.done());
     }
+    feed.finish();
     inf.ms_host_busy += feed.host_ms;
     GRM_CUDA_TRY(cudaEventRecord(ev[1], st));
     GRM_CUDA_TRY(cudaEventRecord(ev[2], st));
@@ -1207,6 +1268,15 @@ extern "C" int32_t grm_cuda_host_detect(const double *payload, const uint8_t *se
 }
 
 extern "C" const char *grm_cuda_host_simd(void) { return grm_host_simd(); }
+
+extern "C" int32_t grm_cuda_host_tune(const char *key, int64_t value) {
+    if (key && !strcmp(key, "prefetch")) {
+        grm_host_set_prefetch(static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20))));
+        return GRM_CUDA_OK;
+    }
+    grm_set_error("host_tune: unknown key (%s)", key ? key : "null");
+    return GRM_CUDA_ERR_BAD_ARGUMENT;
+}
 
 extern "C" int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
                                               int32_t location, int32_t *iters, double *eps_total) {

@@ -226,6 +226,8 @@ int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *selectors, 
 int32_t grm_cuda_host_detect(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
                              int64_t lda, int64_t max_cells, int32_t ignore_missing, int32_t *m_out);
 const char *grm_cuda_host_simd(void);
+/* Process-wide knobs of the host quantiser: "prefetch" = software prefetch distance in bytes (0 = off, default 8192). */
+int32_t grm_cuda_host_tune(const char *key, int64_t value);
 
 /* inflatediagonals!, calc.jl:41-70.  `location` says where X lives (GRM_CUDA_LOC_*). */
 int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
