@@ -244,7 +244,8 @@ def run_b200(args, wl):
     m = ploidy if kind == "dosage" else 0  # generator emits c/ploidy; ploidy 2 and 4 are power-of-two denominators
     centred = wl["fn"] == "grmploidyaware"
     pl = ploidy if centred else None
-    tiles_out = bool(wl.get("tiles")) or world > 1
+    e2e_tiles = bool(wl.get("tiles"))         # C5: the GRM never exists as one dense matrix, not even end to end
+    tiles_out = e2e_tiles or world > 1        # device step at N > 1: the finished tiles stay sharded on their owners
     missing = wl.get("missing", "error")
     k0, k1 = GD.loci_range(p, rank, world)
     pc = k1 - k0
@@ -411,16 +412,16 @@ def run_b200(args, wl):
                 blk[miss] = 0.25
         del A_dev
         torch.cuda.empty_cache()
-        if tiles_out:
+        if e2e_tiles:
             G_host = np.empty((max(int(tiles_rank), 1), 256, 256), dtype=np.float64)
         else:
             G_host = np.empty((n, n), dtype=np.float64, order="F") if rank == 0 else None  # pageable, like Julia's Matrix{Float64}
         o = _lib.default_options()
         o.path = _lib.PATH_AUTO  # the dosage denominator is detected on load, as the Julia shim does
         o.missing_policy = _lib.MISSING_MEANFILL if missing == "meanfill" else _lib.MISSING_ERROR
-        if world > 1 or tiles_out:
+        if world > 1 or e2e_tiles:
             o.distributed, o.input_slab = 1, 1
-        if tiles_out:
+        if e2e_tiles:
             o.output_mode, o.skip_repair = _lib.OUT_TILES, 1
         info = _lib.new_info()
         g_ptr = G_host.ctypes.data if G_host is not None else None
@@ -448,7 +449,7 @@ def run_b200(args, wl):
         dt = allmax((time.perf_counter() - t0) / esteps)
         launches_e2e = info.kernel_launches
         detail = {k: allmax(v / esteps) for k, v in acc.items()}  # max over ranks of the per-rank mean
-        if tiles_out:
+        if e2e_tiles:
             d2h = 8 * 65536 * int(tiles_rank)
         else:
             d2h = 8 * n * n if rank == 0 else 0
@@ -466,8 +467,19 @@ def run_b200(args, wl):
                    " + int64 all-reduce" if world > 1 else "", " over own loci in waves + int32 reduce-scatter (NCCL inside the library) + "
                    "all-gather of the finished tiles" if world > 1 else "", "rounds probed in parallel, one per rank" if world > 1 else
                    "cuSOLVER LU/Cholesky", " on rank 0" if world > 1 else "")}
-        if verified is not None and G_host is not None and not tiles_out and world == 1:
+        if verified is not None and G_host is not None and not e2e_tiles and world == 1:
             verified.update(verify_e2e(G_host, out_dev, info, n))
+        if verified is not None and G_host is not None and not e2e_tiles and world > 1:
+            # rank 0's gathered, repaired matrix against the exactly recomputed rows: off the diagonal the raw GRM, on it + eps_total
+            rws, ref = verified["_rows"], verified["_ref"].copy()
+            ref[np.arange(len(rws)), rws] += info.eps_total
+            got = G_host[rws]  # symmetric: row i
+            verified["e2e_rows_max_rel_err"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+            verified["e2e_rows_ok"] = bool(verified["e2e_rows_max_rel_err"] <= 1e-12)
+            verified["e2e_symmetric"] = bool(np.array_equal(G_host, G_host.T))
+    if verified is not None:
+        verified.pop("_rows", None)
+        verified.pop("_ref", None)
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------------------
     cpu = None
@@ -723,6 +735,7 @@ def verify_int8(ctx, A_dev, out_dev, info, n, p, pc, k0, m, pl, rank, world, til
     res["rows_ok"] = bool(err <= 1e-12)  # north_star: final GRM within 1e-12 relative on the int8 path
     res["what"] = ("output of the timed device step vs an exact recomputation from the integer codes (torch FP64 matmul, "
                    "reference formula calc.jl:197-209) on %d random rows; integer identities of the Gram matrix" % nrows)
+    res["_rows"], res["_ref"] = rows.cpu().numpy(), ref.cpu().numpy()  # kept for the end-to-end check, dropped from the line
     del codes, colsum, part
     torch.cuda.empty_cache()
     return res

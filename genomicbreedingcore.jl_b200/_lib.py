@@ -105,6 +105,7 @@ SIGNATURES = {
     "grm_cuda_ctx_synchronize": (_i32, [_vp]),
     "grm_cuda_ctx_set_tuning": (_i32, [_vp, C.c_char_p, _i64]),
     "grm_cuda_ctx_get_tuning": (_i32, [_vp, C.c_char_p, C.POINTER(_i64)]),
+    "grm_cuda_comm_set_library": (_i32, [C.c_char_p]),
     "grm_cuda_comm_unique_id": (_i32, [_vp]),
     "grm_cuda_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
     "grm_cuda_comm_destroy": (_i32, [_vp]),
@@ -231,6 +232,7 @@ class Context:
 
     # ---- communicator (one process per GPU; NCCL lives inside the library) --------------------------------------
     def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        _name_nccl()
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(self.lib.grm_cuda_comm_init(self.handle, buf, int(rank), int(world)))
 
@@ -254,8 +256,32 @@ class Context:
             pass
 
 
+_nccl_named = False
+
+
+def _name_nccl() -> None:
+    """Point the library at the NCCL that PyTorch links against (the nvidia-nccl wheel) BEFORE it loads any: the loader
+    hands out whichever libnccl.so.2 came first, and a later `import torch` must not be given the older system copy."""
+    global _nccl_named
+    if _nccl_named:
+        return
+    _nccl_named = True
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                load().grm_cuda_comm_set_library(path.encode())  # refused (harmless) if an NCCL is already loaded
+                return
+    except Exception:
+        pass
+
+
 def comm_unique_id() -> bytes:
     """128 opaque bytes created on ONE rank; hand them to the others and call Context.comm_init on every rank."""
+    _name_nccl()
     buf = (C.c_uint8 * 128)()
     check(load().grm_cuda_comm_unique_id(buf))
     return bytes(buf)

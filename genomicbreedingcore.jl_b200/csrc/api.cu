@@ -11,6 +11,7 @@
 #include "ingest_host.h"
 
 int32_t grm_comm_destroy(grm_cuda_ctx *ctx);  // comm.cu
+int32_t grm_comm_abort(grm_cuda_ctx *ctx);
 
 // ---------------------------------------------------------------------------------------------------------------
 // errors
@@ -143,6 +144,7 @@ int32_t grm_cusolver_destroy(void *h);
 extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     if (!ctx) return GRM_CUDA_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->comm) grm_comm_abort(ctx);  // never wait for collectives the peers may not enter any more
     cudaDeviceSynchronize();
     if (ctx->comm) grm_comm_destroy(ctx);
     if (ctx->cusolver) grm_cusolver_destroy(ctx->cusolver);
@@ -203,6 +205,7 @@ static int *tuning_slot(GrmTuning &t, const char *key) {
         {"tile_band", &GrmTuning::tile_band},       {"host_threads", &GrmTuning::host_threads},
         {"ingest", &GrmTuning::ingest},             {"ksplit_waves", &GrmTuning::ksplit_waves},
         {"f64_kernel", &GrmTuning::f64_kernel},     {"ring_mb", &GrmTuning::ring_mb},
+        {"comm_ctas", &GrmTuning::comm_ctas},       {"exchange", &GrmTuning::exchange},
     };
     for (const Entry &e : table)
         if (!strcmp(e.name, key)) return &(t.*(e.field));

@@ -7,11 +7,22 @@
 // torch.distributed, a file); afterwards grm_cuda_simple / grm_cuda_ploidyaware with opts.distributed = 1 run the
 // whole loci-split pipeline (run.cu).
 //
-// NCCL is loaded with dlopen on first use, so single-GPU users need no NCCL at all and, inside a process that already
-// carries an NCCL (PyTorch), that same copy is used (dlopen by soname returns the loaded object).
+// NCCL is loaded with dlopen on first use, so single-GPU users need no NCCL at all.  Which copy: the one the host named
+// (grm_cuda_comm_set_library), else one that is ALREADY in the process (RTLD_NOLOAD — PyTorch brings its own), else the
+// system's libnccl.so.2.  The order matters in someone else's process: the dynamic loader matches DT_NEEDED entries by
+// soname, so an older system NCCL loaded here first would later be handed to a PyTorch that needs a newer one
+// ("undefined symbol ncclDevCommCreate").  Hosts that load another NCCL afterwards should therefore name it up front;
+// the Python wrapper does (the nvidia-nccl wheel PyTorch links against).
+//
+// Exchange of bulk data that only has to MOVE (the partial tiles of the K-split) does not go through NCCL kernels: they
+// need SMs, which the persistent SYRK owns.  It goes through the copy engines into peer-mapped receive buffers
+// (grm_comm_peer_buffer: cudaMalloc + CUDA IPC handles, exchanged once through the communicator).
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,7 +30,9 @@ struct GrmNccl {
     void *handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;  // optional
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;  // optional
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -27,17 +40,36 @@ struct GrmNccl {
     ncclResult_t (*GetVersion)(int *) = nullptr;
 };
 
+constexpr int GRM_MAX_WORLD = 64;
+
 struct GrmComm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // copy-engine exchange
+    void *recv = nullptr;  // own peer-visible buffer (cudaMalloc)
+    size_t recv_bytes = 0;
+    void *peers[GRM_MAX_WORLD] = {};  // peers[q] = rank q's buffer as mapped in this process
+    uint32_t epoch = 0;
+    cudaStream_t xs[GRM_XSTREAMS] = {};
+    cudaEvent_t xe[GRM_XSTREAMS + 1] = {};
 };
 
 static GrmNccl g_nccl;
+static char g_nccl_path[1024] = "";
 
 static int32_t nccl_load() {
     if (g_nccl.handle) return GRM_CUDA_OK;
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    void *h = nullptr;
+    if (g_nccl_path[0]) {
+        h = dlopen(g_nccl_path, RTLD_NOW | RTLD_LOCAL);
+        if (!h) {
+            grm_set_error("dlopen(%s) failed: %s", g_nccl_path, dlerror());
+            return GRM_CUDA_ERR_COMM;
+        }
+    }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);  // the host process already has one
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) {
         grm_set_error("multi-GPU support needs NCCL: dlopen(libnccl.so.2) failed: %s", dlerror());
         return GRM_CUDA_ERR_COMM;
@@ -61,6 +93,8 @@ static int32_t nccl_load() {
     GRM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
     GRM_NCCL_SYM(GetVersion, "ncclGetVersion");
 #undef GRM_NCCL_SYM
+    *reinterpret_cast<void **>(&t.CommInitRankConfig) = dlsym(h, "ncclCommInitRankConfig");
+    *reinterpret_cast<void **>(&t.CommAbort) = dlsym(h, "ncclCommAbort");
     g_nccl = t;
     return GRM_CUDA_OK;
 }
@@ -73,6 +107,19 @@ static int32_t nccl_load() {
             return GRM_CUDA_ERR_COMM;                                                                       \
         }                                                                                                   \
     } while (0)
+
+extern "C" int32_t grm_cuda_comm_set_library(const char *path) {
+    if (g_nccl.handle) {
+        grm_set_error("comm_set_library: NCCL is already loaded");
+        return GRM_CUDA_ERR_COMM;
+    }
+    if (!path || strlen(path) >= sizeof(g_nccl_path)) {
+        grm_set_error("comm_set_library: bad path");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    strcpy(g_nccl_path, path);
+    return GRM_CUDA_OK;
+}
 
 extern "C" int32_t grm_cuda_comm_unique_id(uint8_t *id128) {
     static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
@@ -87,8 +134,32 @@ extern "C" int32_t grm_cuda_comm_unique_id(uint8_t *id128) {
     return GRM_CUDA_OK;
 }
 
+static void peer_release(GrmComm *c) {
+    for (int q = 0; q < c->world; ++q)
+        if (c->peers[q] && q != c->rank) cudaIpcCloseMemHandle(c->peers[q]);
+    for (auto &pp : c->peers) pp = nullptr;
+    if (c->recv) cudaFree(c->recv);
+    c->recv = nullptr;
+    c->recv_bytes = 0;
+}
+
+// Context teardown without a prior grm_cuda_comm_destroy (an error path, an interpreter exiting after an exception): the
+// peers may never enter the collectives this rank still has in flight, so they are aborted rather than waited for.
+int32_t grm_comm_abort(grm_cuda_ctx *ctx) {
+    if (ctx && ctx->comm && ctx->comm->comm && g_nccl.CommAbort) {
+        g_nccl.CommAbort(ctx->comm->comm);
+        ctx->comm->comm = nullptr;
+    }
+    return GRM_CUDA_OK;
+}
+
 int32_t grm_comm_destroy(grm_cuda_ctx *ctx) {
     if (ctx && ctx->comm) {
+        peer_release(ctx->comm);
+        for (auto &x : ctx->comm->xs)
+            if (x) cudaStreamDestroy(x);
+        for (auto &e : ctx->comm->xe)
+            if (e) cudaEventDestroy(e);
         if (ctx->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->comm);
         delete ctx->comm;
         ctx->comm = nullptr;
@@ -108,7 +179,23 @@ extern "C" int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, i
     if (!c) return GRM_CUDA_ERR_OOM;
     ncclUniqueId id;
     memcpy(&id, id128, 128);
-    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    // tuning key "comm_ctas" (> 0, set before this call) caps NCCL's CTAs — for hosts that run the library next to
+    // their own kernels.  Off by default: measured on C3 / 8 GPUs, 8 CTAs move ~80 GB/s (profiles/README.md).
+    ncclResult_t r;
+    const int ctas = ctx->tune.comm_ctas;
+    if (world > GRM_MAX_WORLD) {
+        grm_set_error("comm_init: world %d exceeds %d", world, GRM_MAX_WORLD);
+        delete c;
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    if (ctas > 0 && g_nccl.CommInitRankConfig) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.maxCTAs = ctas;
+        cfg.minCTAs = std::min(ctas, 4);
+        r = g_nccl.CommInitRankConfig(&c->comm, world, id, rank, &cfg);
+    } else {
+        r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    }
     if (r != ncclSuccess) {
         grm_set_error("ncclCommInitRank(rank %d of %d) failed: %s", rank, world, g_nccl.GetErrorString(r));
         delete c;
@@ -117,8 +204,65 @@ extern "C" int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, i
     c->rank = rank;
     c->world = world;
     ctx->comm = c;
+    int prio_least = 0, prio_greatest = 0;
+    GRM_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    for (auto &x : c->xs) GRM_CUDA_TRY(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, prio_greatest));
+    for (auto &e : c->xe) GRM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return GRM_CUDA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// peer-mapped receive buffer
+// ---------------------------------------------------------------------------------------------------------------
+int32_t grm_comm_peer_buffer(grm_cuda_ctx *ctx, size_t bytes, void ***peers) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    GrmComm *c = ctx->comm;
+    if (!c) {
+        grm_set_error("no communicator on this context (grm_cuda_comm_init)");
+        return GRM_CUDA_ERR_COMM;
+    }
+    if (c->recv && c->recv_bytes >= bytes) {
+        *peers = c->peers;
+        return GRM_CUDA_OK;
+    }
+    // (re)allocation: every rank gets here in the same call (same n, same world), so this is a collective
+    GRM_CUDA_TRY(cudaDeviceSynchronize());
+    peer_release(c);
+    GRM_CUDA_TRY(cudaMalloc(&c->recv, bytes));
+    GRM_CUDA_TRY(cudaMemset(c->recv, 0, GRM_PEER_HEADER));  // flag words start below every epoch
+    c->recv_bytes = bytes;
+    cudaIpcMemHandle_t mine;
+    GRM_CUDA_TRY(cudaIpcGetMemHandle(&mine, c->recv));
+    GRM_TRY(ctx->cons.reserve(8192 + 64 * static_cast<size_t>(c->world + 1)));
+    uint8_t *d = ctx->cons.as<uint8_t>() + 8192;
+    GRM_CUDA_TRY(cudaMemcpyAsync(d, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    GRM_TRY(grm_comm_allgather(ctx, d, d + 64, 64, GRM_DT_U8, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    GRM_CUDA_TRY(cudaMemcpyAsync(all.data(), d + 64, 64 * static_cast<size_t>(c->world), cudaMemcpyDeviceToHost, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < c->world; ++q) {
+        if (q == c->rank) {
+            c->peers[q] = c->recv;
+            continue;
+        }
+        const cudaError_t e = cudaIpcOpenMemHandle(&c->peers[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            grm_set_error("cudaIpcOpenMemHandle(rank %d's receive buffer) failed: %s", q, cudaGetErrorString(e));
+            c->peers[q] = nullptr;
+            return GRM_CUDA_ERR_COMM;
+        }
+    }
+    // nobody may start storing into a buffer whose owner has not finished setting it up
+    GRM_TRY(grm_comm_allreduce(ctx, d, d, 1, GRM_DT_U8, 1, ctx->stream));
+    GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *peers = c->peers;
+    return GRM_CUDA_OK;
+}
+
+uint32_t grm_comm_next_epoch(grm_cuda_ctx *ctx) { return ++ctx->comm->epoch; }
+cudaStream_t grm_comm_xstream(grm_cuda_ctx *ctx, int i) { return ctx->comm->xs[i % GRM_XSTREAMS]; }
+cudaEvent_t grm_comm_xevent(grm_cuda_ctx *ctx, int i) { return ctx->comm->xe[i % (GRM_XSTREAMS + 1)]; }
 
 extern "C" int32_t grm_cuda_comm_destroy(grm_cuda_ctx *ctx) {
     if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;

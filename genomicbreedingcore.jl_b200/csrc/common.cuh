@@ -59,7 +59,9 @@ struct GrmTuning {
     int tile_band = 0;      // band height (tile rows) of the tile enumeration; 0 = default
     int host_threads = 0;   // host ingest threads; 0 = automatic
     int ingest = 0;         // host input: 0 auto, 1 stream FP64 and pack on the device, 2 quantise on the host
-    int ksplit_waves = 0;   // K-split exchange waves (reduce-scatter of wave w under the SYRK of wave w+1); 0 = auto
+    int ksplit_waves = 0;   // K-split exchange waves (reduce-scatter of wave w under the SYRK of the later waves); 0 = auto
+    int comm_ctas = 0;      // > 0: cap NCCL's CTAs (and leave as many SMs free during the K-split SYRK when NCCL carries it)
+    int exchange = 0;       // K-split partial tiles: 0 auto = NCCL reduce-scatter, 2 = copy engines into peer-mapped buffers
     int f64_kernel = 0;     // FP64 SYRK operand staging: 0 auto (TMA when aligned), 1 register-staged
     int ring_mb = 0;        // bytes (MiB) of one pinned ingest slot; 0 = automatic
 };
@@ -129,6 +131,15 @@ int32_t grm_comm_allreduce(grm_cuda_ctx *ctx, const void *send, void *recv, size
 int32_t grm_comm_reduce_scatter(grm_cuda_ctx *ctx, const void *send, void *recv, size_t recvcount, int dtype,
                                 cudaStream_t s);
 int32_t grm_comm_allgather(grm_cuda_ctx *ctx, const void *send, void *recv, size_t sendcount, int dtype, cudaStream_t s);
+// Peer-mapped receive buffer of the copy-engine exchange: every rank owns `bytes` (grow-only; COLLECTIVE when it has to
+// grow: handles travel through the communicator) that all peers can address.  peers[q] = rank q's buffer as mapped here
+// (peers[rank] = the own one).  The first GRM_PEER_HEADER bytes are flag words, the data follows.
+constexpr size_t GRM_PEER_HEADER = 65536;
+constexpr int GRM_XSTREAMS = 4;
+int32_t grm_comm_peer_buffer(grm_cuda_ctx *ctx, size_t bytes, void ***peers);
+uint32_t grm_comm_next_epoch(grm_cuda_ctx *ctx);
+cudaStream_t grm_comm_xstream(grm_cuda_ctx *ctx, int i);
+cudaEvent_t grm_comm_xevent(grm_cuda_ctx *ctx, int i);
 
 // tile-layout helpers of the distributed paths (tiles.cu)
 int32_t grm_packed_plan(grm_cuda_ctx *ctx, int64_t n, int32_t world, int32_t waves, PackedPlanCache **out);
@@ -149,6 +160,15 @@ int32_t grm_scatter_tiles(grm_cuda_ctx *ctx, const double *d_tiles, int64_t n, i
 void grm_packed_wave_range(int64_t n, int32_t world, int32_t waves, int32_t w, int64_t *s0, int64_t *s1);
 int32_t grm_syrk_i8_packed_wave(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t world,
                                 int32_t waves, int32_t wave, int32_t *d_packed);
+int32_t grm_syrk_i8_packed_stream(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t world,
+                                  int32_t waves, int32_t *d_packed, uint32_t *d_wave_done, int32_t reserve_sms);
+int32_t grm_wave_gate(grm_cuda_ctx *ctx, const uint32_t *d_wave_done, int64_t n, int32_t world, int32_t waves, int32_t wave,
+                      cudaStream_t stream);
+int32_t grm_flags_gate(grm_cuda_ctx *ctx, const uint32_t *d_flags, int count, uint32_t epoch, cudaStream_t stream);
+int32_t grm_set_u32(grm_cuda_ctx *ctx, uint32_t *d_word, uint32_t value, cudaStream_t stream);
+int32_t grm_finalize_parts_range(grm_cuda_ctx *ctx, const int32_t *d_parts, int64_t n, double alpha, double beta, double gamma,
+                                 double denom, const double *d_u, double *d_Gt, int32_t rank, int32_t world, int64_t t0,
+                                 int64_t cnt, cudaStream_t stream);
 int32_t grm_finalize_tiles_range(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha, double beta,
                                  double gamma, double denom, const double *d_u, double *d_G, int64_t ldg, double *d_Gt,
                                  int32_t rank, int32_t world, int64_t t0, int64_t cnt, cudaStream_t stream);

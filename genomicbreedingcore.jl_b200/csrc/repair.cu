@@ -312,12 +312,10 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
 // wall time of the repair becomes one LU (+ one Cholesky) instead of rounds + 1 of them.  The arithmetic of each probe
 // is the arithmetic of the sequential loop, so the outcome is identical.
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds,
-                                         double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs) {
-    if (!ctx || !dX || n < 1 || ldx < n || rounds < 0 || !det_out || !posdef_out || !scan_flags || !maxabs) {
-        grm_set_error("repair_probe: bad argument");
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
+// which: bit 0 = the determinant, bit 1 = isposdef; 3 = both with the reference's short-circuit (isposdef only when
+// !(det < eps)).  A part that was not evaluated comes back as det = NaN / posdef = -1.
+int32_t grm_repair_probe_part(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds, int32_t which,
+                              double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs) {
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     Repair r;
     unsigned long long h_scan[2];
@@ -329,15 +327,32 @@ extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, in
         memcpy(&mx, &bits, sizeof(double));
     }
     *maxabs = mx;
-    *det_out = 0.0;
+    *det_out = NAN;
     *posdef_out = -1;
     if (h_scan[0] & 1ull) return GRM_CUDA_OK;  // not symmetric: the caller raises before any factorisation (calc.jl:43)
     r.shift_rounds = rounds;
     r.shift_eps0 = mx;
     bool pd = false;
-    GRM_TRY(r.evaluate(&pd, det_out));
-    *posdef_out = (*det_out < DBL_EPSILON) ? -1 : (pd ? 1 : 0);  // -1: not evaluated, det < eps already decides
+    if (which == 3) {
+        GRM_TRY(r.evaluate(&pd, det_out));
+        *posdef_out = (*det_out < DBL_EPSILON) ? -1 : (pd ? 1 : 0);  // -1: not evaluated, det < eps already decides
+        return GRM_CUDA_OK;
+    }
+    if (which & 1) GRM_TRY(r.det(det_out));
+    if (which & 2) {
+        GRM_TRY(r.posdef(&pd));
+        *posdef_out = pd ? 1 : 0;
+    }
     return GRM_CUDA_OK;
+}
+
+extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds,
+                                         double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs) {
+    if (!ctx || !dX || n < 1 || ldx < n || rounds < 0 || !det_out || !posdef_out || !scan_flags || !maxabs) {
+        grm_set_error("repair_probe: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    return grm_repair_probe_part(ctx, dX, n, ldx, rounds, 3, det_out, posdef_out, scan_flags, maxabs);
 }
 
 extern "C" int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t n, int64_t ldx, int32_t rounds,

@@ -26,6 +26,8 @@
 
 int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
                           double *eps_total);
+int32_t grm_repair_probe_part(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds, int32_t which,
+                              double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs);
 
 namespace {
 
@@ -657,22 +659,82 @@ int32_t Run::int8_path(int32_t m, double *dG, int64_t ldG, double **d_tiles_out,
         int waves = ctx->tune.ksplit_waves > 0 ? ctx->tune.ksplit_waves : (world > 1 ? 4 : 1);
         waves = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(waves, 8), tmax)));
         inf.exchange_waves = waves;
+        const bool via_nccl = ctx->tune.exchange != 2;
         GRM_TRY(ctx->packed.reserve(static_cast<size_t>(tmax) * world * 65536 * sizeof(int32_t)));
-        GRM_TRY(ctx->reduced.reserve(static_cast<size_t>(tmax) * 65536 * sizeof(int32_t)));
-        int32_t *d_packed = ctx->packed.as<int32_t>(), *d_red = ctx->reduced.as<int32_t>();
+        int32_t *d_packed = ctx->packed.as<int32_t>();
         cudaStream_t cs = ctx->comm_stream;
-        for (int w = 0; w < waves; ++w) {
-            GRM_TRY(grm_syrk_i8_packed_wave(ctx, d_codes, n, pk, ldc, world, waves, w, d_packed));
-            GRM_CUDA_TRY(cudaEventRecord(ctx->wave_ev[w], st));
-            GRM_CUDA_TRY(cudaStreamWaitEvent(cs, ctx->wave_ev[w], 0));
-            int64_t s0, s1;
-            grm_packed_wave_range(n, world, waves, w, &s0, &s1);
-            GRM_TRY(grm_comm_reduce_scatter(ctx, d_packed + static_cast<size_t>(world) * s0 * 65536, d_red + s0 * 65536,
-                                            static_cast<size_t>(s1 - s0) * 65536, GRM_DT_I32, cs));
-            GRM_TRY(grm_finalize_tiles_range(ctx, d_red, n, sc[0], sc[1], sc[2], sc[3], d_u, nullptr, 0, d_gt, rank, world, s0,
-                                             s1 - s0, cs));
+        // ONE persistent launch contracts every tile in wave order and counts the finished tiles per wave; a gate kernel
+        // per wave on the communication stream waits for that count and releases the exchange of the wave while the
+        // tensor cores work on the later waves
+        GRM_TRY(ctx->progress.reserve(4096));
+        uint32_t *d_done = ctx->progress.as<uint32_t>() + 512;  // clear of the K-window progress words
+        uint32_t *d_epoch = d_done + 16;
+        GRM_CUDA_TRY(cudaMemsetAsync(d_done, 0, 8 * sizeof(uint32_t), st));
+        if (via_nccl) {
+            // exchange by NCCL reduce-scatter (int32 sum): its kernels need SMs, so the SYRK leaves `comm_ctas` of them free
+            GRM_TRY(ctx->reduced.reserve(static_cast<size_t>(tmax) * 65536 * sizeof(int32_t)));
+            int32_t *d_red = ctx->reduced.as<int32_t>();
+            GRM_CUDA_TRY(cudaEventRecord(ctx->wave_ev[9], st));
+            GRM_CUDA_TRY(cudaStreamWaitEvent(cs, ctx->wave_ev[9], 0));  // codes, u and the zeroed counters are ready
+            GRM_TRY(grm_syrk_i8_packed_stream(ctx, d_codes, n, pk, ldc, world, waves, d_packed, d_done,
+                                              waves > 1 ? std::max(ctx->tune.comm_ctas, 0) : 0));
+            GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
+            for (int w = 0; w < waves; ++w) {
+                int64_t s0, s1;
+                grm_packed_wave_range(n, world, waves, w, &s0, &s1);
+                if (s1 <= s0) continue;
+                GRM_TRY(grm_wave_gate(ctx, d_done, n, world, waves, w, cs));
+                GRM_TRY(grm_comm_reduce_scatter(ctx, d_packed + static_cast<size_t>(world) * s0 * 65536, d_red + s0 * 65536,
+                                                static_cast<size_t>(s1 - s0) * 65536, GRM_DT_I32, cs));
+                GRM_TRY(grm_finalize_tiles_range(ctx, d_red, n, sc[0], sc[1], sc[2], sc[3], d_u, nullptr, 0, d_gt, rank, world, s0,
+                                                 s1 - s0, cs));
+            }
+        } else {
+            // exchange by the COPY ENGINES over NVLink peer mappings (tuning "exchange" = 2) — no SM is taken from the
+            // contraction, but with every GPU sending to every other at once the engines move only 80 GB/s per sender in
+            // 16 MiB pieces and ~340 GB/s in 128 MiB ones (profiles/p2p_copy_engine_probe_r2.jsonl) against ~530 GB/s for
+            // NCCL's reduce-scatter, so it is not the default.  Rank r's
+            // receive buffer holds one part per source rank; when wave w is stored, this rank copies, for every owner q,
+            // its partial tiles of q's slots [s0, s1) into part `rank` of q's buffer and then a 4-byte epoch flag on the
+            // same stream (so the flag lands after the data).  The owner's gate waits for the flags of all sources, then
+            // the parts are summed (int32, exact, fixed order) inside the finalisation of the wave's tiles.
+            void **peers = nullptr;
+            GRM_TRY(grm_comm_peer_buffer(ctx, GRM_PEER_HEADER + static_cast<size_t>(world) * tmax * 65536 * sizeof(int32_t), &peers));
+            const uint32_t epoch = grm_comm_next_epoch(ctx);
+            GRM_TRY(grm_set_u32(ctx, d_epoch, epoch, st));
+            GRM_CUDA_TRY(cudaEventRecord(ctx->wave_ev[9], st));
+            GRM_CUDA_TRY(cudaStreamWaitEvent(cs, ctx->wave_ev[9], 0));  // codes, u, the counters and the epoch word are ready
+            GRM_TRY(grm_syrk_i8_packed_stream(ctx, d_codes, n, pk, ldc, world, waves, d_packed, d_done, 0));
+            GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
+            auto data_of = [&](int q) { return reinterpret_cast<int32_t *>(static_cast<char *>(peers[q]) + GRM_PEER_HEADER); };
+            auto flag_of = [&](int q, int w, int src) { return static_cast<uint32_t *>(peers[q]) + w * 64 + src; };
+            cudaEvent_t released = grm_comm_xevent(ctx, GRM_XSTREAMS);
+            for (int w = 0; w < waves; ++w) {
+                int64_t s0, s1;
+                grm_packed_wave_range(n, world, waves, w, &s0, &s1);
+                if (s1 <= s0) continue;
+                const int64_t len = s1 - s0;
+                GRM_TRY(grm_wave_gate(ctx, d_done, n, world, waves, w, cs));
+                GRM_CUDA_TRY(cudaEventRecord(released, cs));
+                for (int i = 0; i < std::min(GRM_XSTREAMS, world); ++i)
+                    GRM_CUDA_TRY(cudaStreamWaitEvent(grm_comm_xstream(ctx, i), released, 0));
+                for (int k = 0; k < world; ++k) {
+                    const int q = (rank + 1 + k) % world;  // every rank starts with another owner: the links share the load
+                    cudaStream_t xs = grm_comm_xstream(ctx, k);
+                    GRM_CUDA_TRY(cudaMemcpyAsync(data_of(q) + (static_cast<size_t>(rank) * tmax + s0) * 65536,
+                                                 d_packed + (static_cast<size_t>(world) * s0 + static_cast<size_t>(q) * len) * 65536,
+                                                 static_cast<size_t>(len) * 65536 * sizeof(int32_t), cudaMemcpyDeviceToDevice, xs));
+                    GRM_CUDA_TRY(cudaMemcpyAsync(flag_of(q, w, rank), d_epoch, sizeof(uint32_t), cudaMemcpyDeviceToDevice, xs));
+                }
+                GRM_TRY(grm_flags_gate(ctx, flag_of(rank, w, 0), world, epoch, cs));
+                GRM_TRY(grm_finalize_parts_range(ctx, data_of(rank), n, sc[0], sc[1], sc[2], sc[3], d_u, d_gt, rank, world, s0, len, cs));
+            }
+            // the copies read d_packed: the compute stream (hence the end of the call) waits for them too
+            for (int i = 0; i < std::min(GRM_XSTREAMS, world); ++i) {
+                GRM_CUDA_TRY(cudaEventRecord(grm_comm_xevent(ctx, i), grm_comm_xstream(ctx, i)));
+                GRM_CUDA_TRY(cudaStreamWaitEvent(st, grm_comm_xevent(ctx, i), 0));
+            }
         }
-        GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
         GRM_CUDA_TRY(cudaEventRecord(ctx->wave_ev[8], cs));
         GRM_CUDA_TRY(cudaStreamWaitEvent(st, ctx->wave_ev[8], 0));
         GRM_CUDA_TRY(cudaEventRecord(ev[10], st));
@@ -822,23 +884,28 @@ int32_t Run::f64_path(double *dG, int64_t ldG, double **d_tiles_out, int64_t *p_
 
 // ---------------------------------------------------------------------------------------------------------------
 // inflatediagonals! with the matrix replicated on every rank (calc.jl:41-70): the loop test of round t only looks at
-// X with its diagonal inflated t times, so rank r evaluates round base + r while the others evaluate theirs — one LU
-// (+ Cholesky) of wall time instead of rounds + 1.  Each probe performs the arithmetic of the sequential loop and the
-// decision is taken on the all-gathered results, hence the same outcome on every rank as the sequential loop.
+// X with its diagonal inflated t times, and its two halves — det(X_t) (LU) and isposdef(X_t) (Cholesky) — are independent
+// of each other.  So the probes are dealt out as (round, half) tasks: rank 2i takes the determinant of round base + i,
+// rank 2i + 1 its Cholesky; a batch of probes costs max(LU, Cholesky) of wall time and covers world / 2 rounds.  Each
+// probe performs the arithmetic of the sequential loop and the decision is taken on the all-gathered results, hence
+// the same outcome on every rank as the sequential loop.  (One rank: both halves, with the reference's short-circuit.)
 // ---------------------------------------------------------------------------------------------------------------
 int32_t Run::repair_parallel(double *dG, int64_t ldG) {
     const double eps = DBL_EPSILON;
+    const int per_batch = world >= 2 ? world / 2 : 1;  // rounds evaluated per batch
     int64_t base = 0;
     int32_t iters = -1;
     double maxabs = 0.0;
     while (iters < 0) {
-        const int64_t r = base + rank;
+        const int64_t r = base + (world >= 2 ? rank / 2 : 0);
+        const int which = world >= 2 ? ((rank & 1) ? 2 : 1) : 3;
+        const bool idle = world >= 2 && rank >= 2 * per_batch;  // the odd rank out
         double mine[4] = {NAN, -1.0, 0.0, 0.0};
-        if (r <= o.max_iter) {
-            double det = 0.0, mx = 0.0;
+        if (!idle && r <= o.max_iter) {
+            double det = NAN, mx = 0.0;
             int32_t pd = -1;
             uint32_t fl = 0;
-            GRM_TRY(grm_cuda_repair_probe(ctx, dG, n, ldG, static_cast<int32_t>(r), &det, &pd, &fl, &mx));
+            GRM_TRY(grm_repair_probe_part(ctx, dG, n, ldG, static_cast<int32_t>(r), which, &det, &pd, &fl, &mx));
             mine[0] = det;
             mine[1] = static_cast<double>(pd);
             mine[2] = static_cast<double>(fl);
@@ -846,16 +913,17 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
         }
         std::vector<double> all;
         GRM_TRY(gather_f64(mine, 4, all));
+        auto det_of = [&](int i) { return world >= 2 ? all[4 * (2 * i)] : all[0]; };
+        auto pd_of = [&](int i) { return world >= 2 ? all[4 * (2 * i + 1) + 1] : all[1]; };
         if (base == 0) {
-            const double det0 = all[0], pd0 = all[1];
             const uint32_t flags = static_cast<uint32_t>(all[2]);
             maxabs = all[3];
             if (flags & 1u) {
                 grm_set_error("The input matrix is not symmetric.");  // calc.jl:43-45
                 return GRM_CUDA_ERR_NOT_SYMMETRIC;
             }
-            if (det0 > eps && pd0 == 1.0) {  // calc.jl:49-51
-                if (rank == 0) ctx->factor_n = n;
+            if (det_of(0) > eps && pd_of(0) == 1.0) {  // calc.jl:49-51
+                if (rank == (world >= 2 ? 1 : 0)) ctx->factor_n = n;  // the rank that holds chol(X)
                 inf.repair_iters = 0;
                 inf.eps_total = 0.0;
                 return GRM_CUDA_OK;
@@ -869,16 +937,17 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
                 return GRM_CUDA_ERR_INF_MATRIX;
             }
         }
-        for (int k = 0; k < world && iters < 0; ++k) {
-            const int64_t t = base + k;
-            const double det = all[4 * k], pd = all[4 * k + 1];
-            const bool need = (det < eps) || (pd != 1.0);  // calc.jl:61 (a NaN det compares false, then isposdef decides)
+        for (int i = 0; i < per_batch && iters < 0; ++i) {
+            const int64_t t = base + i;
+            const double det = det_of(i), pd = pd_of(i);
+            // calc.jl:61 (a NaN det compares false, then isposdef decides; a half that was not evaluated is decided by the other)
+            const bool need = (det < eps) || (pd != 1.0);
             if (!need || t >= o.max_iter) {
                 iters = static_cast<int32_t>(t);
-                if (!need && k == rank) ctx->factor_n = n;  // this rank's last factorisation is chol of the result
+                if (!need && rank == (world >= 2 ? 2 * i + 1 : 0)) ctx->factor_n = n;  // this rank's Cholesky is of the result
             }
         }
-        base += world;
+        base += per_batch;
     }
     double tot = 0.0;
     GRM_TRY(grm_cuda_repair_apply(ctx, dG, n, ldG, iters, maxabs, &tot));

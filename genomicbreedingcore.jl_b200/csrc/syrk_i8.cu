@@ -47,6 +47,12 @@ struct EpiParams {
     const int32_t *slots;  // mode 3: slot of tile t in the packed int32 tile buffer C ([slot][256 cols][256 rows])
     double *Gt;            // modes 1, 2 (2-CTA kernel): if set, tile t is stored packed at Gt + t*65536 ([col][row],
                            // zeros outside n) instead of into the dense matrix G: the sharded-output form
+    // mode 3, streamed exchange: tiles [wave_end[w-1], wave_end[w]) of the list form exchange wave w; every epilogue warp
+    // that has stored its quarter of a tile adds 1 to wave_done[w] (8 per tile), so a gate kernel on the communication
+    // stream can release the reduce-scatter of wave w while the contraction of the later waves is still running
+    uint32_t *wave_done;
+    int32_t wave_end[8];
+    int32_t nwaves;
 };
 
 // Correctly rounded v / d for a launch-constant divisor: q0 = RN(v*rcp), then two FMA residual corrections
@@ -445,6 +451,14 @@ syrk_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__rest
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+            if (EPI == 3 && ep.wave_done != nullptr) {
+                __threadfence();  // this warp's stores of the tile are visible device-wide before it is counted
+                if (lane == 0) {
+                    int w = 0;
+                    while (w + 1 < ep.nwaves && t >= ep.wave_end[w]) ++w;
+                    atomicAdd(ep.wave_done + w, 1u);
+                }
+            }
         }
     }
 
@@ -959,15 +973,25 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
 // Exchange volume 4 n^2 / 2 bytes per GPU instead of n p for the all-gather of the codes — the better choice whenever
 // p > 4 n (BASELINE C2, C3).
 //
-// Waves: the slots 0 .. tiles_max-1 every rank owns are cut into `waves` ranges [s_w, s_{w+1}); wave w of the packed
-// buffer is the contiguous block [world][s_{w+1} - s_w][256 x 256] starting at element world * s_w * 65536, so the
-// reduce-scatter of wave w is one plain call that can run on a second stream while the tensor cores contract wave
-// w + 1 (run.cu).  waves = 1 is the layout [world][tiles_max][256 x 256] of the single-exchange form.
+// Waves: the slots 0 .. tiles_max-1 every rank owns are cut into `waves` ranges [s_w, s_{w+1}) of decreasing size; wave
+// w of the packed buffer is the contiguous block [world][s_{w+1} - s_w][256 x 256] starting at element
+// world * s_w * 65536, so the reduce-scatter of wave w is one plain call.  ONE persistent launch contracts all tiles in
+// wave order (grm_syrk_i8_packed_stream) and counts finished tiles per wave; a gate kernel on the communication stream
+// (grm_wave_gate) releases the reduce-scatter of wave w as soon as its tiles are stored, while the tensor cores are
+// already deep in the later waves (run.cu).  The launch leaves `comm_ctas` SMs free: the persistent grid would
+// otherwise own every SM and NCCL's CTAs could only run between launches.  waves = 1 is the layout
+// [world][tiles_max][256 x 256] of the single-exchange form.
 // ---------------------------------------------------------------------------------------------------------------
 void grm_packed_wave_range(int64_t n, int32_t world, int32_t waves, int32_t w, int64_t *s0, int64_t *s1) {
+    // wave w gets (waves - w) shares: the exchange of the LAST wave is the one nothing can hide, so it is the smallest
     const int64_t tmax = grm_cuda_packed_tiles_max(n, world);
-    *s0 = tmax * w / waves;
-    *s1 = tmax * (w + 1) / waves;
+    const int64_t total = static_cast<int64_t>(waves) * (waves + 1) / 2;
+    auto cut = [&](int64_t k) {  // slots before wave k
+        const int64_t shares = k * waves - k * (k - 1) / 2;
+        return tmax * shares / total;
+    };
+    *s0 = cut(w);
+    *s1 = w + 1 == waves ? tmax : cut(w + 1);
 }
 
 namespace {
@@ -1116,6 +1140,165 @@ int32_t grm_syrk_i8_packed_wave(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_
 extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                            int32_t world, int32_t *d_packed) {
     return grm_syrk_i8_packed_wave(ctx, d_codes, n, p, ldc, world, 1, 0, d_packed);
+}
+
+namespace {
+__global__ void wave_gate_kernel(const uint32_t *counter, uint32_t target) {
+    // bounded: if the producer never gets there (its launch failed) the stream must still drain — the caller already
+    // holds the launch error.  ~2^22 x 1 us.
+    if (threadIdx.x == 0) {
+        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+            uint32_t v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            __nanosleep(1000);
+        }
+    }
+}
+}  // namespace
+
+namespace {
+// all `count` flags (32-bit words, written by the peers' copy engines after their data) have reached `epoch`
+__global__ void flags_gate_kernel(const uint32_t *flags, int count, uint32_t epoch) {
+    if (static_cast<int>(threadIdx.x) < count) {
+        for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (static_cast<int32_t>(v - epoch) >= 0) break;  // epochs only grow (wrap-safe comparison)
+            __nanosleep(500);
+        }
+    }
+}
+
+__global__ void set_u32_kernel(uint32_t *p, uint32_t v) { *p = v; }
+
+// G tile <- formula(sum over the `world` parts of the owned tile t): parts[q][t][256 x 256] int32, exact sum in the
+// fixed order q = 0 .. world-1, then the arithmetic of the fused SYRK epilogue; written packed at Gt + t * 65536
+template <int EPI>
+__global__ void __launch_bounds__(256)
+finalize_parts_kernel(const int32_t *__restrict__ parts, int64_t part_stride, int world, const int2 *__restrict__ tiles, EpiParams ep,
+                      int t0) {
+    const int t = t0 + blockIdx.x;
+    const int2 tc = tiles[t];
+    const int32_t *base = parts + static_cast<int64_t>(t) * 65536;
+    double *gt = ep.Gt + static_cast<int64_t>(t) * 65536;
+    for (int idx = threadIdx.x; idx < 65536; idx += 256) {
+        const int cl = idx >> 8, rl = idx & 255;
+        const int64_t row = tc.x + rl, col = tc.y + cl;
+        double out = 0.0;
+        if (row < ep.n && col < ep.n) {
+            int32_t c = 0;
+            for (int q = 0; q < world; ++q) c += base[q * part_stride + idx];
+            double v = static_cast<double>(c) * ep.alpha;
+            if (EPI == 2) v = (v - ep.beta * (__ldg(ep.u + row) + __ldg(ep.u + col))) + ep.gamma;
+            out = (ep.rcp != 0.0) ? div_const(v, ep.denom, ep.rcp) : v / ep.denom;
+        }
+        gt[idx] = out;
+    }
+}
+}  // namespace
+
+int32_t grm_flags_gate(grm_cuda_ctx *ctx, const uint32_t *d_flags, int count, uint32_t epoch, cudaStream_t stream) {
+    if (count < 1 || count > 1024) {
+        grm_set_error("flags_gate: bad count %d", count);
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    flags_gate_kernel<<<1, (count + 31) / 32 * 32, 0, stream>>>(d_flags, count, epoch);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+int32_t grm_set_u32(grm_cuda_ctx *ctx, uint32_t *d_word, uint32_t value, cudaStream_t stream) {
+    set_u32_kernel<<<1, 1, 0, stream>>>(d_word, value);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+// owned tiles [t0, t0 + cnt) from the `world` received parts ([q][tiles_max][256 x 256] int32) -> packed FP64 tiles
+int32_t grm_finalize_parts_range(grm_cuda_ctx *ctx, const int32_t *d_parts, int64_t n, double alpha, double beta, double gamma,
+                                 double denom, const double *d_u, double *d_Gt, int32_t rank, int32_t world, int64_t t0,
+                                 int64_t cnt, cudaStream_t stream) {
+    if (!ctx || !d_parts || !d_Gt || n < 1 || world < 1 || rank < 0 || rank >= world || (beta != 0.0 && !d_u)) {
+        grm_set_error("finalize_parts: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int2 *d_tiles;
+    int count;
+    GRM_TRY(get_tile_list_2cta(ctx, n, rank, world, &d_tiles, &count));
+    if (t0 < 0) t0 = 0;
+    cnt = std::min<int64_t>(cnt, count - t0);
+    if (cnt <= 0) return GRM_CUDA_OK;
+    EpiParams ep{};
+    ep.n = n;
+    ep.Gt = d_Gt;
+    ep.alpha = alpha;
+    ep.beta = beta;
+    ep.gamma = gamma;
+    set_division(ctx, ep, denom);
+    ep.u = d_u;
+    const int64_t stride = grm_cuda_packed_tiles_max(n, world) * 65536;
+    if (beta == 0.0 && gamma == 0.0)
+        finalize_parts_kernel<1><<<static_cast<unsigned>(cnt), 256, 0, stream>>>(d_parts, stride, world, d_tiles, ep, static_cast<int>(t0));
+    else
+        finalize_parts_kernel<2><<<static_cast<unsigned>(cnt), 256, 0, stream>>>(d_parts, stride, world, d_tiles, ep, static_cast<int>(t0));
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+// blocks `stream` until wave `wave` of the streamed contraction has been stored (8 counts per tile)
+int32_t grm_wave_gate(grm_cuda_ctx *ctx, const uint32_t *d_wave_done, int64_t n, int32_t world, int32_t waves, int32_t wave,
+                      cudaStream_t stream) {
+    PackedPlanCache *pc;
+    GRM_TRY(grm_packed_plan(ctx, n, world, waves, &pc));
+    const uint32_t target = 8u * static_cast<uint32_t>(pc->tile_cnt[wave]);
+    if (target == 0) return GRM_CUDA_OK;
+    wave_gate_kernel<<<1, 32, 0, stream>>>(d_wave_done + wave, target);
+    GRM_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return GRM_CUDA_OK;
+}
+
+// all waves of the K-split contraction in ONE persistent launch, tiles in wave order, per-wave completion counters in
+// d_wave_done[waves] (zeroed by the caller); `reserve_sms` SMs are left to the communication kernels
+int32_t grm_syrk_i8_packed_stream(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t world,
+                                  int32_t waves, int32_t *d_packed, uint32_t *d_wave_done, int32_t reserve_sms) {
+    if (!ctx || !d_codes || !d_packed || !d_wave_done || n < 1 || p < 1 || ldc < p || (ldc % 16) != 0 || world < 1 ||
+        waves < 1 || waves > 8) {
+        grm_set_error("syrk_i8_packed_stream: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    GRM_CUDA_TRY(cudaSetDevice(ctx->device));
+    CUtensorMap tmap;
+    GRM_TRY(make_codes_tmap(d_codes, n, p, ldc, 1, &tmap));
+    PackedPlanCache *pc;
+    GRM_TRY(grm_packed_plan(ctx, n, world, waves, &pc));
+    const int64_t tiles_max = grm_cuda_packed_tiles_max(n, world);
+    if (static_cast<int64_t>(pc->total_tiles) != tiles_max * world)
+        GRM_CUDA_TRY(cudaMemsetAsync(d_packed, 0, static_cast<size_t>(tiles_max) * world * 65536 * sizeof(int32_t), ctx->stream));
+    const int count = pc->total_tiles;
+    if (count == 0) return GRM_CUDA_OK;
+    EpiParams ep{};
+    ep.n = n;
+    ep.C = d_packed;
+    ep.slots = reinterpret_cast<const int32_t *>(pc->buf.as<int2>() + pc->total_tiles);
+    ep.wave_done = d_wave_done;
+    ep.nwaves = waves;
+    for (int w = 0; w < 8; ++w) ep.wave_end[w] = w < waves ? pc->tile_off[w] + pc->tile_cnt[w] : count;
+    const int kbs = static_cast<int>((p + BK - 1) / BK);
+    const int pairs = std::max(1, std::min(count, ctx->num_sms / 2 - std::max(0, (reserve_sms + 1) / 2)));
+    const int saved_sync = ctx->tune.syrk_sync;
+    ctx->tune.syrk_sync = 0;  // a grid that shares the device with the exchange kernels must not wait on co-residency
+    const int32_t st = launch_pairs(ctx, reinterpret_cast<const void *>(syrk_i8_2cta_kernel<3>), SMEM2_BYTES, pairs, count, n * ldc,
+                                    [&](const cudaLaunchConfig_t *cfg, uint32_t *prog) {
+                                        return cudaLaunchKernelEx(cfg, syrk_i8_2cta_kernel<3>, tmap, pc->buf.as<int2>(), count, kbs,
+                                                                  kbs, ep, prog, window_blocks(ctx));
+                                    });
+    ctx->tune.syrk_sync = saved_sync;
+    return st;
 }
 
 // finalise owned tiles [t0, t0 + cnt) of the reduced buffer ([tiles_max][256 x 256] int32, slot = position in the

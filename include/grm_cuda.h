@@ -167,7 +167,9 @@ int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx);
 /* Per-context tuning knobs; the library never reads the environment.  Keys (value 0 / -1 = automatic, the measured
  * best): "syrk_i8" (1 single-CTA, 2 CTA pair, 3 wide), "syrk_packed" (2, 3), "syrk_sync" (-1 auto, 0 off, 1 on),
  * "syrk_window", "pack" (1 = register-staged), "ieee_div", "tile_band", "host_threads", "ingest" (GRM_CUDA_INGEST_*),
- * "ksplit_waves", "f64_kernel" (1 = register-staged operands), "ring_mb".  Unknown key -> GRM_CUDA_ERR_BAD_ARGUMENT. */
+ * "ksplit_waves", "f64_kernel" (1 = register-staged operands), "ring_mb", "comm_ctas" (> 0: cap NCCL's CTAs; set before
+ * grm_cuda_comm_init), "exchange" (K-split partial tiles: 0 auto = NCCL reduce-scatter, 2 = copy engines into
+ * peer-mapped buffers).  Unknown key -> GRM_CUDA_ERR_BAD_ARGUMENT. */
 int32_t grm_cuda_ctx_set_tuning(grm_cuda_ctx *ctx, const char *key, int64_t value);
 int32_t grm_cuda_ctx_get_tuning(grm_cuda_ctx *ctx, const char *key, int64_t *value);
 
@@ -177,6 +179,10 @@ int32_t grm_cuda_ctx_get_tuning(grm_cuda_ctx *ctx, const char *key, int64_t *val
  * application hands them to the others (MPI, Distributed.jl, torch.distributed, a file ...) and every rank calls
  * grm_cuda_comm_init (collective).  NCCL is dlopen'ed on first use: single-GPU users need no NCCL, and a process that
  * already carries one (PyTorch) shares it. */
+/* Optional, before the first communicator call: full path of the libnccl.so.2 to use.  Default: an NCCL already loaded
+ * into the process, else the system's.  A host that will load a (newer) NCCL of its own LATER — e.g. by importing
+ * PyTorch — must name that copy here, because the dynamic loader hands out whichever libnccl.so.2 was loaded first. */
+int32_t grm_cuda_comm_set_library(const char *path);
 int32_t grm_cuda_comm_unique_id(uint8_t *id128);
 int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world);
 int32_t grm_cuda_comm_destroy(grm_cuda_ctx *ctx);

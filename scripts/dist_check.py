@@ -23,6 +23,10 @@ def relerr(G, ref):
 
 def main():
     import ctypes as C
+    import faulthandler
+
+    # a stuck collective must show WHERE: every rank dumps its stack and exits instead of hanging the box
+    faulthandler.dump_traceback_later(int(os.environ.get("DIST_CHECK_WATCHDOG_S", "240")), exit=True)
 
     import torch
     import torch.distributed as dist
@@ -64,6 +68,8 @@ def main():
         ("dosage", 600, 5000, 4, 4), ("dosage", 600, 5000, 2, None), ("dosage", 1100, 2000, 2, 2),
         ("dosage", 1100, 2000, 4, None), ("continuous", 500, 3000, 0, 2), ("continuous", 700, 900, 0, None),
         ("dosage", 300, 3, 2, 2), ("dosage", 130, 1, 2, None),  # fewer loci than ranks x 128: short and empty slabs
+        # ONE output tile: with two or more ranks some of them own no tile at all (what 8 ranks see at n = 600)
+        ("dosage", 200, 2000, 2, 2), ("dosage", 200, 2000, 4, None), ("continuous", 200, 1500, 0, 2), ("dosage", 256, 900, 2, 2),
     ]
     for kind, n, p, gm, ploidy in cases:
         A = synth.dosage(n, p, gm, seed=n + p) if kind == "dosage" else synth.continuous(n, p, seed=n + p)
@@ -95,7 +101,8 @@ def main():
         # (4) the same from host memory
         T2, i4 = grm_call(A, ploidy, ctx=ctx, distributed=True, tiles=True, skip_repair=True)
         cnt = lib.grm_cuda_tile_count(n, rank, world)
-        assert (np.array_equal(T2[:cnt], Th[:cnt]) if exact else relerr(T2[:cnt], Th[:cnt]) <= 1e-13 or cnt == 0)
+        if cnt > 0:  # a rank may own no tile at all
+            assert (np.array_equal(T2[:cnt], Th[:cnt]) if exact else relerr(T2[:cnt], Th[:cnt]) <= 1e-13), (kind, n, p)
         if p > 4 * n and exact and world > 1:
             assert i3["exchange_waves"] >= 1
         dist.barrier()
@@ -103,11 +110,22 @@ def main():
     # exchange waves: any number gives the same bits
     A = synth.dosage(1300, 6000, 4, seed=3)
     ref, _ = grm_call(A, 4, ctx=ctx, skip_repair=True)
-    for waves in (1, 2, 3, 8):
-        ctx.set_tuning("ksplit_waves", waves)
-        G, info = grm_call(A, 4, ctx=ctx, distributed=True, skip_repair=True)
-        assert info["exchange_waves"] == min(waves, lib.grm_cuda_packed_tiles_max(1300, world)) and np.array_equal(G, ref), waves
+    # ... through either transport: 0 = NCCL reduce-scatter (default), 2 = copy engines into peer-mapped receive buffers
+    for exchange in (0, 2):
+        ctx.set_tuning("exchange", exchange)
+        for waves in (1, 2, 3, 8):
+            ctx.set_tuning("ksplit_waves", waves)
+            for pl in (4, None):
+                G, info = grm_call(A, pl, ctx=ctx, distributed=True, skip_repair=True)
+                want = ref if pl == 4 else grm_call(A, None, ctx=ctx, skip_repair=True)[0]
+                assert info["exchange_waves"] == min(waves, lib.grm_cuda_packed_tiles_max(1300, world)), (exchange, waves)
+                assert np.array_equal(G, want), (exchange, waves, pl)
     ctx.set_tuning("ksplit_waves", 0)
+    ctx.set_tuning("exchange", 0)
+    # back-to-back calls reuse the peer buffers: the epoch flags must keep the steps apart
+    for _ in range(5):
+        G, info = grm_call(A, 4, ctx=ctx, distributed=True, skip_repair=True)
+        assert np.array_equal(G, ref)
 
     # QC mask + mean-fill, distributed: kept loci / scale agree with the single-GPU call
     A = synth.add_missing(synth.dosage(400, 3000, 2, seed=8), 0.002, seed=9)
@@ -148,8 +166,19 @@ def main():
     ctx.comm_destroy()
     ctx.close()
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
     print(f"DIST_CHECK_OK rank {rank} of {world}", flush=True)
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        # leave at once: a destructor that waits for a collective the peers are still in would keep the launcher from
+        # noticing the failure (and from tearing the other ranks down)
+        import traceback
+
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)

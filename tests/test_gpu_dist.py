@@ -56,11 +56,14 @@ def test_world_of_one_reproduces_the_plain_call(ctx1, kind, n, p, gm, ploidy):
     assert np.array_equal(G, ref) if kind == "dosage" else relerr(G, ref) <= 1e-13
     assert np.array_equal(G, G.T)
     if kind == "dosage" and p > 4 * n:
-        for waves in (1, 3):
-            ctx1.set_tuning("ksplit_waves", waves)
-            G2, i2 = grm_call(A, ploidy, ctx=ctx1, distributed=True)
-            assert i2["exchange_waves"] == waves and np.array_equal(G2, ref)
+        for exchange in (0, 2):  # NCCL reduce-scatter / copy engines into the (here: own) peer-mapped buffer
+            ctx1.set_tuning("exchange", exchange)
+            for waves in (1, 3, 8):
+                ctx1.set_tuning("ksplit_waves", waves)
+                G2, i2 = grm_call(A, ploidy, ctx=ctx1, distributed=True)
+                assert i2["exchange_waves"] == min(waves, ctx1.lib.grm_cuda_packed_tiles_max(n, 1)) and np.array_equal(G2, ref), (exchange, waves)
         ctx1.set_tuning("ksplit_waves", 0)
+        ctx1.set_tuning("exchange", 0)
     # sharded output: every upper-triangular tile, packed [col][row]
     raw, _ = grm_call(A, ploidy, ctx=ctx1, skip_repair=True)
     T, it = grm_call(A, ploidy, ctx=ctx1, distributed=True, tiles=True, skip_repair=True)
@@ -99,7 +102,8 @@ def test_ranks_on_separate_gpus_match_the_single_gpu_result():
     port = 29500 + os.getpid() % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "dist_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    env = dict(os.environ, DIST_CHECK_WATCHDOG_S="120")  # a stuck rank dumps its stack and exits instead of hanging the box
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=ROOT, env=env)
     tail = (r.stdout + r.stderr)[-6000:]
     assert r.returncode == 0, tail
     assert r.stdout.count("DIST_CHECK_OK") == world, tail
