@@ -322,6 +322,34 @@ def run_b200(args, wl):
     waves = infos[-1]["exchange_waves"]
     window = infos[-1]["syrk_window"]
 
+    # ---- side measurements on the same resident input (outside the timed region, N = 1) ----------------------------
+    extras = {}
+    if world == 1 and not tiles_out and kind == "dosage" and args.extras:
+        def timed_steps(k=3, **kw):
+            D.grm_device(ctx, A_dev, pl, path=path, denominator=m, skip_repair=True, out=out_dev, **kw)  # warm
+            t = []
+            for _ in range(k):
+                _, inf = D.grm_device(ctx, A_dev, pl, path=path, denominator=m, skip_repair=True, out=out_dev, **kw)
+                t.append(inf)
+            return t
+        # QC locus mask folded into the pack pass (missing counts per locus, keep decision, zeroing of dropped columns):
+        # the same step with maf = 0.05 — no second read of A
+        tm = timed_steps(maf=0.05)
+        extras["masked_step"] = {"maf": 0.05, "loci_kept": tm[-1]["loci_kept"],
+                                 "ms_pack_incl_mask": sum(i["ms_pack"] for i in tm) / len(tm),
+                                 "ms_pack_unmasked": stage_ms["ms_pack"],
+                                 "ms_step": sum(i["ms_pack"] + i["ms_rowdot"] + i["ms_syrk"] + i["ms_finalize"] for i in tm) / len(tm),
+                                 "ms_step_unmasked": sum(stage_ms[k] for k in ("ms_pack", "ms_rowdot", "ms_syrk", "ms_finalize"))}
+        # band height of the tile enumeration (L2 reuse of the operand panels vs working set)
+        sweep = {}
+        for band in (8, 12, 16, 24):
+            ctx.set_tuning("tile_band", band)
+            tb = timed_steps()
+            sweep[str(band)] = sum(i["ms_syrk"] for i in tb) / len(tb)
+        ctx.set_tuning("tile_band", 0)
+        extras["tile_band_ms_syrk"] = sweep
+        timed_steps(k=1)  # leave the default-order result in out_dev for the verification below
+
     # ---- what was timed is what is verified (outside the timed region) -------------------------------------------
     verified = None
     if not args.no_verify and kind == "dosage":
@@ -533,7 +561,7 @@ def run_b200(args, wl):
                    "parallelism": par, "macs_per_step": macs(n, p)},
         "clocks": clocks, "e2e": e2e if e2e is not None else ({"unavailable": e2e_skip} if e2e_skip else None),
         "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack, "roofline_f64": roofline_f64,
-        "verified": verified, "cpu_baseline": cpu, "stage_ms": stage_ms,
+        "verified": verified, "cpu_baseline": cpu, "stage_ms": stage_ms, "extras": extras or None,
     }
     if world > 1:
         dist.destroy_process_group()
@@ -769,6 +797,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time the masked step and sweep the tile-band height (N = 1)")
     ap.add_argument("--no-f64", action="store_true", help="skip the FP64-mode slice (roofline_f64) of the default line")
     ap.add_argument("--no-libpeaks", action="store_true", help="skip the same-run cuBLASLt int8 / cuBLAS dgemm timings")
     args = ap.parse_args()

@@ -6,8 +6,13 @@
 // centre_f64_kernel (reference rounding sequence, optional mean-fill and QC mask); the SYRK main loop is pure DMMA.
 //
 // tcgen05 has no FP64 kind, so the contraction runs on the FP64 tensor path that exists on sm_100:
-// mma.sync.m16n8k8.f64 (DMMA).  Block tile 128 x 128 entries, 8 warps (2 x 4), warp tile 64 x 32, K slab of 16
-// loci, double-buffered shared memory with register prefetch.  Only tiles that touch the upper triangle run.
+// mma.sync.m16n8k8.f64 (DMMA).  Block tile 128 x 128 entries, 8 consumer warps (2 x 4), warp tile 64 x 32.  Only tiles
+// that touch the upper triangle run.  Two operand feeds:
+//   syrk_f64_tma_kernel (default when the operand rows are 16-byte aligned): an elected lane keeps a 3-stage ring of
+//     TMA boxes (16 entries x 32 loci, SWIZZLE_128B) in flight; no block-wide barrier in the main loop, a diagonal tile
+//     loads its panel once.
+//   syrk_f64_kernel: register-staged __ldg -> st.shared into a padded layout, double buffered (tuning f64_kernel = 1,
+//     and for operands TMA cannot describe).
 #include "common.cuh"
 
 namespace {
@@ -141,6 +146,160 @@ syrk_f64_kernel(const double *__restrict__ A, int64_t n, int64_t p, int64_t lda,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-fed variant.  The operand Z is column-major (entry fastest), which is already the [k][entry] order the DMMA
+// fragments want, so a 2-D box {16 entries, 32 loci} lands ready to use: 32 rows of 128 bytes.  Under SWIZZLE_128B
+// the 16-byte chunk c of row r sits at chunk c ^ (r & 7).  A fragment load touches, per half-warp, 4 entries-pairs x 4
+// values of k; with k = t -> row t the four rows would fall on the same banks (2-way conflict).  A sum over loci does not
+// care which physical locus plays which k of the MMA, so within each group of 8 loci logical k = t reads row 2t and
+// k = t + 4 reads row 2t + 1 (the same mapping for A and B): the XOR then spreads the 16 threads of a half-warp over
+// all 8 chunks — every fragment load is conflict-free.  r & 7 does not depend on the 8-locus step, so the swizzled
+// column offsets are four per-thread constants.
+// ---------------------------------------------------------------------------------------------------------------
+// shared-space load on a 32-bit shared address (the 1 KiB alignment cast hides the address space from the compiler, which
+// would otherwise emit generic loads); volatile: stays after the mbarrier wait that publishes the stage
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+constexpr int TS = 3;                      // ring stages
+constexpr int TBOX = 16;                   // entries per box = 128 bytes = the swizzle span
+constexpr int TBOX_DBL = TBOX * FK;        // 512 doubles = 4 KiB per box
+constexpr int TPANEL_DBL = (FB / TBOX) * TBOX_DBL;  // 128 entries x 32 loci = 32 KiB
+constexpr size_t F64T_SMEM = static_cast<size_t>(TS) * 2 * TPANEL_DBL * sizeof(double) + 1024 /*alignment*/ + 128 /*barriers*/;
+
+// 8 warps (the register file of an SM is split over 4 sub-cores of 16 K registers: a ninth warp would put three warps of
+// ~200 registers on one of them, which does not fit — so there is no dedicated producer warp).  Lane 0 of warp 0 issues
+// the TMA loads: slabs 0 .. TS-2 up front, then slab s + TS - 1 right after warp 0 has finished slab s; the stage it
+// refills was consumed during slab s - 1, so the wait for "stage empty" is normally over before it is asked.
+__global__ void __launch_bounds__(256, 1)
+syrk_f64_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n, int64_t p, const int2 *__restrict__ tiles,
+                    double *__restrict__ G, int64_t ldg, int accumulate) {
+    extern __shared__ uint8_t f64t_raw[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(f64t_raw) + 1023) & ~uintptr_t(1023));
+    double *ring = reinterpret_cast<double *>(base);  // [TS][A panel | B panel]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(base + static_cast<size_t>(TS) * 2 * TPANEL_DBL * sizeof(double));
+    uint64_t *empty_bar = full_bar + TS;
+
+    const int2 tc = tiles[blockIdx.x];
+    const int64_t row0 = tc.x, col0 = tc.y;
+    const bool diag = row0 == col0;  // both operands are the same panel: load it once
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < TS; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);  // one arrival per warp
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int nslab = static_cast<int>((p + FK - 1) / FK);
+
+    // producer state (used by thread 0 only)
+    int pstage = 0;
+    uint32_t pphase = 0;
+    const uint32_t stage_bytes = (diag ? 1u : 2u) * TPANEL_DBL * sizeof(double);
+    auto produce = [&](int t) {
+        mbar_wait(&empty_bar[pstage], pphase ^ 1);  // passes at once for the first use of a stage
+        mbar_arrive_expect_tx(&full_bar[pstage], stage_bytes);
+        double *dA = ring + static_cast<size_t>(pstage) * 2 * TPANEL_DBL;
+        // entries beyond n and loci beyond p are zero-filled by TMA: ragged edges add exact zeros
+#pragma unroll
+        for (int b = 0; b < FB / TBOX; ++b)
+            tma_load_2d(dA + b * TBOX_DBL, &tmap, &full_bar[pstage], static_cast<int32_t>(row0) + TBOX * b, t * FK);
+        if (!diag) {
+#pragma unroll
+            for (int b = 0; b < FB / TBOX; ++b)
+                tma_load_2d(dA + TPANEL_DBL + b * TBOX_DBL, &tmap, &full_bar[pstage], static_cast<int32_t>(col0) + TBOX * b, t * FK);
+        }
+        if (++pstage == TS) {
+            pstage = 0;
+            pphase ^= 1;
+        }
+    };
+    if (tid == 0)
+        for (int t = 0; t < TS - 1 && t < nslab; ++t) produce(t);
+
+    // ===================== consumers: 8 warps, warp tile 64 x 32 =====================
+    const int wm = warp >> 2, wn = warp & 3;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][4][4];  // [m16 tile][n8 tile][fragment]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[i][j][f] = 0.0;
+    // element (entry e of the box, row r) lives at r * 16 + (((e >> 1) ^ (r & 7)) << 1) + (e & 1); rows used by this
+    // thread are 8 ks + 2 fk (+ 1), so r & 7 = 2 fk (+ 1) for every ks
+    const int re = 2 * fk, ro = 2 * fk + 1;
+    const int c_lo_e = (((fr >> 1) ^ re) << 1) + (fr & 1), c_hi_e = ((((fr + 8) >> 1) ^ re) << 1) + (fr & 1);
+    const int c_lo_o = (((fr >> 1) ^ ro) << 1) + (fr & 1), c_hi_o = ((((fr + 8) >> 1) ^ ro) << 1) + (fr & 1);
+
+    const uint32_t ring_s = smem_u32(ring);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < nslab; ++s) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t pA = ring_s + static_cast<uint32_t>(stage) * 2 * TPANEL_DBL * 8;
+        const uint32_t pB = diag ? pA : pA + TPANEL_DBL * 8;
+#pragma unroll
+        for (int ks = 0; ks < FK / 8; ++ks) {
+            const int row_e = (ks * 8 + re) * TBOX, row_o = (ks * 8 + ro) * TBOX;
+            double a[4][4], b[4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const uint32_t box = pA + (wm * 4 + mi) * TBOX_DBL * 8;
+                a[mi][0] = lds_f64(box + (row_e + c_lo_e) * 8);
+                a[mi][1] = lds_f64(box + (row_e + c_hi_e) * 8);
+                a[mi][2] = lds_f64(box + (row_o + c_lo_o) * 8);
+                a[mi][3] = lds_f64(box + (row_o + c_hi_o) * 8);
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const uint32_t box = pB + (wn * 2 + (ni >> 1)) * TBOX_DBL * 8;
+                b[ni][0] = lds_f64(box + (row_e + ((ni & 1) ? c_hi_e : c_lo_e)) * 8);
+                b[ni][1] = lds_f64(box + (row_o + ((ni & 1) ? c_hi_o : c_lo_o)) * 8);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma_m16n8k8(acc[mi][ni], a[mi], b[ni]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);  // this warp has read the stage
+        if (tid == 0 && s + TS - 1 < nslab) produce(s + TS - 1);
+        if (++stage == TS) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+            const int64_t row = row0 + wm * 64 + mi * 16 + fr + 8 * hr;
+            if (row >= n) continue;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t col = col0 + wn * 32 + ni * 8 + 2 * fk + h;
+                    if (col < n) {
+                        double *dst = G + row + col * ldg;
+                        const double v = acc[mi][ni][2 * hr + h];
+                        *dst = accumulate ? (*dst + v) : v;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // G[i,j] = G[i,j] / denom for i <= j, then G[j,i] = G[i,j]: 32 x 32 tiles through shared memory so both the read
 // of the upper tile and the write of its mirror are coalesced.
 __global__ void __launch_bounds__(256) scale_mirror_kernel(double *__restrict__ G, int64_t n, int64_t ldg, double denom,
@@ -241,6 +400,29 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_
     int count;
     GRM_TRY(get_tile_list_f64(ctx, n, rank, world, &d_tiles, &count));
     if (count == 0) return GRM_CUDA_OK;
+    if (ctx->tune.f64_kernel != 1 && (ldz % 2) == 0 && (reinterpret_cast<uintptr_t>(dZ) % 16) == 0 && n < (1ll << 31) - 256 &&
+        p < (1ll << 31) - 64) {
+        // TMA-fed variant: needs 16-byte aligned operand rows (global strides are multiples of 16 bytes)
+        GrmEncodeTiledFn encode = nullptr;
+        GRM_TRY(grm_tmap_encoder(&encode));
+        CUtensorMap tmap;
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(p)};
+        cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ldz) * sizeof(double)};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(TBOX), static_cast<cuuint32_t>(FK)};
+        cuuint32_t estr[2] = {1u, 1u};
+        const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(dZ), gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            grm_set_error("cuTensorMapEncodeTiled (FP64 SYRK operand) failed with CUresult %d", static_cast<int>(r));
+            return GRM_CUDA_ERR_CUDA;
+        }
+        GRM_TRY(grm_func_smem(ctx, reinterpret_cast<const void *>(syrk_f64_tma_kernel), F64T_SMEM));
+        syrk_f64_tma_kernel<<<count, 256, F64T_SMEM, ctx->stream>>>(tmap, n, p, d_tiles, d_G, ldg, accumulate);
+        GRM_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        return GRM_CUDA_OK;
+    }
     GRM_TRY(grm_func_smem(ctx, reinterpret_cast<const void *>(syrk_f64_kernel), F64_SMEM));
     syrk_f64_kernel<<<count, 256, F64_SMEM, ctx->stream>>>(dZ, n, p, ldz, d_tiles, d_G, ldg, accumulate);
     GRM_CUDA_TRY(cudaGetLastError());

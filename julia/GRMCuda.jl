@@ -16,9 +16,9 @@ import StatsBase
 
 const LIB = get(ENV, "GRM_CUDA_LIB", joinpath(@__DIR__, "..", "genomicbreedingcore.jl_b200", "libgrm_cuda.so"))
 
-# mirrors of grm_cuda_options / grm_cuda_info (include/grm_cuda.h)
+# mirrors of grm_cuda_options / grm_cuda_info (include/grm_cuda.h, ABI 0.2.0: 80 and 120 bytes)
 Base.@kwdef mutable struct Options
-    struct_size::Int32 = 64
+    struct_size::Int32 = 80
     path::Int32 = 0
     denominator::Int32 = 0
     max_iter::Int32 = 1000
@@ -31,10 +31,14 @@ Base.@kwdef mutable struct Options
     chunk_loci::Int64 = 0
     maf::Float64 = 0.0
     max_locus_sparsity::Float64 = 1.0
+    distributed::Int32 = 0
+    input_slab::Int32 = 0
+    output_mode::Int32 = 0
+    reserved0::Int32 = 0
 end
 
 Base.@kwdef mutable struct Info
-    struct_size::Int32 = 80
+    struct_size::Int32 = 120
     path::Int32 = 0
     denominator::Int32 = 0
     repair_iters::Int32 = 0
@@ -51,6 +55,15 @@ Base.@kwdef mutable struct Info
     ms_total::Float32 = 0
     kernel_launches::Int32 = 0
     loci_kept::Int32 = 0
+    ms_exchange::Float32 = 0
+    ms_gather::Float32 = 0
+    ms_host_busy::Float32 = 0
+    ingest::Int32 = 0
+    host_threads::Int32 = 0
+    world::Int32 = 1
+    exchange_waves::Int32 = 0
+    syrk_window::Int32 = 0
+    reserved0::Int32 = 0
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -73,7 +86,11 @@ function throwstatus(st::Int32)
         # the reference fails with a MethodError(convert, (Float64, missing)) inside a TaskFailedException (calc.jl:127)
         throw(MethodError(convert, (Float64, missing)))
     elseif st in (1, 3, 4, 5, 6, 9, 10)
-        throw(ArgumentError(msg))
+        throw(ArgumentError(msg))                                                # 4: "The input matrix is not symmetric." (calc.jl:44)
+    elseif st == 11
+        throw(ErrorException(msg))                                               # filter.jl:363-365
+    elseif st == 13
+        throw(ErrorException("libgrm_cuda communicator: $msg"))
     elseif st == 12
         throw(LinearAlgebra.PosDefException(1))                                  # what cholesky / MvNormal throw
     else
@@ -81,30 +98,76 @@ function throwstatus(st::Int32)
     end
 end
 
-# Matrix{Union{Float64,Missing}} has no zero-copy Ptr{Float64} view (payloads and selector bytes are stored
-# separately), so the shim makes one pass: missing -> NaN.  A Matrix{Float64} is passed as is.
+# ---- genomes.allele_frequencies as Julia stores it ----------------------------------------------------------------
+# `Matrix{Union{Float64,Missing}}` (src/all_structs.jl:66) is an isbits-Union array: n*p Float64 payloads followed, in the
+# same allocation, by n*p selector ("type tag") bytes.  The library reads both in place (grm_cuda_*_union): no
+# conversion pass, no copy, no pinning on this side.  Returns (payload pointer, selector pointer or C_NULL, selector
+# value of a Float64 cell).
+function unionptrs(A::Matrix{Union{Float64,Missing}})
+    T = eltype(A)
+    tag = Int32(findfirst(==(Float64), Base.uniontypes(T)) - 1)      # component index of Float64 in the union
+    payload = Ptr{Float64}(pointer(A))
+    sel = @static if VERSION >= v"1.11"
+        mem = A.ref.mem                                                # Memory{T}: data, then the selector bytes
+        off = (UInt(pointer(A)) - UInt(pointer(mem))) ÷ sizeof(Float64)
+        ccall(:jl_genericmemory_typetagdata, Ptr{UInt8}, (Any,), mem) + off
+    else
+        ccall(:jl_array_typetagdata, Ptr{UInt8}, (Any,), A)
+    end
+    (payload, sel, tag)
+end
+unionptrs(A::Matrix{Float64}) = (pointer(A), Ptr{UInt8}(C_NULL), Int32(0))   # NaN then stands for `missing`
+
+# anything else (views, other element types) is materialised once; the two concrete layouts above are zero-copy
+hostmatrix(A::Matrix{Union{Float64,Missing}}) = A
+hostmatrix(A::Matrix{Float64}) = A
+hostmatrix(A::AbstractMatrix) = convert(Matrix{Union{Float64,Missing}}, A)
+
+# dense Float64 copy (missing -> NaN) for the entry points that take plain double* (distances)
 dense(A::Matrix{Float64}) = A
 dense(A::AbstractMatrix) = Float64[ismissing(x) ? NaN : Float64(x) for x in A]
 
-function rungrm(genomes::Genomes, centred::Bool, ploidy::Int64, max_iter::Int64, verbose::Bool)::GRM
+# ---- multi-GPU: one Julia process per GPU (Distributed.jl / MPI.jl), the exchange lives inside the library -----------
+# On ONE process:  id = GRMCuda.uniqueid();  hand the 128 bytes to the others (remotecall, MPI.Bcast!, a file);  on
+# EVERY process:  GRMCuda.initcomm!(id, rank, world)  (0-based rank).  Afterwards grmsimple / grmploidyaware with
+# `distributed = true` are collective calls: each process passes the same Genomes (or, with `slab = true`, only its own
+# loci range  L*rank+1 : min(p, L*(rank+1)),  L = cld(p, world))  and every process receives the complete GRM.
+function uniqueid()::Vector{UInt8}
+    id = Vector{UInt8}(undef, 128)
+    st = ccall((:grm_cuda_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id)
+    st == 0 || throwstatus(st)
+    id
+end
+
+function initcomm!(id::Vector{UInt8}, rank::Integer, world::Integer)
+    length(id) == 128 || throw(ArgumentError("the communicator id is 128 bytes"))
+    st = ccall((:grm_cuda_comm_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), context(), id, Int32(rank), Int32(world))
+    st == 0 || throwstatus(st)
+    nothing
+end
+
+function rungrm(genomes::Genomes, centred::Bool, ploidy::Int64, max_iter::Int64, verbose::Bool;
+                distributed::Bool = false, slab::Bool = false, total_loci::Int64 = 0)::GRM
     if !checkdims(genomes)
         throw(ArgumentError("The Genomes struct is corrupted ☹."))          # calc.jl:118-120, :191-193
     end
-    A = dense(genomes.allele_frequencies)
+    A = hostmatrix(genomes.allele_frequencies)
     n, p = size(A)
+    ptotal = (distributed && slab) ? total_loci : p
     grm = GRM(genomes.entries, genomes.loci_alleles, Matrix{Float64}(undef, n, n))   # calc.jl:123, :196
     G = grm.genomic_relationship_matrix
-    opts = Options(max_iter = Int32(max_iter))
+    opts = Options(max_iter = Int32(max_iter), distributed = Int32(distributed), input_slab = Int32(distributed && slab))
     info = Info()
+    payload, sel, tag = unionptrs(A)
     st = GC.@preserve A G begin
         if centred
-            ccall((:grm_cuda_ploidyaware, LIB), Int32,
-                  (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int32, Ptr{Float64}, Int64, Ref{Options}, Ref{Info}),
-                  context(), A, n, p, n, Int32(ploidy), G, n, opts, info)
+            ccall((:grm_cuda_ploidyaware_union, LIB), Int32,
+                  (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Int32, Int64, Int64, Int64, Int32, Ptr{Float64}, Int64, Ref{Options}, Ref{Info}),
+                  context(), payload, sel, tag, n, ptotal, n, Int32(ploidy), G, n, opts, info)
         else
-            ccall((:grm_cuda_simple, LIB), Int32,
-                  (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Options}, Ref{Info}),
-                  context(), A, n, p, n, G, n, opts, info)
+            ccall((:grm_cuda_simple_union, LIB), Int32,
+                  (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Int32, Int64, Int64, Int64, Ptr{Float64}, Int64, Ref{Options}, Ref{Info}),
+                  context(), payload, sel, tag, n, ptotal, n, G, n, opts, info)
         end
     end
     st == 0 || throwstatus(st)
@@ -117,11 +180,12 @@ function rungrm(genomes::Genomes, centred::Bool, ploidy::Int64, max_iter::Int64,
     grm
 end
 
-grmsimple(genomes::Genomes; max_iter::Int64 = 1_000, verbose::Bool = false)::GRM =
-    rungrm(genomes, false, 0, max_iter, verbose)
+# the reference's signatures; the keyword-only extras (`distributed`, `slab`, `total_loci`) select the multi-GPU call
+grmsimple(genomes::Genomes; max_iter::Int64 = 1_000, verbose::Bool = false, kw...)::GRM =
+    rungrm(genomes, false, 0, max_iter, verbose; kw...)
 
-grmploidyaware(genomes::Genomes; ploidy::Int64 = 2, max_iter::Int64 = 1_000, verbose::Bool = false)::GRM =
-    rungrm(genomes, true, ploidy, max_iter, verbose)
+grmploidyaware(genomes::Genomes; ploidy::Int64 = 2, max_iter::Int64 = 1_000, verbose::Bool = false, kw...)::GRM =
+    rungrm(genomes, true, ploidy, max_iter, verbose; kw...)
 
 function inflatediagonals!(X::Matrix{Float64}; max_iter::Int64 = 1_000, verbose::Bool = false)::Nothing
     if size(X, 1) != size(X, 2)
