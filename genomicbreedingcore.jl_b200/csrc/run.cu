@@ -320,7 +320,9 @@ struct OutCopier {
     }
 
     // ready: event on which dG is complete.  Uses ctx->copy_stream, ctx->copy_done[] and the pinned ring.
-    void start(grm_cuda_ctx *ctx, const double *dG, int64_t ldG, int64_t n, double *G, int64_t ldg, cudaEvent_t ready) {
+    // `n` rows (contiguous) x `ncols` columns: the dense matrix (n x n) or a rank's packed tiles (65536 x count).
+    void start(grm_cuda_ctx *ctx, const double *dG, int64_t ldG, int64_t n, int64_t ncols, double *G, int64_t ldg,
+               cudaEvent_t ready) {
         active = true;
         th = std::thread([=]() {
             cudaError_t e = cudaSetDevice(ctx->device);
@@ -328,10 +330,10 @@ struct OutCopier {
             cudaStream_t cs = ctx->copy_stream;
             if ((e = cudaStreamWaitEvent(cs, ready, 0)) != cudaSuccess) return fail("cudaStreamWaitEvent", e);
             const int64_t cols = std::max<int64_t>(1, static_cast<int64_t>(ctx->pin_cap / (static_cast<size_t>(n) * sizeof(double))));
-            const int64_t nchunks = (n + cols - 1) / cols;
+            const int64_t nchunks = (ncols + cols - 1) / cols;
             auto issue = [&](int64_t c) -> cudaError_t {
                 const int s = static_cast<int>(c % RING);
-                const int64_t c0 = c * cols, l = std::min(cols, n - c0);
+                const int64_t c0 = c * cols, l = std::min(cols, ncols - c0);
                 cudaError_t r = cudaMemcpy2DAsync(ctx->pin[s], n * sizeof(double), dG + c0 * ldG, ldG * sizeof(double),
                                                   n * sizeof(double), static_cast<size_t>(l), cudaMemcpyDeviceToHost, cs);
                 if (r != cudaSuccess) return r;
@@ -342,7 +344,7 @@ struct OutCopier {
             for (int64_t c = 0; c < nchunks; ++c) {
                 const int s = static_cast<int>(c % RING);
                 if ((e = cudaEventSynchronize(ctx->copy_done[s])) != cudaSuccess) return fail("cudaEventSynchronize", e);
-                const int64_t c0 = c * cols, l = std::min(cols, n - c0);
+                const int64_t c0 = c * cols, l = std::min(cols, ncols - c0);
                 CopyJob job{static_cast<const double *>(ctx->pin[s]), G + c0 * ldg, n, ldg, l};
                 grm_pool_run(ctx->pool, copy_job, &job);
                 if (c + RING < nchunks && (e = issue(c + RING)) != cudaSuccess) return fail("cudaMemcpy2DAsync", e);
@@ -659,7 +661,7 @@ int32_t Run::int8_path(int32_t m, double *dG, int64_t ldG, double **d_tiles_out,
         int waves = ctx->tune.ksplit_waves > 0 ? ctx->tune.ksplit_waves : (world > 1 ? 4 : 1);
         waves = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(waves, 8), tmax)));
         inf.exchange_waves = waves;
-        const bool via_nccl = ctx->tune.exchange != 2;
+        const int exchange = ctx->tune.exchange;  // 0: one launch per wave + NCCL; 1: streamed + NCCL; 2: streamed + copy engines
         GRM_TRY(ctx->packed.reserve(static_cast<size_t>(tmax) * world * 65536 * sizeof(int32_t)));
         int32_t *d_packed = ctx->packed.as<int32_t>();
         cudaStream_t cs = ctx->comm_stream;
@@ -670,8 +672,26 @@ int32_t Run::int8_path(int32_t m, double *dG, int64_t ldG, double **d_tiles_out,
         uint32_t *d_done = ctx->progress.as<uint32_t>() + 512;  // clear of the K-window progress words
         uint32_t *d_epoch = d_done + 16;
         GRM_CUDA_TRY(cudaMemsetAsync(d_done, 0, 8 * sizeof(uint32_t), st));
-        if (via_nccl) {
-            // exchange by NCCL reduce-scatter (int32 sum): its kernels need SMs, so the SYRK leaves `comm_ctas` of them free
+        if (exchange == 0) {
+            // default: one launch per wave; the reduce-scatter (int32 sum, exact) and the finalisation of wave w go to the
+            // communication stream and slot in next to the launch of wave w + 1
+            GRM_TRY(ctx->reduced.reserve(static_cast<size_t>(tmax) * 65536 * sizeof(int32_t)));
+            int32_t *d_red = ctx->reduced.as<int32_t>();
+            for (int w = 0; w < waves; ++w) {
+                int64_t s0, s1;
+                grm_packed_wave_range(n, world, waves, w, &s0, &s1);
+                GRM_TRY(grm_syrk_i8_packed_wave(ctx, d_codes, n, pk, ldc, world, waves, w, d_packed));
+                GRM_CUDA_TRY(cudaEventRecord(ctx->wave_ev[w], st));
+                if (s1 <= s0) continue;
+                GRM_CUDA_TRY(cudaStreamWaitEvent(cs, ctx->wave_ev[w], 0));
+                GRM_TRY(grm_comm_reduce_scatter(ctx, d_packed + static_cast<size_t>(world) * s0 * 65536, d_red + s0 * 65536,
+                                                static_cast<size_t>(s1 - s0) * 65536, GRM_DT_I32, cs));
+                GRM_TRY(grm_finalize_tiles_range(ctx, d_red, n, sc[0], sc[1], sc[2], sc[3], d_u, nullptr, 0, d_gt, rank, world, s0,
+                                                 s1 - s0, cs));
+            }
+            GRM_CUDA_TRY(cudaEventRecord(ev[3], st));
+        } else if (exchange == 1) {
+            // streamed, NCCL reduce-scatter: its kernels need SMs, so the SYRK leaves `comm_ctas` of them free
             GRM_TRY(ctx->reduced.reserve(static_cast<size_t>(tmax) * 65536 * sizeof(int32_t)));
             int32_t *d_red = ctx->reduced.as<int32_t>();
             GRM_CUDA_TRY(cudaEventRecord(ctx->wave_ev[9], st));
@@ -690,7 +710,7 @@ int32_t Run::int8_path(int32_t m, double *dG, int64_t ldG, double **d_tiles_out,
                                                  s1 - s0, cs));
             }
         } else {
-            // exchange by the COPY ENGINES over NVLink peer mappings (tuning "exchange" = 2) — no SM is taken from the
+            // streamed, exchange by the COPY ENGINES over NVLink peer mappings (tuning "exchange" = 2) — no SM is taken from the
             // contraction, but with every GPU sending to every other at once the engines move only 80 GB/s per sender in
             // 16 MiB pieces and ~340 GB/s in 128 MiB ones (profiles/p2p_copy_engine_probe_r2.jsonl) against ~530 GB/s for
             // NCCL's reduce-scatter, so it is not the default.  Rank r's
@@ -885,21 +905,27 @@ int32_t Run::f64_path(double *dG, int64_t ldG, double **d_tiles_out, int64_t *p_
 // ---------------------------------------------------------------------------------------------------------------
 // inflatediagonals! with the matrix replicated on every rank (calc.jl:41-70): the loop test of round t only looks at
 // X with its diagonal inflated t times, and its two halves — det(X_t) (LU) and isposdef(X_t) (Cholesky) — are independent
-// of each other.  So the probes are dealt out as (round, half) tasks: rank 2i takes the determinant of round base + i,
-// rank 2i + 1 its Cholesky; a batch of probes costs max(LU, Cholesky) of wall time and covers world / 2 rounds.  Each
-// probe performs the arithmetic of the sequential loop and the decision is taken on the all-gathered results, hence
-// the same outcome on every rank as the sequential loop.  (One rank: both halves, with the reference's short-circuit.)
+// of each other.  From 4 ranks on the probes are dealt out as (round, half) tasks: rank 2i takes the determinant of round
+// base + i, rank 2i + 1 its Cholesky; a batch of probes costs max(LU, Cholesky) of wall time and covers world / 2 rounds.
+// With fewer ranks every rank probes a whole round (both halves, with the reference's short-circuit).  Each probe
+// performs the arithmetic of the sequential loop and the decision is taken on the all-gathered results, hence the same
+// outcome on every rank as the sequential loop.
 // ---------------------------------------------------------------------------------------------------------------
 int32_t Run::repair_parallel(double *dG, int64_t ldG) {
     const double eps = DBL_EPSILON;
-    const int per_batch = world >= 2 ? world / 2 : 1;  // rounds evaluated per batch
+    // From 4 ranks on a round is split over two ranks (a batch costs max(LU, Cholesky) and covers world / 2 rounds).  With
+    // 2 or 3 ranks each rank probes a whole round of its own (LU, then Cholesky unless det < eps already decides): one
+    // batch of LU + Cholesky covers `world` rounds, which beats two LU-bound batches of one round each (measured on C3, 2
+    // GPUs: 587 ms split against ~400 ms whole).
+    const bool split = world >= 4;
+    const int per_batch = split ? world / 2 : world;  // rounds evaluated per batch
     int64_t base = 0;
     int32_t iters = -1;
     double maxabs = 0.0;
     while (iters < 0) {
-        const int64_t r = base + (world >= 2 ? rank / 2 : 0);
-        const int which = world >= 2 ? ((rank & 1) ? 2 : 1) : 3;
-        const bool idle = world >= 2 && rank >= 2 * per_batch;  // the odd rank out
+        const int64_t r = base + (split ? rank / 2 : rank);
+        const int which = split ? ((rank & 1) ? 2 : 1) : 3;
+        const bool idle = split && rank >= 2 * per_batch;  // the odd rank out
         double mine[4] = {NAN, -1.0, 0.0, 0.0};
         if (!idle && r <= o.max_iter) {
             double det = NAN, mx = 0.0;
@@ -913,8 +939,9 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
         }
         std::vector<double> all;
         GRM_TRY(gather_f64(mine, 4, all));
-        auto det_of = [&](int i) { return world >= 2 ? all[4 * (2 * i)] : all[0]; };
-        auto pd_of = [&](int i) { return world >= 2 ? all[4 * (2 * i + 1) + 1] : all[1]; };
+        auto det_of = [&](int i) { return split ? all[4 * (2 * i)] : all[4 * i]; };
+        auto pd_of = [&](int i) { return split ? all[4 * (2 * i + 1) + 1] : all[4 * i + 1]; };
+        auto chol_rank = [&](int i) { return split ? 2 * i + 1 : i; };  // the rank whose last factorisation is chol(round i)
         if (base == 0) {
             const uint32_t flags = static_cast<uint32_t>(all[2]);
             maxabs = all[3];
@@ -923,7 +950,7 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
                 return GRM_CUDA_ERR_NOT_SYMMETRIC;
             }
             if (det_of(0) > eps && pd_of(0) == 1.0) {  // calc.jl:49-51
-                if (rank == (world >= 2 ? 1 : 0)) ctx->factor_n = n;  // the rank that holds chol(X)
+                if (rank == chol_rank(0)) ctx->factor_n = n;
                 inf.repair_iters = 0;
                 inf.eps_total = 0.0;
                 return GRM_CUDA_OK;
@@ -944,7 +971,7 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
             const bool need = (det < eps) || (pd != 1.0);
             if (!need || t >= o.max_iter) {
                 iters = static_cast<int32_t>(t);
-                if (!need && rank == (world >= 2 ? 2 * i + 1 : 0)) ctx->factor_n = n;  // this rank's Cholesky is of the result
+                if (!need && rank == chol_rank(i)) ctx->factor_n = n;  // this rank's Cholesky is of the result
             }
         }
         base += per_batch;
@@ -1111,7 +1138,8 @@ int32_t Run::go() {
     // O(n^3) factorisations run; if a round of inflation happened, the n diagonal values are copied again afterwards.
     const bool want_copy = out_host && G != nullptr;
     // a pageable dense result leaves through the helper thread (OutCopier); pinned memory is copied to directly
-    const bool via_ring = want_copy && !out_tiles && !is_pinned(G);
+    const int64_t tiles_owned = dist ? grm_cuda_tile_count(n, rank, world) : grm_cuda_tile_count(n, o.rank, o.world);
+    const bool via_ring = want_copy && !is_pinned(G) && (!out_tiles || tiles_owned > 0);
     OutCopier drain;
     bool bulk_started = false;
     auto copy_out = [&](cudaStream_t s) -> int32_t {
@@ -1130,9 +1158,12 @@ int32_t Run::go() {
     if (via_ring) {
         GRM_TRY(ensure_pool(ctx, world));
         GRM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));  // the ring and its events belong to the finished ingest
-        GRM_TRY(ensure_ring(ctx, std::max<size_t>(ctx->pin_cap, std::max<size_t>(32u << 20, static_cast<size_t>(n) * sizeof(double)))));
+        GRM_TRY(ensure_ring(ctx, std::max<size_t>(ctx->pin_cap, std::max<size_t>(32u << 20, static_cast<size_t>(out_tiles ? 65536 : n) * sizeof(double)))));
         GRM_CUDA_TRY(cudaEventRecord(ev[7], st));
-        drain.start(ctx, dG, ldG, n, G, ldg, ev[4]);
+        if (out_tiles)
+            drain.start(ctx, d_tiles, 65536, 65536, tiles_owned, G, 65536, ev[4]);
+        else
+            drain.start(ctx, dG, ldG, n, n, G, ldg, ev[4]);
         bulk_started = true;
     } else if (want_copy && do_repair) {
         GRM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ev[4], 0));

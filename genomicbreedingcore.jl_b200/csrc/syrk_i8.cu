@@ -973,25 +973,23 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
 // Exchange volume 4 n^2 / 2 bytes per GPU instead of n p for the all-gather of the codes — the better choice whenever
 // p > 4 n (BASELINE C2, C3).
 //
-// Waves: the slots 0 .. tiles_max-1 every rank owns are cut into `waves` ranges [s_w, s_{w+1}) of decreasing size; wave
-// w of the packed buffer is the contiguous block [world][s_{w+1} - s_w][256 x 256] starting at element
-// world * s_w * 65536, so the reduce-scatter of wave w is one plain call.  ONE persistent launch contracts all tiles in
-// wave order (grm_syrk_i8_packed_stream) and counts finished tiles per wave; a gate kernel on the communication stream
-// (grm_wave_gate) releases the reduce-scatter of wave w as soon as its tiles are stored, while the tensor cores are
-// already deep in the later waves (run.cu).  The launch leaves `comm_ctas` SMs free: the persistent grid would
-// otherwise own every SM and NCCL's CTAs could only run between launches.  waves = 1 is the layout
+// Waves: the slots 0 .. tiles_max-1 every rank owns are cut into `waves` equal ranges [s_w, s_{w+1}); wave w of the packed
+// buffer is the contiguous block [world][s_{w+1} - s_w][256 x 256] starting at element world * s_w * 65536, so the
+// reduce-scatter of wave w is one plain call.  Default flow (run.cu): one launch per wave (grm_syrk_i8_packed_wave), the
+// reduce-scatter of wave w on a second stream next to the launch of wave w + 1.  Streamed flow (tuning "exchange" = 1 / 2):
+// ONE persistent launch contracts all tiles in wave order (grm_syrk_i8_packed_stream) and counts finished tiles per
+// wave; a gate kernel on the communication stream (grm_wave_gate) releases the exchange of wave w as soon as its tiles
+// are stored.  Measured on C3 / 8 GPUs the streamed flow loses: the persistent grid owns every SM, so NCCL's kernels
+// only run once it retires (10.4 ms per step against 9.85), reserving SMs for a CTA-capped NCCL costs more than it hides
+// (11.3 ms), and the copy engines are slow when all GPUs send at once (10.3 ms).  waves = 1 is the layout
 // [world][tiles_max][256 x 256] of the single-exchange form.
 // ---------------------------------------------------------------------------------------------------------------
 void grm_packed_wave_range(int64_t n, int32_t world, int32_t waves, int32_t w, int64_t *s0, int64_t *s1) {
-    // wave w gets (waves - w) shares: the exchange of the LAST wave is the one nothing can hide, so it is the smallest
+    // equal waves: each is a kernel launch of its own in the default flow, so each should fill the CTA pairs as evenly as
+    // the others (shrinking waves were tried with the single-launch flow and do not pay there either, profiles/README.md)
     const int64_t tmax = grm_cuda_packed_tiles_max(n, world);
-    const int64_t total = static_cast<int64_t>(waves) * (waves + 1) / 2;
-    auto cut = [&](int64_t k) {  // slots before wave k
-        const int64_t shares = k * waves - k * (k - 1) / 2;
-        return tmax * shares / total;
-    };
-    *s0 = cut(w);
-    *s1 = w + 1 == waves ? tmax : cut(w + 1);
+    *s0 = tmax * w / waves;
+    *s1 = tmax * (w + 1) / waves;
 }
 
 namespace {

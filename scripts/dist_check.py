@@ -110,8 +110,8 @@ def main():
     # exchange waves: any number gives the same bits
     A = synth.dosage(1300, 6000, 4, seed=3)
     ref, _ = grm_call(A, 4, ctx=ctx, skip_repair=True)
-    # ... through either transport: 0 = NCCL reduce-scatter (default), 2 = copy engines into peer-mapped receive buffers
-    for exchange in (0, 2):
+    # ... through every exchange flow: 0 = one launch per wave + NCCL (default), 1 = streamed + NCCL, 2 = streamed + copy engines
+    for exchange in (0, 1, 2):
         ctx.set_tuning("exchange", exchange)
         for waves in (1, 2, 3, 8):
             ctx.set_tuning("ksplit_waves", waves)

@@ -56,7 +56,7 @@ def test_world_of_one_reproduces_the_plain_call(ctx1, kind, n, p, gm, ploidy):
     assert np.array_equal(G, ref) if kind == "dosage" else relerr(G, ref) <= 1e-13
     assert np.array_equal(G, G.T)
     if kind == "dosage" and p > 4 * n:
-        for exchange in (0, 2):  # NCCL reduce-scatter / copy engines into the (here: own) peer-mapped buffer
+        for exchange in (0, 1, 2):  # per-wave launches + NCCL (default) / streamed + NCCL / streamed + copy engines
             ctx1.set_tuning("exchange", exchange)
             for waves in (1, 3, 8):
                 ctx1.set_tuning("ksplit_waves", waves)
