@@ -148,11 +148,19 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->comm) grm_comm_destroy(ctx);
     if (ctx->cusolver) grm_cusolver_destroy(ctx->cusolver);
+    for (auto &h : ctx->cusolver_lane)
+        if (h) grm_cusolver_destroy(h);
+    for (auto &x : ctx->lane_stream)
+        if (x) cudaStreamDestroy(x);
+    for (auto &e : ctx->lane_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->lane_pin) cudaFreeHost(ctx->lane_pin);
     if (ctx->pool) grm_pool_destroy(ctx->pool);
     for (auto &pp : ctx->pin)
         if (pp) cudaFreeHost(pp);
     DevBuf *bufs[] = {&ctx->codes, &ctx->colsum, &ctx->flags, &ctx->q, &ctx->w, &ctx->u, &ctx->stats, &ctx->partials,
-                      &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->stage[2], &ctx->stage[3], &ctx->lu, &ctx->lu2,
+                      &ctx->G, &ctx->C, &ctx->stage[0], &ctx->stage[1], &ctx->stage[2], &ctx->stage[3], &ctx->lu, &ctx->lu2, &ctx->lu3, &ctx->lane_work[0], &ctx->lane_work[1], &ctx->lane_ipiv[0],
+                      &ctx->lane_ipiv[1],
                       &ctx->lu_work, &ctx->ipiv, &ctx->misc, &ctx->misc2, &ctx->planes, &ctx->rT, &ctx->cnt, &ctx->keep,
                       &ctx->progress, &ctx->packed, &ctx->reduced, &ctx->gtiles, &ctx->gtiles_all, &ctx->codes_all,
                       &ctx->cons, &ctx->tiles_i8.buf, &ctx->tiles_i8_2cta.buf, &ctx->tiles_f64.buf, &ctx->tiles_packed.buf,
@@ -206,6 +214,7 @@ static int *tuning_slot(GrmTuning &t, const char *key) {
         {"ingest", &GrmTuning::ingest},             {"ksplit_waves", &GrmTuning::ksplit_waves},
         {"f64_kernel", &GrmTuning::f64_kernel},     {"ring_mb", &GrmTuning::ring_mb},
         {"comm_ctas", &GrmTuning::comm_ctas},       {"exchange", &GrmTuning::exchange},
+        {"repair", &GrmTuning::repair},
     };
     for (const Entry &e : table)
         if (!strcmp(e.name, key)) return &(t.*(e.field));

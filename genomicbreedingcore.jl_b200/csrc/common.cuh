@@ -61,6 +61,7 @@ struct GrmTuning {
     int ingest = 0;         // host input: 0 auto, 1 stream FP64 and pack on the device, 2 quantise on the host
     int ksplit_waves = 0;   // K-split exchange waves (reduce-scatter of wave w under the SYRK of the later waves); 0 = auto
     int comm_ctas = 0;      // > 0: cap NCCL's CTAs (and leave as many SMs free during the K-split SYRK when NCCL carries it)
+    int repair = 0;         // single-GPU inflatediagonals!: 0 auto (two rounds evaluated concurrently from n = 3072), 1 sequential
     int exchange = 0;       // K-split partial tiles: 0 auto = NCCL reduce-scatter, 2 = copy engines into peer-mapped buffers
     int f64_kernel = 0;     // FP64 SYRK operand staging: 0 auto (TMA when aligned), 1 register-staged
     int ring_mb = 0;        // bytes (MiB) of one pinned ingest slot; 0 = automatic
@@ -88,8 +89,14 @@ struct grm_cuda_ctx {
     cudaEvent_t wave_ev[16] = {};        // K-split waves: SYRK of wave w finished / exchange of wave w finished
     cudaEvent_t copy_done[4] = {}, stage_free[4] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
+    // concurrent lanes of the speculative repair (repair.cu): extra handles, streams, events, pinned result buffers
+    void *cusolver_lane[2] = {nullptr, nullptr};
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_ev[4] = {};
+    void *lane_pin = nullptr;
+    size_t lane_pin_cap = 0;
     // workspaces (grow-only; reused across calls so a warm call does no cudaMalloc)
-    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[4], lu, lu2, lu_work, ipiv, misc, misc2, planes, rT, cnt,
+    DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[4], lu, lu2, lu3, lu_work, lane_work[2], lane_ipiv[2], ipiv, misc, misc2, planes, rT, cnt,
         keep, progress, packed, reduced, gtiles, gtiles_all, codes_all, cons;
     TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed, tiles_wide, tiles_f64_all;
     int64_t factor_n = -1;  // >= 0: ctx->lu holds the upper Cholesky factor of the n x n matrix the last repair returned

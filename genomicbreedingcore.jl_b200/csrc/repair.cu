@@ -17,6 +17,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <string>
+#include <thread>
+
 #include "common.cuh"
 
 #define GRM_SOLVER_TRY(expr)                                                                  \
@@ -248,6 +251,266 @@ static int32_t repair_setup(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx
     return GRM_CUDA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Speculative repair on ONE GPU.  The loop test of round t only looks at X with its diagonal inflated t times, so the
+// tests of rounds t and t + 1 are independent — what the multi-GPU probes exploit across GPUs.  cuSOLVER's getrf runs at
+// about half of dgemm's rate (its panel phases leave the GPU mostly idle), so here det(t), det(t + 1) and the Cholesky of
+// round t + 1 are put on three streams with a handle, a work matrix and a workspace each and evaluated CONCURRENTLY: the
+// panels of one factorisation hide under the trailing updates of the others.  Same routines on the same inputs as the
+// sequential loop, hence the same values and the same decisions; X itself stays untouched until the outcome is known.
+// The Cholesky of round t is evaluated on demand (only when !(det_t < eps): for a large GRM the determinant is what fails).
+// Results travel through pinned host memory: a copy into pageable memory would block the host and serialise the lanes.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Lane {
+    cusolverDnHandle_t h = nullptr;
+    cudaStream_t stream = nullptr;
+    double *mat = nullptr, *work = nullptr;
+    int lwork = 0;
+    int *d_ipiv = nullptr, *d_info = nullptr;
+    double *d_diag = nullptr;
+    // pinned results
+    double *h_diag = nullptr;
+    int *h_ipiv = nullptr, *h_info = nullptr;
+};
+
+int32_t lane_copy_in(grm_cuda_ctx *ctx, const Lane &l, const double *X, int64_t n, int64_t ldx, int rounds, double eps0) {
+    const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
+    copy_matrix_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, l.stream>>>(X, n, ldx, l.mat);
+    GRM_CUDA_TRY(cudaGetLastError());
+    if (rounds > 0) {
+        diag_add_rounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, l.stream>>>(l.mat, n, n, eps0, rounds);
+        GRM_CUDA_TRY(cudaGetLastError());
+        }
+    return GRM_CUDA_OK;
+}
+
+int32_t lane_launch_det(grm_cuda_ctx *ctx, const Lane &l, const double *X, int64_t n, int64_t ldx, int rounds, double eps0) {
+    GRM_TRY(lane_copy_in(ctx, l, X, n, ldx, rounds, eps0));
+    GRM_SOLVER_TRY(cusolverDnDgetrf(l.h, static_cast<int>(n), static_cast<int>(n), l.mat, static_cast<int>(n), l.work, l.d_ipiv,
+                                    l.d_info));
+    diag_extract_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, l.stream>>>(l.mat, n, l.d_diag);
+    GRM_CUDA_TRY(cudaGetLastError());
+    GRM_CUDA_TRY(cudaMemcpyAsync(l.h_diag, l.d_diag, n * sizeof(double), cudaMemcpyDeviceToHost, l.stream));
+    GRM_CUDA_TRY(cudaMemcpyAsync(l.h_ipiv, l.d_ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, l.stream));
+    GRM_CUDA_TRY(cudaMemcpyAsync(l.h_info, l.d_info, sizeof(int), cudaMemcpyDeviceToHost, l.stream));
+    return GRM_CUDA_OK;
+}
+
+int32_t lane_launch_chol(grm_cuda_ctx *ctx, const Lane &l, const double *X, int64_t n, int64_t ldx, int rounds, double eps0) {
+    GRM_TRY(lane_copy_in(ctx, l, X, n, ldx, rounds, eps0));
+    GRM_SOLVER_TRY(cusolverDnDpotrf(l.h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), l.mat, static_cast<int>(n), l.work, l.lwork,
+                                    l.d_info));
+    GRM_CUDA_TRY(cudaMemcpyAsync(l.h_info, l.d_info, sizeof(int), cudaMemcpyDeviceToHost, l.stream));
+    return GRM_CUDA_OK;
+}
+
+// Julia's det(lu(X; check = false)) from a finished lane (the stream has been synchronised)
+int32_t lane_det_value(const Lane &l, int64_t n, double *out) {
+    if (*l.h_info < 0) {
+        grm_set_error("cusolverDnDgetrf: illegal argument %d", -*l.h_info);
+        return GRM_CUDA_ERR_CUDA;
+    }
+    if (*l.h_info > 0) {
+        *out = 0.0;
+        return GRM_CUDA_OK;
+    }
+    volatile double P = 1.0;  // one IEEE binary64 rounding per multiply, no reassociation
+    int swaps = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        P = P * l.h_diag[i];
+        if (static_cast<int64_t>(l.h_ipiv[i]) != i + 1) ++swaps;
+    }
+    *out = (swaps & 1) ? -P : P;
+    return GRM_CUDA_OK;
+}
+
+int32_t lanes_setup(grm_cuda_ctx *ctx, int64_t n, Lane (&L)[3]) {
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->cusolver_lane[i]) {
+            cusolverDnHandle_t h;
+            GRM_SOLVER_TRY(cusolverDnCreate(&h));
+            ctx->cusolver_lane[i] = h;
+            int lo = 0, hi = 0;
+            GRM_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            GRM_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->lane_stream[i], cudaStreamNonBlocking, hi));
+            GRM_SOLVER_TRY(cusolverDnSetStream(h, ctx->lane_stream[i]));
+        }
+    }
+    for (auto &e : ctx->lane_ev)
+        if (!e) GRM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const size_t mat = static_cast<size_t>(n) * n * sizeof(double);
+    GRM_TRY(ctx->lu.reserve(mat));
+    GRM_TRY(ctx->lu2.reserve(mat));
+    GRM_TRY(ctx->lu3.reserve(mat));
+    L[0].h = static_cast<cusolverDnHandle_t>(ctx->cusolver);  // det(t): the context's own handle and stream
+    L[0].stream = ctx->stream;
+    L[0].mat = ctx->lu2.as<double>();
+    L[1].h = static_cast<cusolverDnHandle_t>(ctx->cusolver_lane[0]);  // det(t + 1)
+    L[1].stream = ctx->lane_stream[0];
+    L[1].mat = ctx->lu3.as<double>();
+    L[2].h = static_cast<cusolverDnHandle_t>(ctx->cusolver_lane[1]);  // Cholesky(t + 1), into the buffer last_factor reads
+    L[2].stream = ctx->lane_stream[1];
+    L[2].mat = ctx->lu.as<double>();
+    int lw1 = 0, lw2 = 0;
+    GRM_SOLVER_TRY(cusolverDnDgetrf_bufferSize(L[0].h, static_cast<int>(n), static_cast<int>(n), L[0].mat, static_cast<int>(n), &lw1));
+    GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(L[0].h, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), L[0].mat, static_cast<int>(n), &lw2));
+    const int lw = std::max(std::max(lw1, lw2), 1);
+    GRM_TRY(ctx->lu_work.reserve(static_cast<size_t>(lw) * sizeof(double)));
+    GRM_TRY(ctx->lane_work[0].reserve(static_cast<size_t>(lw) * sizeof(double)));
+    GRM_TRY(ctx->lane_work[1].reserve(static_cast<size_t>(lw) * sizeof(double)));
+    // per lane on the device: ipiv (n ints) | info | pad | diag (n doubles); pinned mirror of the same size
+    const int64_t int_slots = (n + 16 + 1) & ~int64_t(1);
+    const size_t per = static_cast<size_t>(int_slots) * sizeof(int) + static_cast<size_t>(n) * sizeof(double);
+    GRM_TRY(ctx->ipiv.reserve(per));
+    GRM_TRY(ctx->lane_ipiv[0].reserve(per));
+    GRM_TRY(ctx->lane_ipiv[1].reserve(per));
+    if (ctx->lane_pin_cap < 3 * per) {
+        if (ctx->lane_pin) cudaFreeHost(ctx->lane_pin);
+        ctx->lane_pin = nullptr;
+        ctx->lane_pin_cap = 0;
+        GRM_CUDA_TRY(cudaHostAlloc(&ctx->lane_pin, 3 * per, cudaHostAllocDefault));
+        ctx->lane_pin_cap = 3 * per;
+    }
+    DevBuf *dev[3] = {&ctx->ipiv, &ctx->lane_ipiv[0], &ctx->lane_ipiv[1]};
+    double *works[3] = {ctx->lu_work.as<double>(), ctx->lane_work[0].as<double>(), ctx->lane_work[1].as<double>()};
+    for (int i = 0; i < 3; ++i) {
+        L[i].work = works[i];
+        L[i].lwork = lw;
+        L[i].d_ipiv = dev[i]->as<int>();
+        L[i].d_info = L[i].d_ipiv + n;
+        L[i].d_diag = reinterpret_cast<double *>(L[i].d_ipiv + int_slots);
+        char *hp = static_cast<char *>(ctx->lane_pin) + static_cast<size_t>(i) * per;
+        L[i].h_ipiv = reinterpret_cast<int *>(hp);
+        L[i].h_info = L[i].h_ipiv + n;
+        L[i].h_diag = reinterpret_cast<double *>(L[i].h_ipiv + int_slots);
+    }
+    return GRM_CUDA_OK;
+}
+
+// inflatediagonals! (calc.jl:41-70) with two rounds in flight; `Repair r` (set up by the caller) supplies the sequential
+// single-factorisation path for the on-demand Cholesky of round t
+int32_t repair_speculative(grm_cuda_ctx *ctx, Repair &r, double *X, int64_t n, int64_t ldx, int32_t max_iter,
+                           const unsigned long long *h_scan, int32_t *iters, double *eps_total) {
+    const double eps = DBL_EPSILON;
+    double maxabs = 0.0;
+    {
+        const long long bits = static_cast<long long>(h_scan[1]);
+        memcpy(&maxabs, &bits, sizeof(double));
+    }
+    Lane L[3];
+    GRM_TRY(lanes_setup(ctx, n, L));
+    GRM_SOLVER_TRY(cusolverDnSetStream(L[0].h, ctx->stream));
+    // results of the batch in flight: det of rounds b and b + 1, Cholesky of round b + 1
+    int64_t b = -1;
+    double det_b[2] = {NAN, NAN};
+    bool pd_next = false;
+    int64_t chol_round = -1;  // round whose Cholesky factor currently sits in ctx->lu (valid only if it succeeded)
+    bool chol_ok = false;
+    auto batch = [&](int64_t t) -> int32_t {
+        // X is final on the context's stream: the two side lanes start after everything enqueued there so far
+        GRM_CUDA_TRY(cudaEventRecord(ctx->lane_ev[0], ctx->stream));
+        GRM_CUDA_TRY(cudaStreamWaitEvent(L[1].stream, ctx->lane_ev[0], 0));
+        GRM_CUDA_TRY(cudaStreamWaitEvent(L[2].stream, ctx->lane_ev[0], 0));
+        // cuSOLVER's getrf keeps its calling thread busy for most of the factorisation (issued from one thread the lanes
+        // ran one after another: 694 -> 658 ms on C3), so every lane is driven by a host thread of its own
+        int32_t st_side[2] = {GRM_CUDA_OK, GRM_CUDA_OK};
+        std::string err_side[2];
+        auto side = [&](int which) {
+            if (cudaSetDevice(ctx->device) != cudaSuccess) {
+                st_side[which] = GRM_CUDA_ERR_CUDA;
+                return;
+            }
+            const Lane &l = L[1 + which];
+            int32_t rc = which == 0 ? lane_launch_det(ctx, l, X, n, ldx, static_cast<int>(t + 1), maxabs)
+                                    : lane_launch_chol(ctx, l, X, n, ldx, static_cast<int>(t + 1), maxabs);
+            if (rc == GRM_CUDA_OK && cudaStreamSynchronize(l.stream) != cudaSuccess) rc = GRM_CUDA_ERR_CUDA;
+            if (rc != GRM_CUDA_OK) err_side[which] = grm_cuda_last_error();  // the message is thread-local
+            st_side[which] = rc;
+        };
+        std::thread th1(side, 0), th2(side, 1);
+        int32_t rc0 = lane_launch_det(ctx, L[0], X, n, ldx, static_cast<int>(t), maxabs);
+        if (rc0 == GRM_CUDA_OK && cudaStreamSynchronize(L[0].stream) != cudaSuccess) {
+            grm_set_error("cudaStreamSynchronize failed in the repair");
+            rc0 = GRM_CUDA_ERR_CUDA;
+        }
+        th1.join();
+        th2.join();
+        ctx->launches += 7 + (t > 0 ? 1 : 0);  // counted here: the lanes run on three host threads (copy, shift, extract)
+        GRM_TRY(rc0);
+        for (int w = 0; w < 2; ++w)
+            if (st_side[w] != GRM_CUDA_OK) {
+                grm_set_error("%s", err_side[w].empty() ? "repair lane failed" : err_side[w].c_str());
+                return st_side[w];
+            }
+        GRM_TRY(lane_det_value(L[0], n, &det_b[0]));
+        GRM_TRY(lane_det_value(L[1], n, &det_b[1]));
+        if (*L[2].h_info < 0) {
+            grm_set_error("cusolverDnDpotrf: illegal argument %d", -*L[2].h_info);
+            return GRM_CUDA_ERR_CUDA;
+        }
+        pd_next = *L[2].h_info == 0;
+        chol_round = t + 1;
+        chol_ok = pd_next;
+        b = t;
+        return GRM_CUDA_OK;
+    };
+    auto det_of = [&](int64_t t, double *out) -> int32_t {
+        if (b < 0 || t < b || t > b + 1) GRM_TRY(batch(t));
+        *out = det_b[t - b];
+        return GRM_CUDA_OK;
+    };
+    auto pd_of = [&](int64_t t, bool *out) -> int32_t {
+        if (t == chol_round) {  // evaluated with its batch (or on demand before)
+            *out = chol_ok;
+            return GRM_CUDA_OK;
+        }
+        r.shift_rounds = static_cast<int>(t);
+        r.shift_eps0 = maxabs;
+        GRM_TRY(r.posdef(out));  // sequential, into ctx->lu
+        chol_round = t;
+        chol_ok = *out;
+        return GRM_CUDA_OK;
+    };
+
+    // calc.jl:49-51 — early return iff det(X) > eps && isposdef(X)
+    double det_t = NAN;
+    bool pd_t = false;
+    GRM_TRY(det_of(0, &det_t));
+    if (!(det_t < eps)) GRM_TRY(pd_of(0, &pd_t));
+    if (pd_t && det_t > eps) {
+        ctx->factor_n = n;
+        return GRM_CUDA_OK;
+    }
+    // calc.jl:52-57
+    if (h_scan[0] & 2ull) {
+        grm_set_error("The input matrix contains NaN values.");
+        return GRM_CUDA_ERR_NAN_MATRIX;
+    }
+    if (h_scan[0] & 4ull) {
+        grm_set_error("The input matrix contains Inf values.");
+        return GRM_CUDA_ERR_INF_MATRIX;
+    }
+    // calc.jl:58-66
+    int64_t t = 0;
+    for (;;) {
+        const bool need = det_t < eps || !pd_t;  // a NaN det compares false, then isposdef decides
+        if (!need || t >= max_iter) {
+            ctx->factor_n = (!need && chol_round == t && chol_ok) ? n : -1;
+            break;
+        }
+        ++t;
+        GRM_TRY(det_of(t, &det_t));
+        pd_t = false;
+        if (!(det_t < eps)) GRM_TRY(pd_of(t, &pd_t));
+    }
+    *iters = static_cast<int32_t>(t);
+    return grm_cuda_repair_apply(ctx, X, n, ldx, *iters, maxabs, eps_total);
+}
+
+}  // namespace
+
 // device-resident implementation; X is a device pointer
 int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
                           double *eps_total) {
@@ -260,6 +523,7 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
         grm_set_error("The input matrix is not symmetric.");
         return GRM_CUDA_ERR_NOT_SYMMETRIC;
     }
+    if (ctx->tune.repair != 1 && n >= 3072) return repair_speculative(ctx, r, X, n, ldx, max_iter, h_scan, iters, eps_total);
 
     const double eps = DBL_EPSILON;
     // calc.jl:49-51 — early return iff det(X) > eps && isposdef(X)

@@ -594,6 +594,72 @@ def test_parallel_repair_equals_sequential_loop(ctx, world):
         assert np.array_equal(Xw.cpu().numpy(), Xs)
 
 
+def test_speculative_repair_equals_the_sequential_loop():
+    """From n = 3072 the single-GPU repair evaluates det(t), det(t+1) and the Cholesky of round t+1 concurrently on three
+    streams (repair.cu: repair_speculative).  Same routines on the same inputs: rounds, eps_total, every bit of the matrix
+    and the cached Cholesky factor must equal the sequential loop's (tuning "repair" = 1), on every kind of outcome."""
+    n = 3200
+    rng = np.random.default_rng(5)
+    cases = {
+        "grm needing rounds": grm_call(synth.dosage(n, 6000, 2, seed=3), 2, skip_repair=True)[0],
+        "grmsimple": grm_call(synth.dosage(n, 6000, 4, seed=4), None, skip_repair=True)[0],
+        "det underflows, one round": np.asfortranarray(np.eye(n) * 0.5),
+        "det overflows, untouched": np.asfortranarray(np.eye(n) * 1e3),
+        "tiny values, several rounds": np.asfortranarray(np.eye(n) * 1e-3),
+        "indefinite": np.asfortranarray(np.eye(n) - 2.0 * np.diag((np.arange(n) % 7 == 0).astype(float))),
+    }
+    W = rng.standard_normal((n, 40))
+    cases["low rank"] = np.asfortranarray(W @ W.T / 40.0)
+    seq, spec = grm_b200.Context(0), grm_b200.Context(0)
+    try:
+        seq.set_tuning("repair", 1)
+        for name, X in cases.items():
+            for max_iter in (1000, 1, 0):
+                out = {}
+                for tag, c in (("seq", seq), ("spec", spec)):
+                    Y = np.array(X, order="F", copy=True)
+                    it, tot = C_inflate(c, Y, max_iter)
+                    try:
+                        U = grm_b200.last_factor(n, ctx=c)
+                    except ArgumentError:
+                        U = None
+                    out[tag] = (it, tot, Y, U)
+                (i0, t0, Y0, U0), (i1, t1, Y1, U1) = out["seq"], out["spec"]
+                assert (i0, t0) == (i1, t1), (name, max_iter, i0, i1, t0, t1)
+                assert np.array_equal(Y0, Y1), (name, max_iter)
+                assert (U0 is None) == (U1 is None), (name, max_iter)
+                if U0 is not None:
+                    assert np.array_equal(U0, U1), (name, max_iter)
+        # the error paths keep their order (calc.jl:43-57)
+        bad = np.array(cases["grmsimple"], order="F", copy=True)
+        bad[3, 5] = bad[5, 3] + 1.0
+        for c in (seq, spec):
+            with pytest.raises(_lib.GrmCudaError) as e:
+                C_inflate(c, bad.copy(order="F"), 10)
+            assert e.value.status == _lib.ERR_NOT_SYMMETRIC
+        # an Inf that the early return does not swallow: det underflows (0.5 I), so calc.jl:52-57 get their turn
+        inf = np.asfortranarray(np.eye(n) * 0.5)
+        inf[3, 5] = inf[5, 3] = np.inf
+        for c in (seq, spec):
+            with pytest.raises(_lib.GrmCudaError) as e:
+                C_inflate(c, inf.copy(order="F"), 10)
+            assert e.value.status == _lib.ERR_INF_MATRIX
+    finally:
+        seq.close()
+        spec.close()
+
+
+def C_inflate(ctx, Y, max_iter):
+    """grm_cuda_inflate_diagonals on a host matrix through a given context -> (iters, eps_total); Y updated in place."""
+    import ctypes as C
+
+    it, tot = C.c_int32(0), C.c_double(0.0)
+    n = Y.shape[0]
+    _lib.check(ctx.lib.grm_cuda_inflate_diagonals(ctx.handle, Y.ctypes.data, n, n, int(max_iter), _lib.LOC_HOST, C.byref(it),
+                                                  C.byref(tot)))
+    return it.value, tot.value
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size (BASELINE C2) properties: a checksum of checksums for the integer Gram matrix
 #   sum_j C_ij = sum_k c_ik S_k ,  C_ii = sum_k c_ik^2 ,  sum_ij C_ij = sum_k S_k^2      (S_k = column sums)
