@@ -483,7 +483,8 @@ def run_b200(args, wl):
             d2h = 8 * n * n if rank == 0 else 0
         e2e = {"value": macs(n, p) / dt, "unit": UNIT, "h2d_bytes_per_step": (n * pc if info.ingest == _lib.INGEST_HOSTQ else 8 * n * pc),
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": esteps, **detail,
-               "repair_iters": info.repair_iters, "eps_total": info.eps_total, "denominator": info.denominator, "path": info.path,
+               "repair_iters": info.repair_iters, "eps_total": info.eps_total, "repair_lu_factorisations": info.repair_lu,
+               "denominator": info.denominator, "path": info.path,
                "ingest": {0: "device", 1: "FP64 stream", 2: "host-quantised int8"}[info.ingest], "host_threads": info.host_threads,
                "host_bytes_read_per_step": 9 * n * pc, "pinned": False, "calls_per_rank_per_step": 1,
                "kernel_launches_per_step": launches_e2e,
@@ -494,9 +495,12 @@ def run_b200(args, wl):
                    "ploidyaware" if centred else "simple", "its own loci slab" if world > 1 else "the whole matrix",
                    " + int64 all-reduce" if world > 1 else "", " over own loci in waves + int32 reduce-scatter (NCCL inside the library) + "
                    "all-gather of the finished tiles" if world > 1 else "", "rounds probed in parallel, one per rank" if world > 1 else
-                   "cuSOLVER LU/Cholesky", " on rank 0" if world > 1 else "")}
+                   "cuSOLVER Cholesky, determinant from its pivots, LU only when they cannot vouch for det < eps",
+                   " on rank 0" if world > 1 else "")}
         if verified is not None and G_host is not None and not e2e_tiles and world == 1:
             verified.update(verify_e2e(G_host, out_dev, info, n))
+            if not o.skip_repair and n <= 46000:
+                e2e["repair_same_run"] = repair_same_run(ctx, out_dev, n)
         if verified is not None and G_host is not None and not e2e_tiles and world > 1:
             # rank 0's gathered, repaired matrix against the exactly recomputed rows: off the diagonal the raw GRM, on it + eps_total
             rws, ref = verified["_rows"], verified["_ref"].copy()
@@ -784,6 +788,44 @@ def verify_e2e(G_host, out_dev, info, n):
         ok_diag = ok_diag and bool(np.array_equal(np.diagonal(G_host), want))
     return {"e2e_offdiag_bit_identical_to_device_step": bool(not diff.any()), "e2e_diag_inflated_by_eps_total": ok_diag,
             "e2e_symmetric": bool(np.array_equal(G_host, G_host.T))}
+
+
+def repair_same_run(ctx, raw_dev, n):
+    """inflatediagonals! (calc.jl:41-70) on the device step's raw GRM, timed twice in this run: the default decision rule
+    (Cholesky first, det from its pivots) and the literal order of calc.jl:49,61 (tuning repair_det = 1: cuSOLVER LU
+    first, Cholesky only when !(det < eps)).  Outside every timed region; same rounds, total and matrix required."""
+    import ctypes as C
+
+    import torch
+
+    from grm_b200 import _lib
+
+    lib = ctx.lib
+    res = {}
+    outs = {}
+    for tag, knob in (("lu_first", 1), ("default", 0)):
+        ctx.set_tuning("repair_det", knob)
+        best = None
+        for _ in range(2):  # first pass warms the workspaces of this variant
+            X = raw_dev.clone()
+            it, tot = C.c_int32(0), C.c_double(0.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _lib.check(lib.grm_cuda_inflate_diagonals(ctx.handle, C.c_void_p(X.data_ptr()), n, n, 1000, _lib.LOC_DEVICE,
+                                                      C.byref(it), C.byref(tot)))
+            ctx.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+        res[f"ms_{tag}"] = best
+        outs[tag] = (it.value, tot.value, X)
+    ctx.set_tuning("repair_det", 0)
+    (i0, t0_, X0), (i1, t1_, X1) = outs["lu_first"], outs["default"]
+    res["same_rounds_and_total"] = bool((i0, t0_) == (i1, t1_))
+    res["same_matrix"] = bool(torch.equal(X0, X1))
+    res["what"] = ("grm_cuda_inflate_diagonals on the device-resident raw GRM of the timed step, best of 2: 'lu_first' = LU "
+                   "(cuSOLVER Dgetrf) + sequential pivot product first, Cholesky only when !(det < eps); 'default' = Cholesky first, "
+                   "pivots from its diagonal when partial pivoting cannot interchange rows")
+    return res
 
 
 def main():

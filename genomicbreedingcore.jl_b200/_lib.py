@@ -84,7 +84,7 @@ class Info(C.Structure):
         ("world", C.c_int32),
         ("exchange_waves", C.c_int32),
         ("syrk_window", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("repair_lu", C.c_int32),
     ]
 
     def as_dict(self):
@@ -122,6 +122,8 @@ SIGNATURES = {
     "grm_cuda_host_detect": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
     "grm_cuda_host_simd": (C.c_char_p, []),
     "grm_cuda_host_tune": (_i32, [C.c_char_p, _i64]),
+    "grm_cuda_host_lu_det": (_f64, [_vp, _vp, _i64]),
+    "grm_cuda_host_chol_det": (_i32, [_vp, _i64, _f64, C.POINTER(_f64)]),
     "grm_cuda_inflate_diagonals": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
     "grm_cuda_repair_probe": (_i32, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(C.c_uint32),
                                      C.POINTER(_f64)]),

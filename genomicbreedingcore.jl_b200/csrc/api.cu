@@ -214,7 +214,7 @@ static int *tuning_slot(GrmTuning &t, const char *key) {
         {"ingest", &GrmTuning::ingest},             {"ksplit_waves", &GrmTuning::ksplit_waves},
         {"f64_kernel", &GrmTuning::f64_kernel},     {"ring_mb", &GrmTuning::ring_mb},
         {"comm_ctas", &GrmTuning::comm_ctas},       {"exchange", &GrmTuning::exchange},
-        {"repair", &GrmTuning::repair},
+        {"repair", &GrmTuning::repair},             {"repair_det", &GrmTuning::repair_det},
     };
     for (const Entry &e : table)
         if (!strcmp(e.name, key)) return &(t.*(e.field));

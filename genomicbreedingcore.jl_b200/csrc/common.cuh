@@ -62,6 +62,8 @@ struct GrmTuning {
     int ksplit_waves = 0;   // K-split exchange waves (reduce-scatter of wave w under the SYRK of the later waves); 0 = auto
     int comm_ctas = 0;      // > 0: cap NCCL's CTAs (and leave as many SMs free during the K-split SYRK when NCCL carries it)
     int repair = 0;         // single-GPU inflatediagonals!: 0 auto (two rounds evaluated concurrently from n = 3072), 1 sequential
+    int repair_det = 0;     // determinant of the repair: 0 auto (pivots of the Cholesky when they can vouch for det < eps,
+                            // else LU), 1 always LU first, Cholesky only when !(det < eps) — the literal order of calc.jl:49,61
     int exchange = 0;       // K-split partial tiles: 0 auto = NCCL reduce-scatter, 2 = copy engines into peer-mapped buffers
     int f64_kernel = 0;     // FP64 SYRK operand staging: 0 auto (TMA when aligned), 1 register-staged
     int ring_mb = 0;        // bytes (MiB) of one pinned ingest slot; 0 = automatic
@@ -99,7 +101,9 @@ struct grm_cuda_ctx {
     DevBuf codes, colsum, flags, q, w, u, stats, partials, G, C, stage[4], lu, lu2, lu3, lu_work, lane_work[2], lane_ipiv[2], ipiv, misc, misc2, planes, rT, cnt,
         keep, progress, packed, reduced, gtiles, gtiles_all, codes_all, cons;
     TileListCache tiles_i8, tiles_i8_2cta, tiles_f64, tiles_packed, tiles_wide, tiles_f64_all;
-    int64_t factor_n = -1;  // >= 0: ctx->lu holds the upper Cholesky factor of the n x n matrix the last repair returned
+    int64_t factor_n = -1;  // >= 0: a LOWER Cholesky factor of the n x n matrix the last repair returned is cached ...
+    int factor_buf = 0;     // ... in ctx->lu (0) or ctx->lu2 (1)
+    int32_t repair_lu_count = 0;  // LU factorisations the repair ran since the counter was last reset
     int32_t launches = 0;  // kernels launched since last reset
     GrmTuning tune;
     std::vector<const void *> attr_done;  // kernels whose dynamic shared memory limit was raised ON THIS CONTEXT'S DEVICE

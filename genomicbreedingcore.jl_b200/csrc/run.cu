@@ -26,8 +26,6 @@
 
 int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter, int32_t *iters,
                           double *eps_total);
-int32_t grm_repair_probe_part(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds, int32_t which,
-                              double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs);
 
 namespace {
 
@@ -904,34 +902,24 @@ int32_t Run::f64_path(double *dG, int64_t ldG, double **d_tiles_out, int64_t *p_
 
 // ---------------------------------------------------------------------------------------------------------------
 // inflatediagonals! with the matrix replicated on every rank (calc.jl:41-70): the loop test of round t only looks at
-// X with its diagonal inflated t times, and its two halves — det(X_t) (LU) and isposdef(X_t) (Cholesky) — are independent
-// of each other.  From 4 ranks on the probes are dealt out as (round, half) tasks: rank 2i takes the determinant of round
-// base + i, rank 2i + 1 its Cholesky; a batch of probes costs max(LU, Cholesky) of wall time and covers world / 2 rounds.
-// With fewer ranks every rank probes a whole round (both halves, with the reference's short-circuit).  Each probe
-// performs the arithmetic of the sequential loop and the decision is taken on the all-gathered results, hence the same
-// outcome on every rank as the sequential loop.
+// X with its diagonal inflated t times, so rank r probes round base + r (isposdef, and the determinant when it is
+// positive definite: repair.cu) and a batch of probes costs one round's factorisation of wall time and covers `world`
+// rounds.  Each probe performs the arithmetic of the single-GPU loop and the decision is taken on the all-gathered
+// results, hence the same outcome on every rank as on one GPU.
 // ---------------------------------------------------------------------------------------------------------------
 int32_t Run::repair_parallel(double *dG, int64_t ldG) {
     const double eps = DBL_EPSILON;
-    // From 4 ranks on a round is split over two ranks (a batch costs max(LU, Cholesky) and covers world / 2 rounds).  With
-    // 2 or 3 ranks each rank probes a whole round of its own (LU, then Cholesky unless det < eps already decides): one
-    // batch of LU + Cholesky covers `world` rounds, which beats two LU-bound batches of one round each (measured on C3, 2
-    // GPUs: 587 ms split against ~400 ms whole).
-    const bool split = world >= 4;
-    const int per_batch = split ? world / 2 : world;  // rounds evaluated per batch
     int64_t base = 0;
     int32_t iters = -1;
     double maxabs = 0.0;
     while (iters < 0) {
-        const int64_t r = base + (split ? rank / 2 : rank);
-        const int which = split ? ((rank & 1) ? 2 : 1) : 3;
-        const bool idle = split && rank >= 2 * per_batch;  // the odd rank out
+        const int64_t r = base + rank;
         double mine[4] = {NAN, -1.0, 0.0, 0.0};
-        if (!idle && r <= o.max_iter) {
+        if (r <= o.max_iter) {
             double det = NAN, mx = 0.0;
             int32_t pd = -1;
             uint32_t fl = 0;
-            GRM_TRY(grm_repair_probe_part(ctx, dG, n, ldG, static_cast<int32_t>(r), which, &det, &pd, &fl, &mx));
+            GRM_TRY(grm_cuda_repair_probe(ctx, dG, n, ldG, static_cast<int32_t>(r), &det, &pd, &fl, &mx));
             mine[0] = det;
             mine[1] = static_cast<double>(pd);
             mine[2] = static_cast<double>(fl);
@@ -939,9 +927,6 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
         }
         std::vector<double> all;
         GRM_TRY(gather_f64(mine, 4, all));
-        auto det_of = [&](int i) { return split ? all[4 * (2 * i)] : all[4 * i]; };
-        auto pd_of = [&](int i) { return split ? all[4 * (2 * i + 1) + 1] : all[4 * i + 1]; };
-        auto chol_rank = [&](int i) { return split ? 2 * i + 1 : i; };  // the rank whose last factorisation is chol(round i)
         if (base == 0) {
             const uint32_t flags = static_cast<uint32_t>(all[2]);
             maxabs = all[3];
@@ -949,8 +934,8 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
                 grm_set_error("The input matrix is not symmetric.");  // calc.jl:43-45
                 return GRM_CUDA_ERR_NOT_SYMMETRIC;
             }
-            if (det_of(0) > eps && pd_of(0) == 1.0) {  // calc.jl:49-51
-                if (rank == chol_rank(0)) ctx->factor_n = n;
+            if (all[0] > eps && all[1] == 1.0) {  // calc.jl:49-51
+                if (rank == 0) ctx->factor_n = n;
                 inf.repair_iters = 0;
                 inf.eps_total = 0.0;
                 return GRM_CUDA_OK;
@@ -964,17 +949,17 @@ int32_t Run::repair_parallel(double *dG, int64_t ldG) {
                 return GRM_CUDA_ERR_INF_MATRIX;
             }
         }
-        for (int i = 0; i < per_batch && iters < 0; ++i) {
+        for (int i = 0; i < world && iters < 0; ++i) {
             const int64_t t = base + i;
-            const double det = det_of(i), pd = pd_of(i);
+            const double det = all[4 * i], pd = all[4 * i + 1];
             // calc.jl:61 (a NaN det compares false, then isposdef decides; a half that was not evaluated is decided by the other)
             const bool need = (det < eps) || (pd != 1.0);
             if (!need || t >= o.max_iter) {
                 iters = static_cast<int32_t>(t);
-                if (!need && rank == chol_rank(i)) ctx->factor_n = n;  // this rank's Cholesky is of the result
+                if (!need && rank == i) ctx->factor_n = n;  // this rank's Cholesky is of the result
             }
         }
-        base += per_batch;
+        base += world;
     }
     double tot = 0.0;
     GRM_TRY(grm_cuda_repair_apply(ctx, dG, n, ldG, iters, maxabs, &tot));
@@ -1035,6 +1020,7 @@ int32_t Run::go() {
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     ctx->launches = 0;
+    ctx->repair_lu_count = 0;
     ctx->last_syrk_window = 0;
     memset(&inf, 0, sizeof(inf));
     inf.struct_size = static_cast<int32_t>(sizeof(inf));
@@ -1241,6 +1227,7 @@ int32_t Run::go() {
     inf.host_threads = (src.host && ctx->pool) ? grm_pool_threads(ctx->pool) : 0;
     inf.ms_total = wall.ms();
     inf.kernel_launches = ctx->launches;
+    inf.repair_lu = ctx->repair_lu_count;
     inf.loci_kept = static_cast<int32_t>(p_eff);
     if (info) memcpy(info, &inf, std::min<size_t>(sizeof(inf), static_cast<size_t>(std::max(info->struct_size, 0))));
     return GRM_CUDA_OK;

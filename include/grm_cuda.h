@@ -135,7 +135,7 @@ typedef struct grm_cuda_info {
     float ms_rowdot;       /* integer row statistics for the rank-1 correction (+ their all-reduce)            */
     float ms_syrk;         /* int8 tcgen05 or FP64 SYRK kernel (+ the exchange waves overlapped with it)       */
     float ms_finalize;     /* mirror kernel / tile finalisation                                                */
-    float ms_repair;       /* inflatediagonals! (cuSOLVER LU/Cholesky + host pivot product)                    */
+    float ms_repair;       /* inflatediagonals! (cuSOLVER Cholesky/LU + host pivot product)                    */
     float ms_d2h;
     float ms_total;        /* wall time of the whole call, host clock                                          */
     int32_t kernel_launches; /* kernels of this library launched by the call                                   */
@@ -149,7 +149,8 @@ typedef struct grm_cuda_info {
     int32_t world;         /* ranks that took part (1 unless distributed)                                       */
     int32_t exchange_waves;/* K-split: reduce-scatter waves overlapped with the SYRK                            */
     int32_t syrk_window;   /* 1 if the SYRK ran with the K-window synchronisation                               */
-    int32_t reserved0;
+    int32_t repair_lu;     /* LU factorisations the repair had to run (0: every determinant came from the pivots of
+                              the Cholesky that isposdef computes anyway, see grm_cuda_inflate_diagonals)         */
 } grm_cuda_info;
 
 /* ---- library / context ------------------------------------------------------------------------------------ */
@@ -167,7 +168,8 @@ int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx);
 /* Per-context tuning knobs; the library never reads the environment.  Keys (value 0 / -1 = automatic, the measured
  * best): "syrk_i8" (1 single-CTA, 2 CTA pair, 3 wide), "syrk_packed" (2, 3), "syrk_sync" (-1 auto, 0 off, 1 on),
  * "syrk_window", "pack" (1 = register-staged), "ieee_div", "tile_band", "host_threads", "ingest" (GRM_CUDA_INGEST_*),
- * "ksplit_waves", "f64_kernel" (1 = register-staged operands), "ring_mb", "comm_ctas" (> 0: cap NCCL's CTAs; set before
+ * "ksplit_waves", "f64_kernel" (1 = register-staged operands), "ring_mb", "repair" (1 = one round at a time),
+ * "repair_det" (1 = determinant always by LU), "comm_ctas" (> 0: cap NCCL's CTAs; set before
  * grm_cuda_comm_init), "exchange" (K-split partial tiles: 0 auto = NCCL reduce-scatter, 2 = copy engines into
  * peer-mapped buffers).  Unknown key -> GRM_CUDA_ERR_BAD_ARGUMENT. */
 int32_t grm_cuda_ctx_set_tuning(grm_cuda_ctx *ctx, const char *key, int64_t value);
@@ -234,8 +236,24 @@ int32_t grm_cuda_host_detect(const double *payload, const uint8_t *selectors, in
 const char *grm_cuda_host_simd(void);
 /* Process-wide knobs of the host quantiser: "prefetch" = software prefetch distance in bytes (0 = off, default 8192). */
 int32_t grm_cuda_host_tune(const char *key, int64_t value);
+/* Host half of the repair's determinant (calc.jl:49,61; no device needed, exported for tests).
+ * grm_cuda_host_lu_det: Julia's det(::LU) from diag(U) and LAPACK's 1-based ipiv: sequential binary64 product, sign by
+ *   the parity of the row interchanges.
+ * grm_cuda_host_chol_det: the same product from the diagonal of a lower Cholesky factor (pivot k = L_kk^2), scale =
+ *   max|X|.  Returns 0 when `det < eps` is decided beyond the reach of rounding differences between factorisation
+ *   routines, else the reason the caller must run the LU (1 ill-determined pivot, 2 product within 2^+-64 of eps, 3 / 4
+ *   the product crossed the subnormal / near-overflow range and what follows could bring it back), -1 bad argument. */
+double grm_cuda_host_lu_det(const double *diag_u, const int32_t *ipiv, int64_t n);
+int32_t grm_cuda_host_chol_det(const double *diag_l, int64_t n, double scale, double *det_out);
 
-/* inflatediagonals!, calc.jl:41-70.  `location` says where X lives (GRM_CUDA_LOC_*). */
+/* inflatediagonals!, calc.jl:41-70.  `location` says where X lives (GRM_CUDA_LOC_*).
+ * The reference returns early iff det(X) > eps && isposdef(X) (calc.jl:49) and inflates again iff det(X) < eps ||
+ * !isposdef(X) (calc.jl:61): a matrix that is not positive definite is inflated whatever its determinant, so the
+ * Cholesky runs first and det(X) — Julia's det(lu(X)): the sequential product of the pivots, under/overflow included —
+ * is only formed for positive definite X.  There its pivots are the squared diagonal of the Cholesky factor whenever
+ * partial pivoting cannot interchange rows (|L_jk| < L_kk, checked on the device); the LU itself (cuSOLVER Dgetrf)
+ * runs when that check fails, a pivot is ill-determined, or the product ends near eps (csrc/repair_host.h).  Tuning
+ * "repair_det" = 1: always LU first, Cholesky only when !(det < eps). */
 int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
                                    int32_t location, int32_t *iters, double *eps_total);
 
@@ -244,8 +262,10 @@ int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int6
  * theirs: one LU (+ Cholesky) of wall time instead of rounds + 1.  Each probe performs the arithmetic of the sequential
  * loop, hence the same outcome.
  *   grm_cuda_repair_probe: X untouched.  scan_flags: bit0 not symmetric, bit1 NaN, bit2 Inf; maxabs = max|X| (the
- *     first epsilon); det_out = det(X after `rounds` rounds); posdef_out = isposdef of the same matrix, evaluated only
- *     when !(det < eps) as in the reference's short-circuit (-1 = not evaluated).
+ *     first epsilon); posdef_out = isposdef(X after `rounds` rounds); det_out = det of the same matrix when it is positive
+ *     definite, NaN otherwise (not needed: calc.jl:61 inflates a matrix that is not positive definite whatever its
+ *     determinant).  With tuning "repair_det" = 1 the determinant is always evaluated and posdef_out = -1 (not
+ *     evaluated) when det < eps already decides.
  *   grm_cuda_repair_apply: performs `rounds` rounds of X[diag] .+= eps_t on X and returns their total. */
 int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds,
                               double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs);

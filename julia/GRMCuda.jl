@@ -63,7 +63,7 @@ Base.@kwdef mutable struct Info
     world::Int32 = 1
     exchange_waves::Int32 = 0
     syrk_window::Int32 = 0
-    reserved0::Int32 = 0
+    repair_lu::Int32 = 0
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)

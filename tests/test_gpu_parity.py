@@ -594,10 +594,13 @@ def test_parallel_repair_equals_sequential_loop(ctx, world):
         assert np.array_equal(Xw.cpu().numpy(), Xs)
 
 
-def test_speculative_repair_equals_the_sequential_loop():
-    """From n = 3072 the single-GPU repair evaluates det(t), det(t+1) and the Cholesky of round t+1 concurrently on three
-    streams (repair.cu: repair_speculative).  Same routines on the same inputs: rounds, eps_total, every bit of the matrix
-    and the cached Cholesky factor must equal the sequential loop's (tuning "repair" = 1), on every kind of outcome."""
+def test_repair_variants_agree():
+    """Three ways through inflatediagonals! (repair.cu) must give the same rounds, eps_total, every bit of the matrix and
+    the same cached Cholesky factor, on every kind of outcome:
+      lit  — tuning "repair_det" = 1: the literal order of calc.jl:49,61 (LU first, Cholesky only when !(det < eps));
+      seq  — the default decision rule, one round at a time ("repair" = 1): Cholesky first, the determinant from the
+             factor's diagonal when partial pivoting cannot interchange rows, LU otherwise;
+      spec — the default from n = 3072: the same rule with two rounds in flight on two streams."""
     n = 3200
     rng = np.random.default_rng(5)
     cases = {
@@ -610,13 +613,23 @@ def test_speculative_repair_equals_the_sequential_loop():
     }
     W = rng.standard_normal((n, 40))
     cases["low rank"] = np.asfortranarray(W @ W.T / 40.0)
-    seq, spec = grm_b200.Context(0), grm_b200.Context(0)
+    # positive definite, but partial pivoting WOULD interchange rows 0 and 1: the pivots of the Cholesky are not the LU's
+    swap = np.eye(n)
+    swap[0, 1] = swap[1, 0] = 2.0
+    swap[1, 1] = 5.0
+    cases["needs pivoting"] = np.asfortranarray(swap)
+    # det = 1e-15: within reach of eps, the LU has the last word
+    near = np.eye(n)
+    near[np.arange(15), np.arange(15)] = 0.1
+    cases["det near eps"] = np.asfortranarray(near)
+    lit, seq, spec = grm_b200.Context(0), grm_b200.Context(0), grm_b200.Context(0)
     try:
+        lit.set_tuning("repair_det", 1)
         seq.set_tuning("repair", 1)
         for name, X in cases.items():
             for max_iter in (1000, 1, 0):
                 out = {}
-                for tag, c in (("seq", seq), ("spec", spec)):
+                for tag, c in (("lit", lit), ("seq", seq), ("spec", spec)):
                     Y = np.array(X, order="F", copy=True)
                     it, tot = C_inflate(c, Y, max_iter)
                     try:
@@ -624,29 +637,57 @@ def test_speculative_repair_equals_the_sequential_loop():
                     except ArgumentError:
                         U = None
                     out[tag] = (it, tot, Y, U)
-                (i0, t0, Y0, U0), (i1, t1, Y1, U1) = out["seq"], out["spec"]
-                assert (i0, t0) == (i1, t1), (name, max_iter, i0, i1, t0, t1)
-                assert np.array_equal(Y0, Y1), (name, max_iter)
-                assert (U0 is None) == (U1 is None), (name, max_iter)
-                if U0 is not None:
-                    assert np.array_equal(U0, U1), (name, max_iter)
+                i0, t0, Y0, U0 = out["lit"]
+                for tag in ("seq", "spec"):
+                    i1, t1, Y1, U1 = out[tag]
+                    assert (i0, t0) == (i1, t1), (name, tag, max_iter, i0, i1, t0, t1)
+                    assert np.array_equal(Y0, Y1), (name, tag, max_iter)
+                    assert (U0 is None) == (U1 is None), (name, tag, max_iter)
+                    if U0 is not None:
+                        assert np.array_equal(U0, U1), (name, tag, max_iter)
+                if U0 is not None:  # U'U is the returned matrix, U upper triangular
+                    assert np.array_equal(np.tril(U0, -1), np.zeros_like(U0))
+                    assert relerr(U0.T @ U0, Y0) < 1e-13
         # the error paths keep their order (calc.jl:43-57)
         bad = np.array(cases["grmsimple"], order="F", copy=True)
         bad[3, 5] = bad[5, 3] + 1.0
-        for c in (seq, spec):
+        for c in (lit, seq, spec):
             with pytest.raises(_lib.GrmCudaError) as e:
                 C_inflate(c, bad.copy(order="F"), 10)
             assert e.value.status == _lib.ERR_NOT_SYMMETRIC
         # an Inf that the early return does not swallow: det underflows (0.5 I), so calc.jl:52-57 get their turn
         inf = np.asfortranarray(np.eye(n) * 0.5)
         inf[3, 5] = inf[5, 3] = np.inf
-        for c in (seq, spec):
+        for c in (lit, seq, spec):
             with pytest.raises(_lib.GrmCudaError) as e:
                 C_inflate(c, inf.copy(order="F"), 10)
             assert e.value.status == _lib.ERR_INF_MATRIX
     finally:
-        seq.close()
-        spec.close()
+        for c in (lit, seq, spec):
+            c.close()
+
+
+def test_repair_reports_how_the_determinant_was_formed():
+    """info.repair_lu: a GRM whose determinant under- or overflows is decided by the Cholesky alone (no LU); the literal
+    order runs one LU per evaluated round; a determinant within reach of eps sends the default rule to the LU too.  Same
+    outcome each time."""
+    A = synth.dosage(1200, 9000, 4, seed=9)  # det(raw) = 1e-52, det(inflated) = Inf: far from eps both times
+    c_def, c_lit = grm_b200.Context(0), grm_b200.Context(0)
+    try:
+        c_lit.set_tuning("repair_det", 1)
+        G0, i0 = grm_call(A, 4, ctx=c_def)
+        G1, i1 = grm_call(A, 4, ctx=c_lit)
+        assert np.array_equal(G0, G1) and (i0["repair_iters"], i0["eps_total"]) == (i1["repair_iters"], i1["eps_total"])
+        assert i0["repair_iters"] == 1 and i0["repair_lu"] == 0 and i1["repair_lu"] == 2
+        # 700 x 9000 with this seed: det(raw) = 4.5e-16, twice eps — no inflation, and only the LU may say so
+        B = synth.dosage(700, 9000, 4, seed=9)
+        G0, i0 = grm_call(B, 4, ctx=c_def)
+        G1, i1 = grm_call(B, 4, ctx=c_lit)
+        assert np.array_equal(G0, G1) and i0["repair_iters"] == i1["repair_iters"] == 0
+        assert i0["repair_lu"] == 1 and i1["repair_lu"] == 1
+    finally:
+        c_def.close()
+        c_lit.close()
 
 
 def C_inflate(ctx, Y, max_iter):
