@@ -259,8 +259,8 @@ int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int6
 
 /* Multi-GPU inflatediagonals! (calc.jl:41-70).  Given max|X|, the loop test of round t only looks at X with its
  * diagonal inflated t times, so with X replicated on every GPU rank r can evaluate round r while the others evaluate
- * theirs: one LU (+ Cholesky) of wall time instead of rounds + 1.  Each probe performs the arithmetic of the sequential
- * loop, hence the same outcome.
+ * theirs: one round's factorisation of wall time instead of rounds + 1.  Each probe performs the arithmetic of the
+ * single-GPU loop, hence the same outcome.
  *   grm_cuda_repair_probe: X untouched.  scan_flags: bit0 not symmetric, bit1 NaN, bit2 Inf; maxabs = max|X| (the
  *     first epsilon); posdef_out = isposdef(X after `rounds` rounds); det_out = det of the same matrix when it is positive
  *     definite, NaN otherwise (not needed: calc.jl:61 inflates a matrix that is not positive definite whatever its
