@@ -499,7 +499,7 @@ def run_b200(args, wl):
                    " on rank 0" if world > 1 else "")}
         if verified is not None and G_host is not None and not e2e_tiles and world == 1:
             verified.update(verify_e2e(G_host, out_dev, info, n))
-            if not o.skip_repair and n <= 46000:
+            if not o.skip_repair:
                 e2e["repair_same_run"] = repair_same_run(ctx, out_dev, n)
         if verified is not None and G_host is not None and not e2e_tiles and world > 1:
             # rank 0's gathered, repaired matrix against the exactly recomputed rows: off the diagonal the raw GRM, on it + eps_total

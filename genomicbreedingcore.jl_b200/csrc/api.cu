@@ -140,6 +140,7 @@ extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) {
 }
 
 int32_t grm_cusolver_destroy(void *h);
+int32_t grm_cusolver_params_destroy(void *p);
 
 extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     if (!ctx) return GRM_CUDA_OK;
@@ -148,6 +149,7 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->comm) grm_comm_destroy(ctx);
     if (ctx->cusolver) grm_cusolver_destroy(ctx->cusolver);
+    if (ctx->cusolver_params) grm_cusolver_params_destroy(ctx->cusolver_params);
     for (auto &h : ctx->cusolver_lane)
         if (h) grm_cusolver_destroy(h);
     for (auto &x : ctx->lane_stream)

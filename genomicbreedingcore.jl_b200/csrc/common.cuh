@@ -91,6 +91,7 @@ struct grm_cuda_ctx {
     cudaEvent_t wave_ev[16] = {};        // K-split waves: SYRK of wave w finished / exchange of wave w finished
     cudaEvent_t copy_done[4] = {}, stage_free[4] = {};
     void *cusolver = nullptr;  // cusolverDnHandle_t
+    void *cusolver_params = nullptr;  // cusolverDnParams_t of the 64-bit entry points (n > 46,000)
     // concurrent lanes of the speculative repair (repair.cu): extra handles, streams, events, pinned result buffers
     void *cusolver_lane[2] = {nullptr, nullptr};
     cudaStream_t lane_stream[2] = {nullptr, nullptr};

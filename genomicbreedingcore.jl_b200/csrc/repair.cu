@@ -45,19 +45,20 @@ __global__ void __launch_bounds__(256) scan_kernel(const double *__restrict__ X,
                                                    unsigned long long *__restrict__ out) {
     unsigned flags = 0;
     unsigned long long mx = 0;
-    const int64_t j = blockIdx.y;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const double a = X[i + j * ldx];
-        if (i <= j) {
-            const double b = X[j + i * ldx];
-            if (!(a == b)) flags |= 1u;
-        }
-        if (a != a) flags |= 2u;
-        else if (isinf(a)) flags |= 4u;
-        else {
-            const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fabs(a)));
-            mx = bits > mx ? bits : mx;
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+             i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+            const double a = X[i + j * ldx];
+            if (i <= j) {
+                const double b = X[j + i * ldx];
+                if (!(a == b)) flags |= 1u;
+            }
+            if (a != a) flags |= 2u;
+            else if (isinf(a)) flags |= 4u;
+            else {
+                const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fabs(a)));
+                mx = bits > mx ? bits : mx;
+            }
         }
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
@@ -73,11 +74,14 @@ __global__ void __launch_bounds__(256) scan_kernel(const double *__restrict__ X,
 }
 
 __global__ void copy_matrix_kernel(const double *__restrict__ X, int64_t n, int64_t ldx, double *__restrict__ Y) {
-    const int64_t j = blockIdx.y;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-        Y[i + j * n] = X[i + j * ldx];
+    for (int64_t j = blockIdx.y; j < n; j += gridDim.y)
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+             i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+            Y[i + j * n] = X[i + j * ldx];
 }
+
+// columns per launch: gridDim.y is limited to 65535
+unsigned grid_cols(int64_t n) { return static_cast<unsigned>(std::min<int64_t>(n, 65535)); }
 
 __global__ void diag_extract_kernel(const double *__restrict__ LU, int64_t n, double *__restrict__ d) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -159,13 +163,78 @@ double bits_to_double(unsigned long long bits) {
     return d;
 }
 
+// cuSOLVER's legacy Dpotrf / Dgetrf index with 32-bit integers (n * n has to stay below 2^31, workspace lengths are ints);
+// beyond n = 46,000 the 64-bit entry points take over.  The legacy ones stay for the sizes they cover: that is where the
+// measurements were taken (scripts/potrf_probe.cu).
+constexpr int64_t LEGACY_MAX_N = 46000;
+
+int32_t solver_params(grm_cuda_ctx *ctx, cusolverDnParams_t *out) {
+    if (!ctx->cusolver_params) {
+        cusolverDnParams_t pr;
+        GRM_SOLVER_TRY(cusolverDnCreateParams(&pr));
+        ctx->cusolver_params = pr;
+    }
+    *out = static_cast<cusolverDnParams_t>(ctx->cusolver_params);
+    return GRM_CUDA_OK;
+}
+
+struct FactorPlan {
+    bool big = false;
+    cusolverDnParams_t params = nullptr;
+    size_t dev_bytes = 8, host_bytes = 0;  // workspaces
+};
+
+int32_t potrf_plan(grm_cuda_ctx *ctx, cusolverDnHandle_t h, int64_t n, double *A, FactorPlan *pl) {
+    pl->big = n > LEGACY_MAX_N;
+    if (pl->big) {
+        GRM_TRY(solver_params(ctx, &pl->params));
+        GRM_SOLVER_TRY(cusolverDnXpotrf_bufferSize(h, pl->params, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A, n, CUDA_R_64F,
+                                                   &pl->dev_bytes, &pl->host_bytes));
+        pl->dev_bytes = std::max<size_t>(pl->dev_bytes, 8);
+    } else {
+        int lw = 0;
+        GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), A, static_cast<int>(n), &lw));
+        pl->dev_bytes = static_cast<size_t>(std::max(lw, 1)) * sizeof(double);
+        pl->host_bytes = 0;
+    }
+    return GRM_CUDA_OK;
+}
+
+// lower Cholesky factor in place, asynchronous on the handle's stream; *d_info as LAPACK's info
+int32_t potrf_run(cusolverDnHandle_t h, const FactorPlan &pl, int64_t n, double *A, void *d_work, void *h_work, int *d_info) {
+    if (pl.big)
+        GRM_SOLVER_TRY(cusolverDnXpotrf(h, pl.params, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A, n, CUDA_R_64F, d_work,
+                                        pl.dev_bytes, h_work, pl.host_bytes, d_info));
+    else
+        GRM_SOLVER_TRY(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), A, static_cast<int>(n),
+                                        static_cast<double *>(d_work), static_cast<int>(pl.dev_bytes / sizeof(double)), d_info));
+    return GRM_CUDA_OK;
+}
+
+int32_t getrf_plan(grm_cuda_ctx *ctx, cusolverDnHandle_t h, int64_t n, double *A, FactorPlan *pl) {
+    pl->big = n > LEGACY_MAX_N;
+    if (pl->big) {
+        GRM_TRY(solver_params(ctx, &pl->params));
+        GRM_SOLVER_TRY(cusolverDnXgetrf_bufferSize(h, pl->params, n, n, CUDA_R_64F, A, n, CUDA_R_64F, &pl->dev_bytes,
+                                                   &pl->host_bytes));
+        pl->dev_bytes = std::max<size_t>(pl->dev_bytes, 8);
+    } else {
+        int lw = 0;
+        GRM_SOLVER_TRY(cusolverDnDgetrf_bufferSize(h, static_cast<int>(n), static_cast<int>(n), A, static_cast<int>(n), &lw));
+        pl->dev_bytes = static_cast<size_t>(std::max(lw, 1)) * sizeof(double);
+        pl->host_bytes = 0;
+    }
+    return GRM_CUDA_OK;
+}
+
 // One factorisation lane: a cuSOLVER handle on its own stream, an n x n work matrix, and pinned slots for what comes back.
 struct Lane {
     cusolverDnHandle_t h = nullptr;
     cudaStream_t stream = nullptr;
     double *mat = nullptr;   // copy of the (inflated) matrix, then its lower Cholesky factor
-    double *work = nullptr;
-    int lwork = 0;
+    void *work = nullptr;
+    FactorPlan plan;
+    std::vector<char> h_work;  // host workspace of the 64-bit entry point (usually empty)
     int *d_info = nullptr;
     unsigned *d_risk = nullptr;
     double *d_diag = nullptr;
@@ -184,10 +253,14 @@ struct Engine {
     Lane L[2];
     // the LU (fallback, or tuning repair_det = 1): set up on first use
     bool lu_ready = false;
-    double *lu_mat = nullptr, *lu_work = nullptr, *lu_diag = nullptr;
-    int *lu_ipiv = nullptr, *lu_info = nullptr;
+    double *lu_mat = nullptr, *lu_diag = nullptr;
+    void *lu_work = nullptr, *lu_ipiv = nullptr;  // ipiv: n ints (legacy) or n int64 (64-bit entry point)
+    int *lu_info = nullptr;
+    FactorPlan lu_plan;
+    std::vector<char> lu_h_work;
     std::vector<double> h_diag;
     std::vector<int> h_ipiv;
+    std::vector<int64_t> h_ipiv64;
 
     int32_t setup(grm_cuda_ctx *c, int64_t n_, int lanes) {
         ctx = c;
@@ -222,10 +295,8 @@ struct Engine {
             L[1].mat = ctx->lu2.as<double>();
             L[1].buf = 1;
         }
-        int lw = 0;
-        GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(L[0].h, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), L[0].mat,
-                                                   static_cast<int>(n), &lw));
-        lw = std::max(lw, 1);
+        FactorPlan plan;
+        GRM_TRY(potrf_plan(ctx, L[0].h, n, L[0].mat, &plan));
         // per lane: info | risk | pad to 16 bytes | diag (n doubles); the same layout on the device and in pinned memory
         const size_t per = (16 + static_cast<size_t>(n) * sizeof(double) + 63) & ~size_t(63);
         if (ctx->lane_pin_cap < 2 * per) {
@@ -238,10 +309,11 @@ struct Engine {
         DevBuf *small[2] = {&ctx->ipiv, &ctx->lane_ipiv[0]};
         DevBuf *works[2] = {&ctx->lu_work, &ctx->lane_work[0]};
         for (int i = 0; i < nlanes; ++i) {
-            GRM_TRY(works[i]->reserve(static_cast<size_t>(lw) * sizeof(double)));
+            GRM_TRY(works[i]->reserve(plan.dev_bytes));
             GRM_TRY(small[i]->reserve(per));
-            L[i].work = works[i]->as<double>();
-            L[i].lwork = lw;
+            L[i].work = works[i]->ptr;
+            L[i].plan = plan;
+            L[i].h_work.resize(plan.host_bytes);
             char *dp = small[i]->as<char>();
             L[i].d_info = reinterpret_cast<int *>(dp);
             L[i].d_risk = reinterpret_cast<unsigned *>(dp + 4);
@@ -256,7 +328,7 @@ struct Engine {
 
     int32_t copy_in(cudaStream_t s, const double *X, int64_t ldx, double *dst, int rounds, double eps0) {
         const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
-        copy_matrix_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, s>>>(X, n, ldx, dst);
+        copy_matrix_kernel<<<dim3(gx, grid_cols(n)), 256, 0, s>>>(X, n, ldx, dst);
         GRM_CUDA_TRY(cudaGetLastError());
         if (rounds > 0) {
             diag_add_rounds_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(dst, n, n, eps0, rounds);
@@ -268,10 +340,9 @@ struct Engine {
     // Cholesky of X after `rounds` rounds + the pivoting check, all asynchronous on the lane's stream.  Does not touch
     // ctx->launches (a lane may be driven by a side thread); the caller adds chol_launches(rounds).
     int32_t launch_chol(int lane, const double *X, int64_t ldx, int rounds, double eps0) {
-        const Lane &l = L[lane];
+        Lane &l = L[lane];
         GRM_TRY(copy_in(l.stream, X, ldx, l.mat, rounds, eps0));
-        GRM_SOLVER_TRY(cusolverDnDpotrf(l.h, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), l.mat, static_cast<int>(n), l.work,
-                                        l.lwork, l.d_info));
+        GRM_TRY(potrf_run(l.h, l.plan, n, l.mat, l.work, l.h_work.data(), l.d_info));
         GRM_CUDA_TRY(cudaMemsetAsync(l.d_risk, 0, sizeof(unsigned), l.stream));
         const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(n, 8 * 148));
         chol_check_kernel<<<blocks, 256, 0, l.stream>>>(l.mat, n, l.d_diag, l.d_risk);
@@ -289,35 +360,48 @@ struct Engine {
         if (!lu_ready) {
             GRM_TRY(ctx->lu3.reserve(static_cast<size_t>(n) * n * sizeof(double)));
             lu_mat = ctx->lu3.as<double>();
-            int lw = 0;
-            GRM_SOLVER_TRY(cusolverDnDgetrf_bufferSize(h, static_cast<int>(n), static_cast<int>(n), lu_mat, static_cast<int>(n), &lw));
-            GRM_TRY(ctx->lane_work[1].reserve(static_cast<size_t>(std::max(lw, 1)) * sizeof(double)));
-            lu_work = ctx->lane_work[1].as<double>();
-            // ipiv (n ints) | info | pad to 16 bytes | diag(U) (n doubles)
-            const size_t ints = (static_cast<size_t>(n + 1) * sizeof(int) + 15) & ~size_t(15);
-            GRM_TRY(ctx->lane_ipiv[1].reserve(ints + static_cast<size_t>(n) * sizeof(double)));
-            lu_ipiv = ctx->lane_ipiv[1].as<int>();
-            lu_info = lu_ipiv + n;
-            lu_diag = reinterpret_cast<double *>(ctx->lane_ipiv[1].as<char>() + ints);
+            GRM_TRY(getrf_plan(ctx, h, n, lu_mat, &lu_plan));
+            GRM_TRY(ctx->lane_work[1].reserve(lu_plan.dev_bytes));
+            lu_work = ctx->lane_work[1].ptr;
+            lu_h_work.resize(lu_plan.host_bytes);
+            // ipiv (n ints, or n int64 for the 64-bit entry point) | info | pad to 16 bytes | diag(U) (n doubles)
+            const size_t piv = static_cast<size_t>(n) * (lu_plan.big ? sizeof(int64_t) : sizeof(int));
+            const size_t head = (piv + sizeof(int) + 15) & ~size_t(15);
+            GRM_TRY(ctx->lane_ipiv[1].reserve(head + static_cast<size_t>(n) * sizeof(double)));
+            lu_ipiv = ctx->lane_ipiv[1].ptr;
+            lu_info = reinterpret_cast<int *>(ctx->lane_ipiv[1].as<char>() + piv);
+            lu_diag = reinterpret_cast<double *>(ctx->lane_ipiv[1].as<char>() + head);
             h_diag.resize(n);
-            h_ipiv.resize(n);
+            if (lu_plan.big) h_ipiv64.resize(n);
+            else h_ipiv.resize(n);
             lu_ready = true;
         }
         GRM_TRY(copy_in(ctx->stream, X, ldx, lu_mat, rounds, eps0));
-        GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), lu_mat, static_cast<int>(n), lu_work, lu_ipiv,
-                                        lu_info));
+        if (lu_plan.big)
+            GRM_SOLVER_TRY(cusolverDnXgetrf(h, lu_plan.params, n, n, CUDA_R_64F, lu_mat, n, static_cast<int64_t *>(lu_ipiv),
+                                            CUDA_R_64F, lu_work, lu_plan.dev_bytes, lu_h_work.data(), lu_plan.host_bytes, lu_info));
+        else
+            GRM_SOLVER_TRY(cusolverDnDgetrf(h, static_cast<int>(n), static_cast<int>(n), lu_mat, static_cast<int>(n),
+                                            static_cast<double *>(lu_work), static_cast<int *>(lu_ipiv), lu_info));
         diag_extract_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(lu_mat, n, lu_diag);
         GRM_CUDA_TRY(cudaGetLastError());
         ctx->launches += 2 + (rounds > 0 ? 1 : 0);
         ctx->repair_lu_count++;
         int h_info = 0;
         GRM_CUDA_TRY(cudaMemcpyAsync(h_diag.data(), lu_diag, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), lu_ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (lu_plan.big)
+            GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv64.data(), lu_ipiv, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            GRM_CUDA_TRY(cudaMemcpyAsync(h_ipiv.data(), lu_ipiv, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, lu_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (h_info < 0) {
-            grm_set_error("cusolverDnDgetrf: illegal argument %d", -h_info);
+            grm_set_error("cusolver getrf: illegal argument %d", -h_info);
             return GRM_CUDA_ERR_CUDA;
+        }
+        if (lu_plan.big) {  // the interchanges as the 32-bit flags grm_det_lu_pivots counts: ipiv[i] != i + 1
+            h_ipiv.resize(n);
+            for (int64_t i = 0; i < n; ++i) h_ipiv[i] = h_ipiv64[i] == i + 1 ? static_cast<int>(i + 1) : 0;
         }
         // an exactly zero pivot: Julia's det returns 0 for a singular factorisation
         *out = h_info > 0 ? 0.0 : grm_det_lu_pivots(h_diag.data(), h_ipiv.data(), n);
@@ -403,16 +487,12 @@ struct Engine {
 
 // symmetry / NaN / Inf / max|X| scan (h_scan[0] = flags, h_scan[1] = bits of max|X|): calc.jl:43-48 and the first epsilon
 int32_t repair_scan(grm_cuda_ctx *ctx, const double *X, int64_t n, int64_t ldx, unsigned long long *h_scan) {
-    if (n > 46000) {  // 32-bit indexing of the legacy potrf/getrf entry points: n*n must stay below 2^31
-        grm_set_error("inflate_diagonals: n=%lld exceeds the single-GPU cuSOLVER range (n <= 46000)", (long long)n);
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
     ctx->factor_n = -1;  // the work matrices are about to be overwritten
     GRM_TRY(ctx->misc.reserve(64));
     unsigned long long *d_scan = ctx->misc.as<unsigned long long>();
     GRM_CUDA_TRY(cudaMemsetAsync(d_scan, 0, 2 * sizeof(unsigned long long), ctx->stream));
     const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64));
-    scan_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, ctx->stream>>>(X, n, ldx, d_scan);
+    scan_kernel<<<dim3(gx, grid_cols(n)), 256, 0, ctx->stream>>>(X, n, ldx, d_scan);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     GRM_CUDA_TRY(cudaMemcpyAsync(h_scan, d_scan, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -424,6 +504,11 @@ int32_t repair_scan(grm_cuda_ctx *ctx, const double *X, int64_t n, int64_t ldx, 
 
 int32_t grm_cusolver_destroy(void *h) {
     cusolverDnDestroy(static_cast<cusolverDnHandle_t>(h));
+    return GRM_CUDA_OK;
+}
+
+int32_t grm_cusolver_params_destroy(void *p) {
+    cusolverDnDestroyParams(static_cast<cusolverDnParams_t>(p));
     return GRM_CUDA_OK;
 }
 
@@ -441,7 +526,8 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
     const double eps = DBL_EPSILON;
     const double maxabs = bits_to_double(h_scan[1]);
     // two rounds in flight from n = 3072 (below, a factorisation is too short to be worth a second stream and thread)
-    const bool pairs = ctx->tune.repair != 1 && ctx->tune.repair_det != 1 && n >= 3072;
+    // (and only while three work matrices are small next to the 180 GB: the 64-bit range runs one round at a time)
+    const bool pairs = ctx->tune.repair != 1 && ctx->tune.repair_det != 1 && n >= 3072 && n <= LEGACY_MAX_N;
     Engine e;
     GRM_TRY(e.setup(ctx, n, pairs ? 2 : 1));
     int64_t b = -1;  // first round of the batch whose results are held
@@ -617,10 +703,6 @@ extern "C" int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t
         grm_set_error("cholesky: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
-    if (n > 46000) {
-        grm_set_error("cholesky: n=%lld exceeds the single-GPU cuSOLVER range (n <= 46000)", (long long)n);
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     if (!ctx->cusolver) {
         cusolverDnHandle_t h;
@@ -648,13 +730,13 @@ extern "C" int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t
     upper_to_lower_kernel<<<dim3(nt, nt), dim3(32, 8), 0, ctx->stream>>>(dX, n, ldd, F);
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
-    int lw = 0;
-    GRM_SOLVER_TRY(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), F, static_cast<int>(n), &lw));
-    GRM_TRY(ctx->lu_work.reserve(std::max<size_t>(static_cast<size_t>(lw), 1) * sizeof(double)));
+    FactorPlan plan;
+    GRM_TRY(potrf_plan(ctx, h, n, F, &plan));
+    GRM_TRY(ctx->lu_work.reserve(plan.dev_bytes));
+    std::vector<char> h_work(plan.host_bytes);
     GRM_TRY(ctx->misc.reserve(64));
     int *info = ctx->misc.as<int>();
-    GRM_SOLVER_TRY(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, static_cast<int>(n), F, static_cast<int>(n),
-                                    ctx->lu_work.as<double>(), lw, info));
+    GRM_TRY(potrf_run(h, plan, n, F, ctx->lu_work.ptr, h_work.data(), info));
     int h_info = 0;
     GRM_CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

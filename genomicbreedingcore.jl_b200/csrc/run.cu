@@ -1009,11 +1009,6 @@ int32_t Run::go() {
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     const bool do_repair = !o.skip_repair && !sharded && !out_tiles;
-    if (do_repair && n > 46000) {
-        grm_set_error("inflatediagonals! on n = %lld exceeds the single-GPU cuSOLVER range (n <= 46000); pass skip_repair "
-                      "to obtain the raw GRM", (long long)n);
-        return GRM_CUDA_ERR_BAD_ARGUMENT;
-    }
     if (n > INT32_MAX - 512 || p > INT32_MAX - 512) {
         grm_set_error("n and p must fit TMA's 32-bit coordinates");
         return GRM_CUDA_ERR_BAD_ARGUMENT;

@@ -608,7 +608,7 @@ def test_repair_variants_agree():
         "grmsimple": grm_call(synth.dosage(n, 6000, 4, seed=4), None, skip_repair=True)[0],
         "det underflows, one round": np.asfortranarray(np.eye(n) * 0.5),
         "det overflows, untouched": np.asfortranarray(np.eye(n) * 1e3),
-        "tiny values, several rounds": np.asfortranarray(np.eye(n) * 1e-3),
+        "several rounds": np.asfortranarray(np.eye(n) * 0.3),  # 0.3^n, 0.6^n, 0.9^n underflow; 1.2^n overflows: 3 rounds
         "indefinite": np.asfortranarray(np.eye(n) - 2.0 * np.diag((np.arange(n) % 7 == 0).astype(float))),
     }
     W = rng.standard_normal((n, 40))
@@ -688,6 +688,54 @@ def test_repair_reports_how_the_determinant_was_formed():
     finally:
         c_def.close()
         c_lit.close()
+
+
+def test_repair_beyond_the_32_bit_range_of_the_legacy_cusolver_entry_points():
+    """n > 46,000: n * n no longer fits the 32-bit indexing of cusolverDnDpotrf / Dgetrf, the 64-bit entry points (Xpotrf /
+    Xgetrf) take over (repair.cu: LEGACY_MAX_N).  Device-resident matrix, default rule against the literal LU-first order;
+    the cached factor is checked through U'U = X on a few rows."""
+    import ctypes as C
+
+    import torch
+
+    n = 46_080
+    free, _total = torch.cuda.mem_get_info(0)
+    if free < 8 * n * n * 7:
+        pytest.skip("needs about 120 GB of free device memory")
+    g = torch.Generator(device=dev()).manual_seed(3)
+    X = torch.rand((n, n), dtype=torch.float64, device=dev(), generator=g)
+    X = (X + X.T) * (0.25 / n)          # small symmetric off-diagonal part: row sums below 0.5
+    X.diagonal().fill_(0.6)             # diagonally dominant => positive definite; det ~ 0.6^n underflows => one round,
+    torch.cuda.synchronize()            # after which det ~ 1.2^n overflows: both far from eps, no LU needed by default
+    torch.cuda.empty_cache()            # the library allocates with cudaMalloc, next to torch's cache
+    out = {}
+    for tag, knob in (("default", 0), ("lu_first", 1)):
+        c = grm_b200.Context(0)
+        try:
+            c.set_tuning("repair_det", knob)
+            Y = X.clone()
+            torch.cuda.synchronize()
+            it, tot = C.c_int32(0), C.c_double(0.0)
+            _lib.check(c.lib.grm_cuda_inflate_diagonals(c.handle, C.c_void_p(Y.data_ptr()), n, n, 1000, _lib.LOC_DEVICE,
+                                                        C.byref(it), C.byref(tot)))
+            c.synchronize()
+            out[tag] = (it.value, tot.value, Y)
+            if tag == "default":
+                U = torch.empty((n, n), dtype=torch.float64, device=dev())  # column-major n x n == U.T in torch's view
+                _lib.check(c.lib.grm_cuda_last_factor(c.handle, n, C.c_void_p(U.data_ptr()), n, _lib.LOC_DEVICE))
+                c.synchronize()
+                Ut = U  # Ut[j, i] = U_colmajor[i, j]
+                for i in (0, 1, 12_345, n - 1):
+                    row = Ut @ Ut[i]  # (U'U)[:, i] = sum_k U[k, :] U[k, i]; in torch's view: Ut[:, k] Ut[i, k]
+                    assert torch.allclose(row, Y[i], rtol=0.0, atol=1e-12)
+                assert float(Ut[5, 7]) == 0.0 and float(Ut[7, 5]) != 0.0  # U[7,5] (below the diagonal) is zero, U[5,7] is not
+                del U, Ut
+        finally:
+            c.close()
+    (i0, t0, Y0), (i1, t1, Y1) = out["default"], out["lu_first"]
+    assert (i0, t0) == (i1, t1) == (1, 0.6)
+    assert torch.equal(Y0, Y1)
+    assert torch.equal(Y0.diagonal(), torch.full((n,), 0.6 + 0.6, dtype=torch.float64, device=dev()))
 
 
 def C_inflate(ctx, Y, max_iter):
