@@ -132,7 +132,8 @@ extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) {
     for (auto &ev : ctx->ev) GRM_CUDA_TRY(cudaEventCreate(&ev));
     for (auto &ev : ctx->wave_ev) GRM_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) {
-        GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+        // waited for by host threads (ingest ring, result copy-out) while the worker pool needs every core: block, do not spin
+        GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming | cudaEventBlockingSync));
         GRM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming));
     }
     *out = ctx;

@@ -126,8 +126,9 @@ static inline int8_t quantise_cell(double x, bool is_float, bool have_sel, doubl
 // fill its share of the memory system; prefetching a few KB ahead does (measured on the build host: 7.8 -> 11.7 GB/s per
 // thread, 56 -> 73 GB/s on 8 threads; on the B200 host, 16 threads: 97 GB/s without, 150 at 4 KB, 157 at 8 KB —
 // profiles/host_ingest_sweep_r2.jsonl).  Run-time adjustable (grm_cuda_host_tune) so that it can be swept on the target.
-static int g_pf_dist = 8192;
-void grm_host_set_prefetch(int bytes) { g_pf_dist = bytes < 0 ? 0 : (bytes > (1 << 20) ? (1 << 20) : bytes); }
+constexpr int PF_DIST_DEFAULT = 16384;
+static int g_pf_dist = PF_DIST_DEFAULT;
+void grm_host_set_prefetch(int bytes) { g_pf_dist = bytes < 0 ? PF_DIST_DEFAULT : (bytes > (1 << 20) ? (1 << 20) : bytes); }
 int grm_host_get_prefetch(void) { return g_pf_dist; }
 
 static uint32_t quantise_col_scalar(const double *x, const uint8_t *s, int tag, int64_t n, double mf, int8_t *out) {
@@ -136,18 +137,32 @@ static uint32_t quantise_col_scalar(const double *x, const uint8_t *s, int tag, 
     return flags;
 }
 
+// Cache level the software prefetch asks for (0 = T0: all levels, 1 = T1, 2 = T2, 3 = NTA) and whether the codes are
+// written with streaming stores: the ring slot is read next by the copy engine, never by this core, and a streaming store
+// spares the read-for-ownership of the output line (1/9 of the pass's read traffic).  Same-box sweep on the B200 host's 16
+// threads (profiles/host_ingest_hints_r2.jsonl): T0 / 8 KB / plain stores 144 GB/s of source, streaming stores 166, T2 +
+// streaming stores at 8 - 32 KB 169 - 170 (NTA: 95).  Defaults: T2, 16 KB, streaming stores.
+constexpr int PF_HINT_DEFAULT = 2, NT_STORE_DEFAULT = 1;
+static int g_pf_hint = PF_HINT_DEFAULT;
+static int g_nt_store = NT_STORE_DEFAULT;
+void grm_host_set_prefetch_hint(int hint) { g_pf_hint = hint < 0 ? PF_HINT_DEFAULT : (hint > 3 ? 3 : hint); }
+int grm_host_get_prefetch_hint(void) { return g_pf_hint; }
+void grm_host_set_stream_stores(int on) { g_nt_store = on < 0 ? NT_STORE_DEFAULT : (on ? 1 : 0); }
+int grm_host_get_stream_stores(void) { return g_nt_store; }
+
+template <int HINT, bool NT>
 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq"))) static uint32_t
-quantise_col_avx512(const double *x, const uint8_t *s, int tag, int64_t n, double mf, int m, int8_t *out) {
+quantise_col_avx512_impl(const double *x, const uint8_t *s, int tag, int64_t n, double mf, int m, int8_t *out, int pf) {
     uint32_t flags = 0;
     const __m512d vm = _mm512_set1_pd(mf);
     const __m256i vmax = _mm256_set1_epi32(m);
     const __m128i vtag = _mm_set1_epi8(static_cast<char>(tag));
     int64_t i = 0;
-    const int pf = g_pf_dist;
+    constexpr _mm_hint hint = HINT == 0 ? _MM_HINT_T0 : HINT == 1 ? _MM_HINT_T1 : HINT == 2 ? _MM_HINT_T2 : _MM_HINT_NTA;
     for (; i + 16 <= n; i += 16) {
         if (pf) {
-            _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf, _MM_HINT_T0);
-            _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf + 64, _MM_HINT_T0);
+            _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf, hint);
+            _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf + 64, hint);
         }
         const __m512d t0 = _mm512_mul_pd(_mm512_loadu_pd(x + i), vm);
         const __m512d t1 = _mm512_mul_pd(_mm512_loadu_pd(x + i + 8), vm);
@@ -159,14 +174,31 @@ quantise_col_avx512(const double *x, const uint8_t *s, int tag, int64_t n, doubl
         if (s) ok &= _mm_cmpeq_epi8_mask(_mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i)), vtag);
         if (ok == 0xFFFF) {
             const __m512i c = _mm512_inserti64x4(_mm512_castsi256_si512(c0), c1, 1);
-            _mm_storeu_si128(reinterpret_cast<__m128i *>(out + i), _mm512_cvtepi32_epi8(c));
+            if (NT) _mm_stream_si128(reinterpret_cast<__m128i *>(out + i), _mm512_cvtepi32_epi8(c));  // out + i is 16-byte aligned
+            else _mm_storeu_si128(reinterpret_cast<__m128i *>(out + i), _mm512_cvtepi32_epi8(c));
         } else {
             for (int j = 0; j < 16; ++j)
                 out[i + j] = quantise_cell(x[i + j], !s || s[i + j] == tag, s != nullptr, mf, flags);
         }
     }
     for (; i < n; ++i) out[i] = quantise_cell(x[i], !s || s[i] == tag, s != nullptr, mf, flags);
+    if (NT) _mm_sfence();  // the column is complete before its unit is reported done
     return flags;
+}
+
+static uint32_t quantise_col_avx512(const double *x, const uint8_t *s, int tag, int64_t n, double mf, int m, int8_t *out) {
+    const int pf = g_pf_dist;
+    const bool nt = g_nt_store && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    switch (g_pf_hint * 2 + (nt ? 1 : 0)) {
+        case 1: return quantise_col_avx512_impl<0, true>(x, s, tag, n, mf, m, out, pf);
+        case 2: return quantise_col_avx512_impl<1, false>(x, s, tag, n, mf, m, out, pf);
+        case 3: return quantise_col_avx512_impl<1, true>(x, s, tag, n, mf, m, out, pf);
+        case 4: return quantise_col_avx512_impl<2, false>(x, s, tag, n, mf, m, out, pf);
+        case 5: return quantise_col_avx512_impl<2, true>(x, s, tag, n, mf, m, out, pf);
+        case 6: return quantise_col_avx512_impl<3, false>(x, s, tag, n, mf, m, out, pf);
+        case 7: return quantise_col_avx512_impl<3, true>(x, s, tag, n, mf, m, out, pf);
+        default: return quantise_col_avx512_impl<0, false>(x, s, tag, n, mf, m, out, pf);
+    }
 }
 
 __attribute__((target("avx2"))) static uint32_t quantise_col_avx2(const double *x, const uint8_t *s, int tag, int64_t n,

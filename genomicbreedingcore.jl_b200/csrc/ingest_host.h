@@ -46,5 +46,10 @@ void grm_host_detect(const double *payload, const uint8_t *sel, int float_tag, i
 // software prefetch distance of the quantiser, bytes (0 = off)
 void grm_host_set_prefetch(int bytes);
 int grm_host_get_prefetch(void);
+// cache level of that prefetch (0 T0, 1 T1, 2 T2, 3 NTA) and streaming stores for the codes (0 / 1)
+void grm_host_set_prefetch_hint(int hint);
+int grm_host_get_prefetch_hint(void);
+void grm_host_set_stream_stores(int on);
+int grm_host_get_stream_stores(void);
 // name of the SIMD level the passes above dispatch to on this machine ("avx512", "avx2", "scalar")
 const char *grm_host_simd(void);

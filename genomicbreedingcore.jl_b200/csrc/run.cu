@@ -1352,8 +1352,17 @@ extern "C" int32_t grm_cuda_host_detect(const double *payload, const uint8_t *se
 extern "C" const char *grm_cuda_host_simd(void) { return grm_host_simd(); }
 
 extern "C" int32_t grm_cuda_host_tune(const char *key, int64_t value) {
+    // a negative value restores the default of the key
     if (key && !strcmp(key, "prefetch")) {
-        grm_host_set_prefetch(static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20))));
+        grm_host_set_prefetch(static_cast<int>(std::max<int64_t>(-1, std::min<int64_t>(value, 1 << 20))));
+        return GRM_CUDA_OK;
+    }
+    if (key && !strcmp(key, "prefetch_hint")) {
+        grm_host_set_prefetch_hint(static_cast<int>(std::max<int64_t>(-1, std::min<int64_t>(value, 3))));
+        return GRM_CUDA_OK;
+    }
+    if (key && !strcmp(key, "stream_stores")) {
+        grm_host_set_stream_stores(value < 0 ? -1 : (value != 0));
         return GRM_CUDA_OK;
     }
     grm_set_error("host_tune: unknown key (%s)", key ? key : "null");

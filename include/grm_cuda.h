@@ -234,7 +234,10 @@ int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *selectors, 
 int32_t grm_cuda_host_detect(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
                              int64_t lda, int64_t max_cells, int32_t ignore_missing, int32_t *m_out);
 const char *grm_cuda_host_simd(void);
-/* Process-wide knobs of the host quantiser: "prefetch" = software prefetch distance in bytes (0 = off, default 8192). */
+/* Process-wide knobs of the host quantiser (memory-system tuning only, results never change; a negative value restores
+ * the default): "prefetch" = software prefetch distance in bytes (0 = off, default 16384), "prefetch_hint" = cache level
+ * asked for (0 T0, 1 T1, 2 T2 = default, 3 NTA), "stream_stores" = write the codes into the pinned ring with streaming
+ * stores (default 1). */
 int32_t grm_cuda_host_tune(const char *key, int64_t value);
 /* Host half of the repair's determinant (calc.jl:49,61; no device needed, exported for tests).
  * grm_cuda_host_lu_det: Julia's det(::LU) from diag(U) and LAPACK's 1-based ipiv: sequential binary64 product, sign by

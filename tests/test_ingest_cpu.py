@@ -74,6 +74,30 @@ def test_host_quantiser_matches_the_pack_rule_cell_by_cell(n, p, m, with_sel):
     assert np.array_equal(got[:, :n].T, want) and np.all(got[:, n:] == 99)
 
 
+@pytest.mark.parametrize("hint", [0, 1, 2, 3])
+@pytest.mark.parametrize("stream", [0, 1])
+def test_host_quantiser_prefetch_hint_and_streaming_stores_change_nothing(hint, stream):
+    """grm_cuda_host_tune("prefetch_hint" / "stream_stores"): memory-system knobs only — same codes, same flags, also
+    when a column of the output is not 16-byte aligned (streaming stores are then not used for it)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    try:
+        assert lib.grm_cuda_host_tune(b"prefetch_hint", hint) == _lib.OK
+        assert lib.grm_cuda_host_tune(b"stream_stores", stream) == _lib.OK
+        for n in (64, 1000, 1001):  # ldo = n: aligned columns, columns aligned every other time, never aligned
+            A = np.asfortranarray(rng.integers(0, 5, (n, 37)) / 4.0)
+            sel = np.ones((n, 37), dtype=np.uint8, order="F")
+            A[5, 3], A[n - 1, 36], A[17, 20] = np.nan, 0.3, np.inf
+            sel[9, 9] = 0
+            want, wflags = np_quantise(A, sel, 1, 4)
+            got, flags = host_quantise(A, sel, 1, 4, 3)
+            assert np.array_equal(got.T, want) and flags == wflags
+    finally:
+        lib.grm_cuda_host_tune(b"prefetch_hint", -1)  # back to the defaults
+        lib.grm_cuda_host_tune(b"stream_stores", -1)
+    assert lib.grm_cuda_host_tune(b"no_such_knob", 1) != _lib.OK
+
+
 def test_host_quantiser_other_float_tag_and_simd_level():
     lib = _lib.load()
     assert lib.grm_cuda_host_simd() in (b"avx512", b"avx2", b"scalar")
