@@ -95,7 +95,7 @@ void DevBuf::release() {
     cap = 0;
 }
 
-extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) {
+extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) try {
     if (!out) {
         grm_set_error("ctx_create: null output pointer");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -138,12 +138,12 @@ extern "C" int32_t grm_cuda_ctx_create(int32_t device, grm_cuda_ctx **out) {
     }
     *out = ctx;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 int32_t grm_cusolver_destroy(void *h);
 int32_t grm_cusolver_params_destroy(void *p);
 
-extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
+extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) try {
     if (!ctx) return GRM_CUDA_OK;
     cudaSetDevice(ctx->device);
     if (ctx->comm) grm_comm_abort(ctx);  // never wait for collectives the peers may not enter any more
@@ -180,18 +180,18 @@ extern "C" int32_t grm_cuda_ctx_destroy(grm_cuda_ctx *ctx) {
     cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" void *grm_cuda_ctx_stream(grm_cuda_ctx *ctx) { return ctx ? ctx->stream : nullptr; }
 
-extern "C" int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx) {
+extern "C" int32_t grm_cuda_ctx_synchronize(grm_cuda_ctx *ctx) try {
     if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->comm_stream));
     GRM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 // ---------------------------------------------------------------------------------------------------------------
 // per-context kernel attributes and tuning knobs
@@ -224,7 +224,7 @@ static int *tuning_slot(GrmTuning &t, const char *key) {
     return nullptr;
 }
 
-extern "C" int32_t grm_cuda_ctx_set_tuning(grm_cuda_ctx *ctx, const char *key, int64_t value) {
+extern "C" int32_t grm_cuda_ctx_set_tuning(grm_cuda_ctx *ctx, const char *key, int64_t value) try {
     int *slot = (ctx && key) ? tuning_slot(ctx->tune, key) : nullptr;
     if (!slot || value < INT32_MIN || value > INT32_MAX) {
         grm_set_error("ctx_set_tuning: unknown key or bad value (%s)", key ? key : "null");
@@ -236,9 +236,9 @@ extern "C" int32_t grm_cuda_ctx_set_tuning(grm_cuda_ctx *ctx, const char *key, i
         ctx->pool = nullptr;
     }
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
-extern "C" int32_t grm_cuda_ctx_get_tuning(grm_cuda_ctx *ctx, const char *key, int64_t *value) {
+extern "C" int32_t grm_cuda_ctx_get_tuning(grm_cuda_ctx *ctx, const char *key, int64_t *value) try {
     int *slot = (ctx && key) ? tuning_slot(ctx->tune, key) : nullptr;
     if (!slot || !value) {
         grm_set_error("ctx_get_tuning: unknown key (%s)", key ? key : "null");
@@ -246,7 +246,7 @@ extern "C" int32_t grm_cuda_ctx_get_tuning(grm_cuda_ctx *ctx, const char *key, i
     }
     *value = *slot;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 // ---------------------------------------------------------------------------------------------------------------
 // tile partition: 256 x 256 tiles of the upper triangle, enumerated in bands of `band` tile rows so that tiles that are
@@ -273,15 +273,15 @@ void grm_tile_range(int64_t total, int32_t rank, int32_t world, int64_t *begin, 
 
 extern "C" int32_t grm_cuda_tile_edge(void) { return GRM_TILE; }
 
-extern "C" int64_t grm_cuda_tile_count(int64_t n, int32_t rank, int32_t world) {
+extern "C" int64_t grm_cuda_tile_count(int64_t n, int32_t rank, int32_t world) try {
     if (n < 1 || world < 1 || rank < 0 || rank >= world) return -1;
     const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
     int64_t b, e;
     grm_tile_range(T * (T + 1) / 2, rank, world, &b, &e);
     return e - b;
-}
+} GRM_CATCH_I64
 
-extern "C" int32_t grm_cuda_tile_owner(int64_t n, int64_t ti, int64_t tj, int32_t world) {
+extern "C" int32_t grm_cuda_tile_owner(int64_t n, int64_t ti, int64_t tj, int32_t world) try {
     if (n < 1 || world < 1 || ti < 0 || tj < ti) return -1;
     std::vector<int2> order;
     grm_tile_order(n, 0, order);
@@ -295,10 +295,10 @@ extern "C" int32_t grm_cuda_tile_owner(int64_t n, int64_t ti, int64_t tj, int32_
             }
         }
     return -1;
-}
+} GRM_CATCH_I64
 
 // position t of the rank's tile list -> (ti, tj); lets a host build gather plans without a device
-extern "C" int32_t grm_cuda_tile_at(int64_t n, int32_t rank, int32_t world, int64_t t, int64_t *ti, int64_t *tj) {
+extern "C" int32_t grm_cuda_tile_at(int64_t n, int32_t rank, int32_t world, int64_t t, int64_t *ti, int64_t *tj) try {
     if (n < 1 || world < 1 || rank < 0 || rank >= world || !ti || !tj) return GRM_CUDA_ERR_BAD_ARGUMENT;
     std::vector<int2> order;
     grm_tile_order(n, 0, order);
@@ -308,5 +308,5 @@ extern "C" int32_t grm_cuda_tile_at(int64_t n, int32_t rank, int32_t world, int6
     *ti = order[b + t].x;
     *tj = order[b + t].y;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 

@@ -108,7 +108,7 @@ static int32_t nccl_load() {
         }                                                                                                   \
     } while (0)
 
-extern "C" int32_t grm_cuda_comm_set_library(const char *path) {
+extern "C" int32_t grm_cuda_comm_set_library(const char *path) try {
     if (g_nccl.handle) {
         grm_set_error("comm_set_library: NCCL is already loaded");
         return GRM_CUDA_ERR_COMM;
@@ -119,9 +119,9 @@ extern "C" int32_t grm_cuda_comm_set_library(const char *path) {
     }
     strcpy(g_nccl_path, path);
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
-extern "C" int32_t grm_cuda_comm_unique_id(uint8_t *id128) {
+extern "C" int32_t grm_cuda_comm_unique_id(uint8_t *id128) try {
     static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
     if (!id128) {
         grm_set_error("comm_unique_id: null pointer");
@@ -132,7 +132,7 @@ extern "C" int32_t grm_cuda_comm_unique_id(uint8_t *id128) {
     GRM_NCCL_TRY(g_nccl.GetUniqueId(&id));
     memcpy(id128, &id, 128);
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 static void peer_release(GrmComm *c) {
     for (int q = 0; q < c->world; ++q)
@@ -167,7 +167,7 @@ int32_t grm_comm_destroy(grm_cuda_ctx *ctx) {
     return GRM_CUDA_OK;
 }
 
-extern "C" int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world) {
+extern "C" int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, int32_t rank, int32_t world) try {
     if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) {
         grm_set_error("comm_init: bad argument (rank=%d world=%d)", rank, world);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -209,7 +209,7 @@ extern "C" int32_t grm_cuda_comm_init(grm_cuda_ctx *ctx, const uint8_t *id128, i
     for (auto &x : c->xs) GRM_CUDA_TRY(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, prio_greatest));
     for (auto &e : c->xe) GRM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 // ---------------------------------------------------------------------------------------------------------------
 // peer-mapped receive buffer
@@ -264,14 +264,14 @@ uint32_t grm_comm_next_epoch(grm_cuda_ctx *ctx) { return ++ctx->comm->epoch; }
 cudaStream_t grm_comm_xstream(grm_cuda_ctx *ctx, int i) { return ctx->comm->xs[i % GRM_XSTREAMS]; }
 cudaEvent_t grm_comm_xevent(grm_cuda_ctx *ctx, int i) { return ctx->comm->xe[i % (GRM_XSTREAMS + 1)]; }
 
-extern "C" int32_t grm_cuda_comm_destroy(grm_cuda_ctx *ctx) {
+extern "C" int32_t grm_cuda_comm_destroy(grm_cuda_ctx *ctx) try {
     if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     return grm_comm_destroy(ctx);
-}
+} GRM_CATCH_STATUS
 
-extern "C" int32_t grm_cuda_comm_info(grm_cuda_ctx *ctx, int32_t *rank, int32_t *world, int32_t *nccl_version) {
+extern "C" int32_t grm_cuda_comm_info(grm_cuda_ctx *ctx, int32_t *rank, int32_t *world, int32_t *nccl_version) try {
     if (!ctx) return GRM_CUDA_ERR_BAD_ARGUMENT;
     if (rank) *rank = ctx->comm ? ctx->comm->rank : 0;
     if (world) *world = ctx->comm ? ctx->comm->world : 1;
@@ -281,7 +281,7 @@ extern "C" int32_t grm_cuda_comm_info(grm_cuda_ctx *ctx, int32_t *rank, int32_t 
         *nccl_version = v;
     }
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 int grm_comm_rank(const grm_cuda_ctx *ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 int grm_comm_world(const grm_cuda_ctx *ctx) { return ctx->comm ? ctx->comm->world : 1; }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <exception>
+#include <new>
 #include <string>
 #include <utility>
 #include <vector>
@@ -30,6 +32,27 @@ void grm_set_error(const char *fmt, ...);
         int32_t _s = (expr);                 \
         if (_s != GRM_CUDA_OK) return _s;    \
     } while (0)
+
+// Every extern "C" entry point is a function-try-block closed by one of these: a C++ exception from the host runtime
+// (std::bad_alloc of a vector, std::system_error of a thread) ends as a status, never in the caller's frames — Julia's
+// ccall, like any C caller, cannot unwind through them.
+#define GRM_CATCH_STATUS                                                    \
+    catch (const std::bad_alloc &) {                                        \
+        grm_set_error("out of host memory");                                \
+        return GRM_CUDA_ERR_OOM;                                            \
+    }                                                                       \
+    catch (const std::exception &e) {                                       \
+        grm_set_error("internal error: %s", e.what());                      \
+        return GRM_CUDA_ERR_CUDA;                                           \
+    }                                                                       \
+    catch (...) {                                                           \
+        grm_set_error("internal error: unknown C++ exception");             \
+        return GRM_CUDA_ERR_CUDA;                                           \
+    }
+#define GRM_CATCH_I64                                                       \
+    catch (...) {                                                           \
+        return -1;                                                          \
+    }
 
 // grow-only device buffer
 struct DevBuf {

@@ -277,7 +277,7 @@ __global__ void finish_split_kernel(const double *part1, const double *part2, in
 extern "C" int32_t grm_cuda_distances(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
                                       int32_t a_location, const int64_t *idx_loci, int64_t t, int32_t dimension,
                                       double *euclidean, double *correlation, double *mad, double *rmsd, double *chi2,
-                                      double *counts, int64_t ldo, int32_t out_location) {
+                                      double *counts, int64_t ldo, int32_t out_location) try {
     const int64_t r = dimension == GRM_CUDA_DIM_ENTRIES ? n : t;
     if (!ctx || !A || !idx_loci || n < 1 || p < 1 || lda < n || t < 1 || t > p ||
         (dimension != GRM_CUDA_DIM_ENTRIES && dimension != GRM_CUDA_DIM_LOCI) || ldo < r ||
@@ -397,4 +397,4 @@ extern "C" int32_t grm_cuda_distances(grm_cuda_ctx *ctx, const double *A, int64_
     }
     GRM_CUDA_TRY(cudaStreamSynchronize(st));
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS

@@ -776,7 +776,7 @@ int32_t grm_launch_detect(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_
 }
 
 extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
-                                               int64_t max_cells, int32_t ignore_missing, int32_t *m_out) {
+                                               int64_t max_cells, int32_t ignore_missing, int32_t *m_out) try {
     if (!ctx || !dA || !m_out || n < 1 || p < 1 || lda < n) {
         grm_set_error("detect_denominator: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -800,11 +800,11 @@ extern "C" int32_t grm_cuda_detect_denominator(grm_cuda_ctx *ctx, const double *
     }
     *m_out = 64 >> tz;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
                                         int32_t m, int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
-                                        int32_t *d_miss) {
+                                        int32_t *d_miss) try {
     if (!ctx || !dA || !d_codes || !d_colsum || !d_flags || n < 1 || pc < 1 || lda < n || m < 1 || m > 64 ||
         (m & (m - 1)) != 0 || (ldc % 128) != 0 || ldc < ((pc + 127) / 128) * 128) {
         grm_set_error("pack_dosage: bad argument (n=%lld pc=%lld lda=%lld m=%d ldc=%lld)", (long long)n, (long long)pc,
@@ -857,11 +857,11 @@ extern "C" int32_t grm_cuda_pack_dosage(grm_cuda_ctx *ctx, const double *dA, int
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_pack_codes(grm_cuda_ctx *ctx, const int8_t *d_src, int64_t n, int64_t pc, int64_t lds,
                                        int8_t *d_codes, int64_t ldc, int32_t *d_colsum, uint32_t *d_flags,
-                                       int32_t *d_miss) {
+                                       int32_t *d_miss) try {
     if (!ctx || !d_src || !d_codes || !d_colsum || !d_flags || n < 1 || pc < 1 || lds < n || (lds % 4) != 0 ||
         (reinterpret_cast<uintptr_t>(d_src) % 4) != 0 || (ldc % 128) != 0 || ldc < ((pc + 127) / 128) * 128) {
         grm_set_error("pack_codes: bad argument (n=%lld pc=%lld lds=%lld ldc=%lld)", (long long)n, (long long)pc,
@@ -881,11 +881,11 @@ extern "C" int32_t grm_cuda_pack_codes(grm_cuda_ctx *ctx, const int8_t *d_src, i
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_locus_keep(grm_cuda_ctx *ctx, int32_t *d_colsum, const int32_t *d_miss, int64_t n, int64_t p,
                                        int32_t m, double maf, double max_locus_sparsity, int32_t error_on_missing,
-                                       uint8_t *d_keep, uint64_t *d_kept, uint32_t *d_flags) {
+                                       uint8_t *d_keep, uint64_t *d_kept, uint32_t *d_flags) try {
     if (!ctx || !d_colsum || !d_miss || !d_keep || !d_kept || !d_flags || n < 1 || p < 1 || m < 1) {
         grm_set_error("locus_keep: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -897,10 +897,10 @@ extern "C" int32_t grm_cuda_locus_keep(grm_cuda_ctx *ctx, int32_t *d_colsum, con
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_mask_codes(grm_cuda_ctx *ctx, int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                       const uint8_t *d_keep) {
+                                       const uint8_t *d_keep) try {
     if (!ctx || !d_codes || !d_keep || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p) {
         grm_set_error("mask_codes: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -912,10 +912,10 @@ extern "C" int32_t grm_cuda_mask_codes(grm_cuda_ctx *ctx, int8_t *d_codes, int64
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_locus_stats_i8(grm_cuda_ctx *ctx, const int32_t *d_colsum, int64_t p, int64_t n, int32_t m,
-                                           int32_t ploidy, double *d_q, double *d_w, double *d_stats) {
+                                           int32_t ploidy, double *d_q, double *d_w, double *d_stats) try {
     if (!ctx || !d_colsum || !d_q || !d_w || !d_stats || p < 1 || n < 1 || m < 1) {
         grm_set_error("locus_stats_i8: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -930,11 +930,11 @@ extern "C" int32_t grm_cuda_locus_stats_i8(grm_cuda_ctx *ctx, const int32_t *d_c
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches += 2;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda,
                                             double *d_q, double *d_stats, uint32_t *d_flags, int32_t accumulate,
-                                            int32_t skip_missing) {
+                                            int32_t skip_missing) try {
     if (!ctx || !dA || !d_q || !d_stats || !d_flags || p < 1 || n < 1 || lda < n) {
         grm_set_error("locus_stats_f64: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -950,10 +950,10 @@ extern "C" int32_t grm_cuda_locus_stats_f64(grm_cuda_ctx *ctx, const double *dA,
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches += 3;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                      const double *d_w, double *d_u) {
+                                      const double *d_w, double *d_u) try {
     if (!ctx || !d_codes || !d_w || !d_u || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p) {
         grm_set_error("rowdot_i8: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -964,11 +964,11 @@ extern "C" int32_t grm_cuda_rowdot_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, 
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                          const int32_t *d_colsum, int32_t m, uint64_t *d_sums, int64_t *d_r,
-                                         int64_t *d_T, int32_t accumulate) {
+                                         int64_t *d_T, int32_t accumulate) try {
     if (!ctx || !d_codes || !d_colsum || !d_sums || !d_r || !d_T || n < 1 || p < 1 || (ldc % 128) != 0 || ldc < p ||
         m < 1 || m > 64) {
         grm_set_error("dosage_stats: bad argument");
@@ -998,11 +998,11 @@ extern "C" int32_t grm_cuda_dosage_stats(grm_cuda_ctx *ctx, const int8_t *d_code
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches += 2;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_sums, const int64_t *d_r,
                                           const int64_t *d_T, int64_t n, int64_t p, int32_t m, int32_t ploidy,
-                                          double *d_u, double *scalars /* host: alpha, beta, gamma, denom */) {
+                                          double *d_u, double *scalars /* host: alpha, beta, gamma, denom */) try {
     if (!ctx || !d_sums || !d_r || !d_T || !d_u || !scalars || n < 1 || p < 1 || m < 1) {
         grm_set_error("dosage_centre: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -1029,13 +1029,13 @@ extern "C" int32_t grm_cuda_dosage_centre(grm_cuda_ctx *ctx, const uint64_t *d_s
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 // QC locus mask in one call: q[k] = mean(skipmissing(column k)), keep[k] per the reference's filter rules, the number
 // of kept loci added to *d_kept, and (d_stats != NULL) {sum q(1-q), 0, sum q} over the kept loci.
 extern "C" int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t p, int64_t lda, double maf,
                                      double max_locus_sparsity, int32_t error_on_missing, double *d_q, uint8_t *d_keep,
-                                     uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags) {
+                                     uint64_t *d_kept, double *d_stats, int32_t accumulate_stats, uint32_t *d_flags) try {
     if (!ctx || !dA || !d_q || !d_keep || !d_kept || !d_flags || n < 1 || p < 1 || lda < n) {
         grm_set_error("locus_qc: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -1059,4 +1059,4 @@ extern "C" int32_t grm_cuda_locus_qc(grm_cuda_ctx *ctx, const double *dA, int64_
         ctx->launches += 2;
     }
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS

@@ -594,7 +594,7 @@ int32_t grm_repair_device(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, 
 // probe is the arithmetic of the single-GPU loop, so the outcome is identical.
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, int64_t n, int64_t ldx, int32_t rounds,
-                                         double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs) {
+                                         double *det_out, int32_t *posdef_out, uint32_t *scan_flags, double *maxabs) try {
     if (!ctx || !dX || n < 1 || ldx < n || rounds < 0 || !det_out || !posdef_out || !scan_flags || !maxabs) {
         grm_set_error("repair_probe: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -616,10 +616,10 @@ extern "C" int32_t grm_cuda_repair_probe(grm_cuda_ctx *ctx, const double *dX, in
     *posdef_out = (ctx->tune.repair_det == 1 && *det_out < DBL_EPSILON) ? -1 : (pd ? 1 : 0);
     ctx->factor_buf = 0;  // a caller that finds this probe to be the deciding one sets ctx->factor_n
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t n, int64_t ldx, int32_t rounds,
-                                         double maxabs, double *eps_total) {
+                                         double maxabs, double *eps_total) try {
     if (!ctx || !dX || n < 1 || ldx < n || rounds < 0) {
         grm_set_error("repair_apply: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -639,12 +639,12 @@ extern "C" int32_t grm_cuda_repair_apply(grm_cuda_ctx *ctx, double *dX, int64_t 
         *eps_total = total;
     }
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
-extern "C" int32_t grm_cuda_host_chol_det(const double *diag_l, int64_t n, double scale, double *det_out) {
+extern "C" int32_t grm_cuda_host_chol_det(const double *diag_l, int64_t n, double scale, double *det_out) try {
     if (!diag_l || n < 1 || !det_out) return -1;
     return grm_det_chol_pivots(diag_l, n, scale, det_out);
-}
+} GRM_CATCH_STATUS
 
 extern "C" double grm_cuda_host_lu_det(const double *diag_u, const int32_t *ipiv, int64_t n) {
     if (!diag_u || !ipiv || n < 1) return NAN;
@@ -681,7 +681,7 @@ int32_t emit_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_
 
 }  // namespace
 
-extern "C" int32_t grm_cuda_last_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_t location) {
+extern "C" int32_t grm_cuda_last_factor(grm_cuda_ctx *ctx, int64_t n, double *U, int64_t ldu, int32_t location) try {
     if (!ctx || !U || n < 1 || ldu < n || (location != GRM_CUDA_LOC_HOST && location != GRM_CUDA_LOC_DEVICE)) {
         grm_set_error("last_factor: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -693,10 +693,10 @@ extern "C" int32_t grm_cuda_last_factor(grm_cuda_ctx *ctx, int64_t n, double *U,
     }
     GRM_CUDA_TRY(cudaSetDevice(ctx->device));
     return emit_factor(ctx, n, U, ldu, location);
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t n, int64_t ldx, int32_t x_location,
-                                     double *U, int64_t ldu, int32_t u_location) {
+                                     double *U, int64_t ldu, int32_t u_location) try {
     if (!ctx || !X || !U || n < 1 || ldx < n || ldu < n ||
         (x_location != GRM_CUDA_LOC_HOST && x_location != GRM_CUDA_LOC_DEVICE) ||
         (u_location != GRM_CUDA_LOC_HOST && u_location != GRM_CUDA_LOC_DEVICE)) {
@@ -752,4 +752,4 @@ extern "C" int32_t grm_cuda_cholesky(grm_cuda_ctx *ctx, const double *X, int64_t
     ctx->factor_n = n;
     ctx->factor_buf = 0;
     return emit_factor(ctx, n, U, ldu, u_location);
-}
+} GRM_CATCH_STATUS

@@ -1246,29 +1246,29 @@ int32_t start(Run &r, grm_cuda_ctx *ctx, int64_t n, int64_t p, bool centred, int
 }  // namespace
 
 extern "C" int32_t grm_cuda_simple(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda, double *G,
-                                   int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info) {
+                                   int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info) try {
     Run r;
     start(r, ctx, n, p, false, 0, G, ldg, opts, info);
     r.src.A = A;
     r.src.lda = lda;
     r.src.host = r.o.input_location == GRM_CUDA_LOC_HOST;
     return r.go();
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_ploidyaware(grm_cuda_ctx *ctx, const double *A, int64_t n, int64_t p, int64_t lda,
                                         int32_t ploidy, double *G, int64_t ldg, const grm_cuda_options *opts,
-                                        grm_cuda_info *info) {
+                                        grm_cuda_info *info) try {
     Run r;
     start(r, ctx, n, p, true, ploidy, G, ldg, opts, info);
     r.src.A = A;
     r.src.lda = lda;
     r.src.host = r.o.input_location == GRM_CUDA_LOC_HOST;
     return r.go();
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_simple_union(grm_cuda_ctx *ctx, const double *payload, const uint8_t *selectors,
                                          int32_t float_tag, int64_t n, int64_t p, int64_t lda, double *G, int64_t ldg,
-                                         const grm_cuda_options *opts, grm_cuda_info *info) {
+                                         const grm_cuda_options *opts, grm_cuda_info *info) try {
     Run r;
     start(r, ctx, n, p, false, 0, G, ldg, opts, info);
     r.src.A = payload;
@@ -1277,11 +1277,11 @@ extern "C" int32_t grm_cuda_simple_union(grm_cuda_ctx *ctx, const double *payloa
     r.src.lda = lda;
     r.src.host = true;
     return r.go();
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_ploidyaware_union(grm_cuda_ctx *ctx, const double *payload, const uint8_t *selectors,
                                               int32_t float_tag, int64_t n, int64_t p, int64_t lda, int32_t ploidy,
-                                              double *G, int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info) {
+                                              double *G, int64_t ldg, const grm_cuda_options *opts, grm_cuda_info *info) try {
     Run r;
     start(r, ctx, n, p, true, ploidy, G, ldg, opts, info);
     r.src.A = payload;
@@ -1290,11 +1290,11 @@ extern "C" int32_t grm_cuda_ploidyaware_union(grm_cuda_ctx *ctx, const double *p
     r.src.lda = lda;
     r.src.host = true;
     return r.go();
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_from_codes(grm_cuda_ctx *ctx, const int8_t *codes, int64_t n, int64_t p, int64_t ldc, int32_t m,
                                        int32_t ploidy, double *G, int64_t ldg, const grm_cuda_options *opts,
-                                       grm_cuda_info *info) {
+                                       grm_cuda_info *info) try {
     Run r;
     start(r, ctx, n, p, ploidy >= 0, ploidy >= 0 ? ploidy : 0, G, ldg, opts, info);
     if (m < 1 || m > 64 || (m & (m - 1)) != 0) {
@@ -1307,7 +1307,7 @@ extern "C" int32_t grm_cuda_from_codes(grm_cuda_ctx *ctx, const int8_t *codes, i
     r.src.lda = ldc;
     r.src.host = true;
     return r.go();
-}
+} GRM_CATCH_STATUS
 
 // ---------------------------------------------------------------------------------------------------------------
 // host utilities (no GPU involved): the quantiser of the ingest, callable on its own — it writes the int8 payload of
@@ -1315,7 +1315,7 @@ extern "C" int32_t grm_cuda_from_codes(grm_cuda_ctx *ctx, const int8_t *codes, i
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n,
                                           int64_t p, int64_t lda, int32_t m, int8_t *codes, int64_t ldo, int32_t threads,
-                                          uint32_t *flags) {
+                                          uint32_t *flags) try {
     if (!payload || !codes || n < 1 || p < 1 || lda < n || ldo < n || m < 1 || m > 64 || (m & (m - 1)) != 0) {
         grm_set_error("host_quantise: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -1335,10 +1335,10 @@ extern "C" int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *
     for (uint32_t v : fl) f |= v;
     if (flags) *flags = f;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_host_detect(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n,
-                                        int64_t p, int64_t lda, int64_t max_cells, int32_t ignore_missing, int32_t *m_out) {
+                                        int64_t p, int64_t lda, int64_t max_cells, int32_t ignore_missing, int32_t *m_out) try {
     if (!payload || !m_out || n < 1 || p < 1 || lda < n) {
         grm_set_error("host_detect: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -1347,11 +1347,11 @@ extern "C" int32_t grm_cuda_host_detect(const double *payload, const uint8_t *se
     grm_host_detect(payload, selectors, float_tag, n, p, lda, max_cells > 0 ? max_cells : n * p, ignore_missing, &bits, &fl);
     *m_out = fl ? 0 : denominator_from_bits(bits & 0x7fu);
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
 extern "C" const char *grm_cuda_host_simd(void) { return grm_host_simd(); }
 
-extern "C" int32_t grm_cuda_host_tune(const char *key, int64_t value) {
+extern "C" int32_t grm_cuda_host_tune(const char *key, int64_t value) try {
     // a negative value restores the default of the key
     if (key && !strcmp(key, "prefetch")) {
         grm_host_set_prefetch(static_cast<int>(std::max<int64_t>(-1, std::min<int64_t>(value, 1 << 20))));
@@ -1367,10 +1367,10 @@ extern "C" int32_t grm_cuda_host_tune(const char *key, int64_t value) {
     }
     grm_set_error("host_tune: unknown key (%s)", key ? key : "null");
     return GRM_CUDA_ERR_BAD_ARGUMENT;
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int64_t n, int64_t ldx, int32_t max_iter,
-                                              int32_t location, int32_t *iters, double *eps_total) {
+                                              int32_t location, int32_t *iters, double *eps_total) try {
     if (!ctx || !X || n < 1 || ldx < n || max_iter < 0) {
         grm_set_error("inflate_diagonals: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -1396,4 +1396,4 @@ extern "C" int32_t grm_cuda_inflate_diagonals(grm_cuda_ctx *ctx, double *X, int6
     if (iters) *iters = it;
     if (eps_total) *eps_total = tot;
     return status;
-}
+} GRM_CATCH_STATUS

@@ -389,7 +389,7 @@ int32_t get_tile_list_f64(grm_cuda_ctx *ctx, int64_t n, int32_t rank, int32_t wo
 }  // namespace
 
 extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_t n, int64_t p, int64_t ldz,
-                                     int32_t accumulate, double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+                                     int32_t accumulate, double *d_G, int64_t ldg, int32_t rank, int32_t world) try {
     if (!ctx || !dZ || !d_G || n < 1 || p < 1 || ldz < n || ldg < n || world < 1 || rank < 0 || rank >= world) {
         grm_set_error("syrk_f64: bad argument (n=%lld p=%lld ldz=%lld ldg=%lld)", (long long)n, (long long)p,
                       (long long)ldz, (long long)ldg);
@@ -428,9 +428,9 @@ extern "C" int32_t grm_cuda_syrk_f64(grm_cuda_ctx *ctx, const double *dZ, int64_
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
-extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom) {
+extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg, double denom) try {
     if (!ctx || !d_G || n < 1 || ldg < n) {
         grm_set_error("scale_mirror: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -441,15 +441,15 @@ extern "C" int32_t grm_cuda_scale_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t
     GRM_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS
 
-extern "C" int32_t grm_cuda_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg) {
+extern "C" int32_t grm_cuda_mirror(grm_cuda_ctx *ctx, double *d_G, int64_t n, int64_t ldg) try {
     return grm_cuda_scale_mirror(ctx, d_G, n, ldg, 1.0);
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_centre_f64(grm_cuda_ctx *ctx, const double *dA, int64_t n, int64_t pc, int64_t lda,
                                        int32_t centred, double ploidy, const double *d_q, int32_t fill_missing,
-                                       const uint8_t *d_keep, double *d_Z, int64_t ldz) {
+                                       const uint8_t *d_keep, double *d_Z, int64_t ldz) try {
     if (!ctx || !dA || !d_Z || n < 1 || pc < 1 || lda < n || ldz < n || ((centred || fill_missing) && !d_q) ||
         pc > 2147483647ll) {
         grm_set_error("centre_f64: bad argument");
@@ -467,4 +467,4 @@ extern "C" int32_t grm_cuda_centre_f64(grm_cuda_ctx *ctx, const double *dA, int6
         ctx->launches++;
     }
     return GRM_CUDA_OK;
-}
+} GRM_CATCH_STATUS

@@ -903,7 +903,7 @@ void set_division(const grm_cuda_ctx *ctx, EpiParams &ep, double denom) {
 }  // namespace
 
 extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                    int64_t nslabs, int32_t *d_C, int64_t ldC, int32_t rank, int32_t world) {
+                                    int64_t nslabs, int32_t *d_C, int64_t ldC, int32_t rank, int32_t world) try {
     if (!d_C || ldC < n) {
         grm_set_error("syrk_i8: bad output (ldC=%lld n=%lld)", (long long)ldC, (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -913,11 +913,11 @@ extern "C" int32_t grm_cuda_syrk_i8(grm_cuda_ctx *ctx, const int8_t *d_codes, in
     ep.C = d_C;
     ep.ldC = ldC;
     return launch<0>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
-}
+} GRM_CATCH_STATUS
 
 extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                         int64_t nslabs, double alpha, double beta, double gamma, double denom, const double *d_u,
-                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) {
+                                        double *d_G, int64_t ldg, int32_t rank, int32_t world) try {
     if (!d_G || ldg < n || (beta != 0.0 && !d_u)) {
         grm_set_error("syrk_i8_f64: bad output or missing u (ldg=%lld n=%lld)", (long long)ldg, (long long)n);
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -933,14 +933,14 @@ extern "C" int32_t grm_cuda_syrk_i8_f64(grm_cuda_ctx *ctx, const int8_t *d_codes
     ep.u = d_u;
     if (beta == 0.0 && gamma == 0.0) return launch<1>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
     return launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
-}
+} GRM_CATCH_STATUS
 
 // Sharded-output form of grm_cuda_syrk_i8_f64: the tiles owned by (rank, world) are written as packed 256 x 256 FP64
 // tiles, d_tiles[t][col][row] for the t-th owned tile (grm_cuda_tile_at), zeros outside the n x n matrix.  For outputs
 // that do not fit one device as a dense matrix (BASELINE C5: n = 100,000 -> 80 GB, 10 GB per GPU on 8 GPUs).
 extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
                                               int64_t nslabs, double alpha, double beta, double gamma, double denom,
-                                              const double *d_u, double *d_tiles, int32_t rank, int32_t world) {
+                                              const double *d_u, double *d_tiles, int32_t rank, int32_t world) try {
     if (!ctx || !d_tiles || (beta != 0.0 && !d_u) || n < 1 || world < 1 || rank < 0 || rank >= world) {
         grm_set_error("syrk_i8_f64_tiles: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
@@ -965,7 +965,7 @@ extern "C" int32_t grm_cuda_syrk_i8_f64_tiles(grm_cuda_ctx *ctx, const int8_t *d
                                                      : launch<2>(ctx, d_codes, n, p, ldc, nslabs, ep, rank, world);
     ctx->tune.syrk_i8 = saved;
     return st;
-}
+} GRM_CATCH_STATUS
 
 // ---------------------------------------------------------------------------------------------------------------
 // loci-split (K-split) multi-GPU support: every GPU contracts ITS loci over ALL upper-triangular tiles and writes raw
@@ -1081,11 +1081,11 @@ int32_t grm_packed_plan(grm_cuda_ctx *ctx, int64_t n, int32_t world, int32_t wav
     return get_packed_plan_impl(ctx, n, world, waves, out);
 }
 
-extern "C" int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world) {
+extern "C" int64_t grm_cuda_packed_tiles_max(int64_t n, int32_t world) try {
     if (n < 1 || world < 1) return -1;
     const int64_t T = (n + GRM_TILE - 1) / GRM_TILE;
     return (T * (T + 1) / 2 + world - 1) / world;
-}
+} GRM_CATCH_I64
 
 // one wave of the K-split contraction (waves = 1, wave = 0: everything)
 int32_t grm_syrk_i8_packed_wave(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc, int32_t world,
@@ -1136,9 +1136,9 @@ int32_t grm_syrk_i8_packed_wave(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_
 }
 
 extern "C" int32_t grm_cuda_syrk_i8_packed(grm_cuda_ctx *ctx, const int8_t *d_codes, int64_t n, int64_t p, int64_t ldc,
-                                           int32_t world, int32_t *d_packed) {
+                                           int32_t world, int32_t *d_packed) try {
     return grm_syrk_i8_packed_wave(ctx, d_codes, n, p, ldc, world, 1, 0, d_packed);
-}
+} GRM_CATCH_STATUS
 
 namespace {
 __global__ void wave_gate_kernel(const uint32_t *counter, uint32_t target) {
@@ -1337,11 +1337,11 @@ int32_t grm_finalize_tiles_range(grm_cuda_ctx *ctx, const int32_t *d_reduced, in
 
 extern "C" int32_t grm_cuda_finalize_tiles(grm_cuda_ctx *ctx, const int32_t *d_reduced, int64_t n, double alpha,
                                            double beta, double gamma, double denom, const double *d_u, double *d_G,
-                                           int64_t ldg, int32_t rank, int32_t world) {
+                                           int64_t ldg, int32_t rank, int32_t world) try {
     if (!ctx) {
         grm_set_error("finalize_tiles: bad argument");
         return GRM_CUDA_ERR_BAD_ARGUMENT;
     }
     return grm_finalize_tiles_range(ctx, d_reduced, n, alpha, beta, gamma, denom, d_u, d_G, ldg, nullptr, rank, world, 0,
                                     INT32_MAX, ctx->stream);
-}
+} GRM_CATCH_STATUS
