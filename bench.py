@@ -235,6 +235,9 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = grm_b200.Context(local)
+    for kv in args.tune or []:  # experiments: per-context tuning knobs of the library, recorded in config
+        key, _, val = kv.partition("=")
+        ctx.set_tuning(key, int(val))
     if world > 1:
         GD.init_comm(ctx)  # the library's own communicator: every exchange step of the path runs inside the C call
     lib = ctx.lib
@@ -562,7 +565,7 @@ def run_b200(args, wl):
         "config": {"workload": wl["name"], "n": n, "p": p, "ploidy": ploidy, "function": wl["fn"],
                    "dosage_denominator": m, "path": "int8 tcgen05 SYRK + FP64 rank-1 epilogue" if kind == "dosage" else "FP64 DMMA SYRK",
                    "step": step_desc, "l2": "inputs larger than L2 (FP64 input and int8 codes >> 126 MB)",
-                   "parallelism": par, "macs_per_step": macs(n, p)},
+                   "parallelism": par, "macs_per_step": macs(n, p), **({"tune": list(args.tune)} if args.tune else {})},
         "clocks": clocks, "e2e": e2e if e2e is not None else ({"unavailable": e2e_skip} if e2e_skip else None),
         "gpu_launches": int(launches), "roofline": roofline, "roofline_pack": roofline_pack, "roofline_f64": roofline_f64,
         "verified": verified, "cpu_baseline": cpu, "stage_ms": stage_ms, "extras": extras or None,
@@ -842,6 +845,7 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also time the masked step and sweep the tile-band height (N = 1)")
     ap.add_argument("--no-f64", action="store_true", help="skip the FP64-mode slice (roofline_f64) of the default line")
     ap.add_argument("--no-libpeaks", action="store_true", help="skip the same-run cuBLASLt int8 / cuBLAS dgemm timings")
+    ap.add_argument("--tune", action="append", metavar="KEY=VALUE", help="set a tuning knob of the library for this run")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -120,6 +120,7 @@ SIGNATURES = {
                                    C.POINTER(Info)]),
     "grm_cuda_host_quantise": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i32, _vp, _i64, _i32, C.POINTER(C.c_uint32)]),
     "grm_cuda_host_detect": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i32, C.POINTER(_i32)]),
+    "grm_cuda_host_copy": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _vp, _i64, _i32, C.POINTER(C.c_uint32)]),
     "grm_cuda_host_simd": (C.c_char_p, []),
     "grm_cuda_host_tune": (_i32, [C.c_char_p, _i64]),
     "grm_cuda_host_lu_det": (_f64, [_vp, _vp, _i64]),

@@ -94,6 +94,8 @@ void grm_pool_run(GrmHostPool *pool, void (*fn)(void *, int, int), void *arg) {
     grm_pool_wait(pool);
 }
 
+static int simd_level();
+
 // ---------------------------------------------------------------------------------------------------------------
 // one cell: the same test as the device pack kernel (pack.cu): c = rn(m x) is a code iff double(c) == m x, 0 <= c <= m
 // ---------------------------------------------------------------------------------------------------------------
@@ -271,9 +273,61 @@ uint32_t grm_host_quantise(const double *payload, const uint8_t *sel, int float_
     return flags;
 }
 
+// One column of the FP64 ring, one pass: copy, missing -> NaN, flags.  The reference-facing semantics are those of the
+// scalar version below: a cell whose selector is not the Float64 tag is `missing` (its payload is never used); a
+// Float64 cell holding NaN is a NaN payload (with selectors) or the missing marker (plain double* input).
+template <bool NT>
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq"))) static uint32_t
+copy_col_avx512_impl(const double *x, const uint8_t *s, int tag, int64_t n, double *out, int pf) {
+    const __m512d vnan = _mm512_set1_pd(__builtin_nan(""));
+    const __m128i vtag = _mm_set1_epi8(static_cast<char>(tag));
+    unsigned any_miss = 0, any_nan = 0;
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        if (pf) _mm_prefetch(reinterpret_cast<const char *>(x + i) + pf, _MM_HINT_T2);
+        const __m512d v = _mm512_loadu_pd(x + i);
+        __mmask8 is_float = 0xFF;
+        if (s) is_float = static_cast<__mmask8>(_mm_cmpeq_epi8_mask(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(s + i)), vtag));
+        any_nan |= static_cast<unsigned>(_mm512_cmp_pd_mask(v, v, _CMP_UNORD_Q) & is_float);
+        any_miss |= static_cast<unsigned>(static_cast<__mmask8>(~is_float));
+        const __m512d w = _mm512_mask_mov_pd(vnan, is_float, v);
+        if (NT) _mm512_stream_pd(out + i, w);  // out + i is 64-byte aligned
+        else _mm512_storeu_pd(out + i, w);
+    }
+    for (; i < n; ++i) {
+        const bool f = !s || s[i] == tag;
+        const double v = x[i];
+        if (!f) {
+            out[i] = __builtin_nan("");
+            any_miss = 1;
+        } else {
+            out[i] = v;
+            if (v != v) any_nan = 1;
+        }
+    }
+    if (NT) _mm_sfence();  // the column is complete before its unit is reported done
+    uint32_t flags = 0;
+    if (s) flags = (any_miss ? GRM_HF_MISSING : 0u) | (any_nan ? GRM_HF_NAN_PAYLOAD : 0u);
+    else if (any_nan) flags = GRM_HF_MISSING;
+    return flags;
+}
+
 uint32_t grm_host_copy(const double *payload, const uint8_t *sel, int float_tag, int64_t n, int64_t lda, int64_t k0,
                        int64_t k1, double *out, int64_t ldo) {
     uint32_t flags = 0;
+    if (simd_level() == 2) {
+        // one pass per column: the source is read once, the ring slot written once — with streaming stores when the
+        // row of the slot is 64-byte aligned (the copy engine reads it next, this core never does)
+        const int pf = g_pf_dist;
+        for (int64_t k = k0; k < k1; ++k) {
+            const double *x = payload + k * lda;
+            const uint8_t *s = sel ? sel + k * lda : nullptr;
+            double *o = out + (k - k0) * ldo;
+            if (g_nt_store && (reinterpret_cast<uintptr_t>(o) & 63) == 0) flags |= copy_col_avx512_impl<true>(x, s, float_tag, n, o, pf);
+            else flags |= copy_col_avx512_impl<false>(x, s, float_tag, n, o, pf);
+        }
+        return flags;
+    }
     const double nan = __builtin_nan("");
     for (int64_t k = k0; k < k1; ++k) {
         const double *x = payload + k * lda;

@@ -190,7 +190,11 @@ struct Feeder {
         ld = kind == RING_I8 ? (n + 3) / 4 * 4 : (n + 1) / 2 * 2;
         int64_t ch = want_chunk;
         if (ch <= 0) {
-            const int64_t slot_mb = ctx->tune.ring_mb > 0 ? ctx->tune.ring_mb : (kind == RING_I8 ? 32 : 64);
+            // FP64 chunks feed one SYRK launch each, with a fixed cost of ~0.8 ms per launch (column means, centring, the
+            // read-modify-write of G): at C4's n = 10,000 a 64 MiB slot is 838 loci = 3.5 ms per chunk, a 256 MiB slot
+            // brought the end-to-end time from 4.22 s to 3.47 s against 3.28 s for the device-resident step
+            // (profiles/bench_r2_c4_n1*.json).  The int8 chunks only feed the transpose: 32 MiB keeps the ring short.
+            const int64_t slot_mb = ctx->tune.ring_mb > 0 ? ctx->tune.ring_mb : (kind == RING_I8 ? 32 : 256);
             ch = (slot_mb << 20) / (ld * static_cast<int64_t>(elt));
         }
         ch = std::max<int64_t>(128, ch / 128 * 128);
@@ -1326,6 +1330,29 @@ extern "C" int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *
     auto work = [&](int t) {
         const int64_t a = p * t / nt, b = p * (t + 1) / nt;
         if (a < b) fl[t] = grm_host_quantise(payload, selectors, float_tag, n, lda, a, b, m, codes + a * ldo, ldo);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    uint32_t f = 0;
+    for (uint32_t v : fl) f |= v;
+    if (flags) *flags = f;
+    return GRM_CUDA_OK;
+} GRM_CATCH_STATUS
+
+extern "C" int32_t grm_cuda_host_copy(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
+                                      int64_t lda, double *out, int64_t ldo, int32_t threads, uint32_t *flags) try {
+    if (!payload || !out || n < 1 || p < 1 || lda < n || ldo < n) {
+        grm_set_error("host_copy: bad argument");
+        return GRM_CUDA_ERR_BAD_ARGUMENT;
+    }
+    int nt = threads > 0 ? threads : host_cpus();
+    nt = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 256), p)));
+    std::vector<uint32_t> fl(nt, 0u);
+    auto work = [&](int t) {
+        const int64_t a = p * t / nt, b = p * (t + 1) / nt;
+        if (a < b) fl[t] = grm_host_copy(payload, selectors, float_tag, n, lda, a, b, out + a * ldo, ldo);
     };
     std::vector<std::thread> th;
     for (int t = 1; t < nt; ++t) th.emplace_back(work, t);

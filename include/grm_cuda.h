@@ -233,6 +233,11 @@ int32_t grm_cuda_host_quantise(const double *payload, const uint8_t *selectors, 
                                int64_t lda, int32_t m, int8_t *codes, int64_t ldo, int32_t threads, uint32_t *flags);
 int32_t grm_cuda_host_detect(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
                              int64_t lda, int64_t max_cells, int32_t ignore_missing, int32_t *m_out);
+/* grm_cuda_host_copy: the FP64 counterpart the ingest runs for continuous data (same arguments): out[i + k*ldo] = the
+ * cell as Float64, `missing` -> NaN; *flags = OR of 1 (missing: a selector that is not float_tag, or NaN in a plain
+ * double* input) and 16 (a Float64 cell holding NaN). */
+int32_t grm_cuda_host_copy(const double *payload, const uint8_t *selectors, int32_t float_tag, int64_t n, int64_t p,
+                           int64_t lda, double *out, int64_t ldo, int32_t threads, uint32_t *flags);
 const char *grm_cuda_host_simd(void);
 /* Process-wide knobs of the host quantiser (memory-system tuning only, results never change; a negative value restores
  * the default): "prefetch" = software prefetch distance in bytes (0 = off, default 16384), "prefetch_hint" = cache level

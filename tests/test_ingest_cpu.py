@@ -98,6 +98,45 @@ def test_host_quantiser_prefetch_hint_and_streaming_stores_change_nothing(hint, 
     assert lib.grm_cuda_host_tune(b"no_such_knob", 1) != _lib.OK
 
 
+@pytest.mark.parametrize("n", [1, 7, 8, 64, 1000, 1001])
+@pytest.mark.parametrize("with_sel", [False, True])
+@pytest.mark.parametrize("stream", [0, 1])
+def test_host_copy_of_continuous_data(n, with_sel, stream):
+    """grm_cuda_host_copy — what the worker threads run for continuous input (FP64 ring): every cell as Float64, `missing`
+    -> NaN whatever its payload, flags as the reference-facing statuses need them; streaming stores change nothing, also
+    with rows of the output that are not 64-byte aligned."""
+    lib = _lib.load()
+    rng = np.random.default_rng(n + 7)
+    p = 23
+    A = np.asfortranarray(rng.random((n, p)))
+    sel = np.ones((n, p), dtype=np.uint8, order="F") if with_sel else None
+    want_flags = 0
+    if n >= 7:
+        A[3, 5] = np.nan   # a Float64 cell holding NaN
+        want_flags |= F_NAN_PAYLOAD if with_sel else F_MISSING
+        if with_sel:
+            sel[n - 1, 0] = sel[0, p - 1] = sel[4, 11] = 0
+            A[4, 11] = np.nan  # garbage under a missing selector must not count as a NaN payload
+            want_flags |= F_MISSING
+    want = A.copy()
+    if with_sel:
+        want[sel != 1] = np.nan
+    try:
+        assert lib.grm_cuda_host_tune(b"stream_stores", stream) == _lib.OK
+        for ldo in (n, (n + 7) // 8 * 8 + 8):
+            for threads in (1, 3):
+                out = np.full((p, ldo), -7.0)
+                flags = C.c_uint32(0)
+                st = lib.grm_cuda_host_copy(A.ctypes.data, sel.ctypes.data if with_sel else None, 1, n, p, n, out.ctypes.data, ldo,
+                                            threads, C.byref(flags))
+                assert st == _lib.OK and flags.value == want_flags
+                got = out[:, :n].T
+                assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+                assert np.all(out[:, n:] == -7.0)  # padding untouched
+    finally:
+        lib.grm_cuda_host_tune(b"stream_stores", -1)
+
+
 def test_host_quantiser_other_float_tag_and_simd_level():
     lib = _lib.load()
     assert lib.grm_cuda_host_simd() in (b"avx512", b"avx2", b"scalar")
